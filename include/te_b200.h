@@ -1,0 +1,157 @@
+/*
+ * te_b200.h — C ABI of libte_b200.so, the B200 (sm_100a) kernels behind TransEditor's
+ * generator / discriminator hot path.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; every data pointer is a DEVICE pointer unless noted;
+ *   - nothing allocates, nothing synchronises, everything is enqueued on `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *   - returns 0 on success, a negative te_status otherwise; te_last_error() gives the
+ *     message of the last failure on the calling thread;
+ *   - stateless / re-entrant apart from a per-process cache of immutable TMA descriptors.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the
+ * TransEditor tree).  INTEGRATION.md shows the binding a reference maintainer adds.
+ */
+#ifndef TE_B200_H
+#define TE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum { TE_F32 = 0, TE_BF16 = 1, TE_F16 = 2, TE_F64 = 3 } te_dtype;
+
+typedef enum {
+  TE_OK = 0,
+  TE_ERR_INVALID = -1,     /* bad argument (shape, dtype, alignment, null pointer) */
+  TE_ERR_UNSUPPORTED = -2, /* valid request this build has no kernel for */
+  TE_ERR_CUDA = -3         /* a CUDA runtime / driver call failed; see te_last_error() */
+} te_status;
+
+/* Library version (major*1000 + minor) and last error text of the calling thread. */
+int te_version(void);
+const char* te_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * fused bias + activation.
+ * Replaces: fused.fused_bias_act(input, bias, refer, act, grad, alpha, scale)
+ *           utils/op/fused_bias_act.cpp:11-17 -> fused_bias_act_kernel.cu:52-99 (kernel :18-49).
+ *   x' = x + bias[(i / step_b) % size_b]            (bias == NULL: no bias)
+ *   act*10+grad: 10,11 -> y = x'        12,32 -> y = 0
+ *                30    -> y = x' > 0 ? x' : alpha*x'
+ *                31    -> y = ref > 0 ? x' : alpha*x'   (ref == NULL reads as 0, as the reference)
+ *   out = y * scale
+ * `n` elements, contiguous.  NCHW: step_b = H*W, size_b = C.  Channels-last: step_b = 1.
+ * dtypes: f32, bf16, f16, f64 (bias/ref same dtype as x).
+ */
+int te_fused_bias_act(void* out, const void* x, const void* bias, const void* ref, int act,
+                      int grad, float alpha, float scale, int64_t n, int64_t step_b,
+                      int64_t size_b, int dtype, void* stream);
+
+/* Backward of the above in ONE pass (replaces FusedLeakyReLUFunctionBackward.forward,
+ * utils/op/fused_act.py:20-38, which runs fused_bias_act(grad=1) and then a separate
+ * `.sum()` reduction that re-reads the tensor):
+ *   grad_in = (ref > 0 ? g : alpha*g) * scale ;  grad_bias[c] += sum of grad_in over channel c.
+ * grad_bias is FLOAT32 [size_b] (FLOAT64 when dtype is TE_F64) and must be zeroed by the caller
+ * (accumulated with atomics); pass NULL to skip the reduction. */
+int te_fused_bias_act_bwd(void* grad_in, void* grad_bias, const void* g, const void* ref,
+                          float alpha, float scale, int64_t n, int64_t step_b, int64_t size_b,
+                          int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * upfirdn2d: zero-insert upsample -> pad/crop -> 2-D FIR (true convolution) -> decimate.
+ * Replaces: upfirdn2d.upfirdn2d(input[major,in_h,in_w,minor], kernel[kh,kw], up_x, up_y,
+ *           down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1)
+ *           utils/op/upfirdn2d.cpp:12-19 -> upfirdn2d_kernel.cu:140-272 (kernel :52-137).
+ * out[major,out_h,out_w,minor], out_h = (in_h*up_y + pad_y0 + pad_y1 - kh)/down_y + 1 (:167-168).
+ * `fir` is FLOAT32 [kh,kw] on the device, kh,kw <= 16.  Unlike the reference, EVERY parameter
+ * combination is computed (the reference launches nothing for unmatched modes, :172,216).
+ * NCHW tensors: major = N*C, minor = 1.  Channels-last: major = N, minor = C.
+ * dtypes: f32, bf16, f16, f64.
+ */
+int te_upfirdn2d(void* out, const void* in, const float* fir, int64_t major, int in_h, int in_w,
+                 int minor, int kh, int kw, int up_x, int up_y, int down_x, int down_y, int pad_x0,
+                 int pad_x1, int pad_y0, int pad_y1, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Gather convolution (SIMT, f32/f64, NCHW) — the full-precision parity engine.
+ * Replaces the F.conv2d / F.conv_transpose2d(groups=batch) calls of ModulatedConv2d
+ * (model_spatial_query.py:318,327,333) and EqualConv2d (:177-183) WITHOUT materialising
+ * per-sample weights: conv(x, W*s*d) == d * conv(x*s, W)  (SURVEY.md App. A.5).
+ *
+ *   y[b,o,oy,ox] = act( out_scale[b,o] * SUM_{i,ky,kx} W(o,i,ky,kx) * in_scale[b,i] * x[b,i,iy,ix]
+ *                       + noise_w[0]*noise[b*noise_bstride + oy*wout + ox] + bias[o] )
+ *   ty = oy*down + ky - pad_y ; tap valid iff ty >= 0, ty % up == 0, iy = ty/up < hin (same for x)
+ *   W(o,i,ky,kx) = w[o*w_so + i*w_si + (flip ? (kh-1-ky)*kw + (kw-1-kx) : ky*kw + kx)]
+ *   act: 0 = identity, 1 = leaky_relu(0.2)*sqrt(2) (FusedLeakyReLU, utils/op/fused_act.py:72-90)
+ * in_scale, out_scale, bias, noise may be NULL.  Covers conv2d (up=1, down=stride), conv_transpose2d
+ * (up=stride, flip=1, pad=k-1-p) and every data-gradient of those (swap up/down, swap w_so/w_si,
+ * toggle flip, pad -> k-1-pad).
+ */
+typedef struct {
+  int batch, cin, hin, win, cout, hout, wout, kh, kw;
+  int up, down, pad_y, pad_x, flip;
+  int64_t w_so, w_si; /* element strides of the weight's output / input channel index */
+  int act;
+  int64_t noise_bstride; /* 0: one noise map shared by the batch */
+} te_conv_geom;
+
+int te_conv2d_simt(void* y, const void* x, const void* w, const void* in_scale,
+                   const void* out_scale, const void* bias, const void* noise, const void* noise_w,
+                   const te_conv_geom* g, int dtype, void* stream);
+
+/* Weight gradient of the gather convolution (same geometry struct; act/noise ignored):
+ *   gw(o,i,ky,kx) += SUM_{b,oy,ox} out_scale[b,o]*gy[b,o,oy,ox] * in_scale[b,i]*x[b,i,iy,ix]
+ * written through the same (w_so, w_si, flip) addressing; gw must be zeroed by the caller
+ * (split-K accumulation with atomics).  Replaces autograd's conv weight-gradient of the calls above. */
+int te_conv2d_wgrad_simt(void* gw, const void* x, const void* gy, const void* in_scale,
+                         const void* out_scale, const te_conv_geom* g, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused Adam + EMA over flat parameter buffers (f32).
+ * Replaces: torch.optim.Adam.step (train_spatial_query.py:464-473 use) and the per-parameter
+ * EMA loop `accumulate` (train_spatial_query.py:56-61), one launch instead of ~650.
+ *   m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g
+ *   p -= lr * (m/(1-b1^t)) / (sqrt(v/(1-b2^t)) + eps)          (torch.optim.Adam semantics)
+ *   ema = ema_decay*ema + (1-ema_decay)*p    (ema == NULL: skipped)
+ *   grad_scale multiplies g first (1/world_size after a sum-all-reduce).
+ */
+int te_adam_ema(float* p, const float* g, float* m, float* v, float* ema, int64_t n, float lr,
+                float beta1, float beta2, float eps, int step, float ema_decay, float grad_scale,
+                void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Tensor-core (tcgen05 + TMA + TMEM) implicit-GEMM convolution, bf16 operands / f32 accumulate,
+ * channels-last.  The speed path of ModulatedConv2d / EqualConv2d (same reference lines as
+ * te_conv2d_simt).  See DESIGN.md §kernels.
+ *   x  [B, Hin, Win, Cin] bf16 ; w [kh*kw, Cout, Cin] bf16 (tap-major, K contiguous)
+ *   y  [B, Hout, Wout, Cout] bf16
+ *   y = act( out_scale[b,o] * conv(x, w)[b,oy,ox,o] + bias[o] ), stride 1, pad = k/2
+ * in_scale is NOT applied here (the modulation is folded into x by the caller's producer
+ * kernel or into per-sample weights: w_bstride != 0 selects w + b*w_bstride for sample b).
+ * Requirements: Cin % 64 == 0, Cout % 64 == 0.
+ */
+int te_conv2d_tc(void* y, const void* x, const void* w, const float* out_scale, const float* bias,
+                 int batch, int hin, int win, int cin, int cout, int kh, int kw, int act,
+                 int64_t w_bstride, void* stream);
+
+/* Self-test of the tcgen05 GEMM core: D[M,N] (f32) = A[M,K] (bf16, K-major) * B[N,K]^T (bf16). */
+int te_gemm_tc_selftest(float* d, const void* a, const void* b, int m, int n, int k, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Cross-attention core of the dual-space transformer (model_spatial_query.py:888-894):
+ *   q [B,M,128] (from P), k,v [B,L,128] (from Z), 4 heads x 32, scale = 128^-0.5, M = L = 16
+ *   sim[b,h,m,l] = softmax_l(q.k * scale) ; o[b,h,c,m] = SUM_l sim*v ; out = o viewed [B,128,L]
+ *   permuted to [B,L,128] exactly as `sv.reshape(N, planes, L).permute(0, 2, 1)` (:894).
+ * f32.  sim_out (may be NULL) receives the [B,4,M,L] similarity the reference returns.
+ */
+int te_attn_core(float* out, float* sim_out, const float* q, const float* k, const float* v,
+                 int batch, int tokens, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TE_B200_H */

@@ -1,0 +1,140 @@
+"""CPU emulation of the libte_b200 entry points, written from the contract in
+include/te_b200.h with plain torch ops.  TEST INFRASTRUCTURE ONLY (used by the
+`-m "not gpu"` host-logic tests through the `cpu_emulation` fixture)."""
+import torch
+import torch.nn.functional as F
+
+from transeditor_b200 import lib
+
+
+def _store(out, flat):
+    """Write logical-flat storage order values into `out` (which may be channels_last)."""
+    if out.dim() == 4 and not out.is_contiguous():
+        n, c, h, w = out.shape
+        out.copy_(flat.reshape(n, h, w, c).permute(0, 3, 1, 2).to(out.dtype))
+    else:
+        out.copy_(flat.reshape(out.shape).to(out.dtype))
+
+
+def _storage_flat(t):
+    if t.dim() == 4 and not t.is_contiguous():
+        return t.permute(0, 2, 3, 1).reshape(-1)
+    return t.reshape(-1)
+
+
+def fused_bias_act(out, x, bias, ref, act, grad, alpha, scale, step_b, size_b):
+    xs = _storage_flat(x)
+    rs = _storage_flat(ref) if ref is not None else None
+    flat = xs.to(torch.float64)
+    if bias is not None:
+        idx = (torch.arange(flat.numel()) // step_b) % size_b
+        flat = flat + bias.to(torch.float64)[idx]
+    r = rs.to(torch.float64) if rs is not None else torch.zeros_like(flat)
+    code = act * 10 + grad
+    if code in (12, 32):
+        y = torch.zeros_like(flat)
+    elif code == 30:
+        y = torch.where(flat > 0, flat, flat * alpha)
+    elif code == 31:
+        y = torch.where(r > 0, flat, flat * alpha)
+    else:
+        y = flat
+    _store(out, y * scale)
+
+
+def fused_bias_act_bwd(grad_in, grad_bias, g, ref, alpha, scale, step_b, size_b):
+    gs = _storage_flat(g).to(torch.float64)
+    rs = _storage_flat(ref).to(torch.float64)
+    y = torch.where(rs > 0, gs, gs * alpha) * scale
+    _store(grad_in, y)
+    if grad_bias is not None:
+        idx = (torch.arange(y.numel()) // step_b) % size_b
+        grad_bias.index_add_(0, idx, y.to(grad_bias.dtype))
+
+
+def upfirdn2d(out, x, fir, major, in_h, in_w, minor, up_x, up_y, down_x, down_y, px0, px1, py0, py1):
+    from oracle.ops_cpu import upfirdn2d_planes
+    xs = _storage_flat(x).reshape(major, in_h, in_w, minor).permute(0, 3, 1, 2).reshape(major * minor, in_h, in_w)
+    y = upfirdn2d_planes(xs.to(torch.float64), fir.to(torch.float64), up_x, up_y, down_x, down_y, px0, px1, py0, py1)
+    oh, ow = y.shape[1], y.shape[2]
+    y = y.reshape(major, minor, oh, ow).permute(0, 2, 3, 1).reshape(-1)
+    _store(out, y)
+
+
+def _logical_weight(w, g):
+    """[cout, cin, kh, kw] view of the stored weight per te_conv_geom (w_so, w_si, flip)."""
+    flat = w.reshape(-1)
+    kk = g.kh * g.kw
+    o = torch.arange(g.cout).view(-1, 1, 1)
+    i = torch.arange(g.cin).view(1, -1, 1)
+    t = torch.arange(kk).view(1, 1, -1)
+    tap = (kk - 1 - t) if g.flip else t
+    idx = o * g.w_so + i * g.w_si + tap
+    return flat[idx].reshape(g.cout, g.cin, g.kh, g.kw), idx
+
+
+def _gather_conv(x, wl, g):
+    b, c, h, w = x.shape
+    xz = x.new_zeros(b, c, (h - 1) * g.up + 1, (w - 1) * g.up + 1)
+    xz[:, :, ::g.up, ::g.up] = x
+    need_h = (g.hout - 1) * g.down + g.kh
+    need_w = (g.wout - 1) * g.down + g.kw
+    pr_y = need_h - g.pad_y - xz.shape[2]
+    pr_x = need_w - g.pad_x - xz.shape[3]
+    xp = F.pad(xz, [g.pad_x, pr_x, g.pad_y, pr_y])  # negative values crop
+    return F.conv2d(xp, wl, stride=g.down)
+
+
+def conv2d_simt(y, x, w, in_scale, out_scale, bias, noise, noise_w, geom):
+    g = geom
+    wl, _ = _logical_weight(w, g)
+    xin = x if in_scale is None else x * in_scale.view(g.batch, g.cin, 1, 1)
+    v = _gather_conv(xin, wl, g)
+    if out_scale is not None:
+        v = v * out_scale.view(g.batch, g.cout, 1, 1)
+    if noise is not None:
+        nz = noise.reshape(-1, 1, g.hout, g.wout)
+        v = v + noise_w.reshape(()) * nz
+    if bias is not None:
+        v = v + bias.view(1, -1, 1, 1)
+    if g.act == 1:
+        v = F.leaky_relu(v, 0.2) * (2 ** 0.5)
+    y.copy_(v)
+
+
+def conv2d_wgrad_simt(gw, x, gy, in_scale, out_scale, geom):
+    g = geom
+    wl, idx = _logical_weight(torch.zeros_like(gw), g)
+    wl = wl.clone().requires_grad_(True)
+    xin = x if in_scale is None else x * in_scale.view(g.batch, g.cin, 1, 1)
+    gyy = gy if out_scale is None else gy * out_scale.view(g.batch, g.cout, 1, 1)
+    with torch.enable_grad():
+        v = _gather_conv(xin.detach(), wl, g)
+        (gl,) = torch.autograd.grad(v, wl, gyy.detach())
+    gw.reshape(-1).index_add_(0, idx.reshape(-1), gl.reshape(-1))
+
+
+def attn_core(out, sim, q, k, v, batch, tokens):
+    from transeditor_b200.op import attn_core_reference
+    o, s = attn_core_reference(q, k, v)
+    out.copy_(o)
+    if sim is not None:
+        sim.copy_(s)
+
+
+def adam_ema(p, g, m, v, ema, lr, beta1, beta2, eps, step, ema_decay, grad_scale):
+    gr = g * grad_scale
+    m.mul_(beta1).add_(gr, alpha=1 - beta1)
+    v.mul_(beta2).addcmul_(gr, gr, value=1 - beta2)
+    bc1 = 1 - beta1 ** step
+    bc2 = 1 - beta2 ** step
+    p.addcdiv_(m, (v.sqrt() / (bc2 ** 0.5)) + eps, value=-lr / bc1)
+    if ema is not None:
+        ema.mul_(ema_decay).add_(p, alpha=1 - ema_decay)
+
+
+def install(monkeypatch):
+    monkeypatch.setattr(lib, "require_cuda", lambda *a: None)
+    for name in ("fused_bias_act", "fused_bias_act_bwd", "upfirdn2d", "conv2d_simt",
+                 "conv2d_wgrad_simt", "attn_core", "adam_ema"):
+        monkeypatch.setattr(lib, name, globals()[name])

@@ -1,0 +1,200 @@
+// upfirdn2d: zero-insert upsample -> pad/crop -> 2-D FIR (true convolution) -> decimate.
+// Semantics follow the reference operator (utils/op/upfirdn2d_kernel.cu:52-137,167-168) — restated.
+//
+// Two kernels:
+//   * upfirdn2d_generic: any (up, down, pad, FIR <= 16x16, minor); one thread per output element
+//     (minor fastest, so NHWC reads vectorise over channels and NCHW reads coalesce over x).
+//     Never leaves the output uninitialised (the reference launches nothing for unmatched modes).
+//   * fir_planes_tiled:  the hot case — up = down = 1, minor = 1 (NCHW planes), FIR <= 4x4:
+//     every Blur of the generator / discriminator (model_spatial_query.py:137-153).  HBM-bound:
+//     input tile staged once in shared memory (zero-filled halo = the padding), each thread
+//     produces a 4x4 register block from a 7x7 patch (3 shared-memory words per output),
+//     16-byte stores.  TMA tiled loads are not usable here: row pitches such as 257*4 B are not
+//     16-byte multiples (cuTensorMapEncodeTiled requirement), so staging uses coalesced LDG.
+#include "common.cuh"
+
+namespace te {
+
+struct UpfirdnParams {
+  int64_t major;
+  int in_h, in_w, minor, kh, kw;
+  int up_x, up_y, down_x, down_y, pad_x0, pad_y0;
+  int out_h, out_w;
+};
+
+__device__ __forceinline__ int floordiv(int a, int b) {
+  int q = a / b;
+  return (q * b > a) ? q - 1 : q;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+upfirdn2d_generic(T* __restrict__ out, const T* __restrict__ in, const float* __restrict__ fir,
+                  UpfirdnParams p, int64_t total) {
+  using A = typename Acc<T>::type;
+  __shared__ float sk[256];  // flipped taps: sk[ky][kx] = fir[kh-1-ky][kw-1-kx]
+  for (int t = threadIdx.x; t < p.kh * p.kw; t += blockDim.x) {
+    int ky = t / p.kw, kx = t - ky * p.kw;
+    sk[t] = fir[(p.kh - 1 - ky) * p.kw + (p.kw - 1 - kx)];
+  }
+  __syncthreads();
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    int64_t r = idx;
+    const int mi = int(r % p.minor); r /= p.minor;
+    const int ox = int(r % p.out_w); r /= p.out_w;
+    const int oy = int(r % p.out_h); r /= p.out_h;
+    const int64_t mj = r;
+    // position in the zero-inserted, padded grid of the first tap
+    const int mid_x = ox * p.down_x + p.up_x - 1 - p.pad_x0;
+    const int mid_y = oy * p.down_y + p.up_y - 1 - p.pad_y0;
+    const int in_x0 = floordiv(mid_x, p.up_x);
+    const int in_y0 = floordiv(mid_y, p.up_y);
+    const int tap_x0 = (in_x0 + 1) * p.up_x - mid_x - 1;
+    const int tap_y0 = (in_y0 + 1) * p.up_y - mid_y - 1;
+    A acc = A(0);
+    for (int ty = tap_y0, iy = in_y0; ty < p.kh; ty += p.up_y, ++iy) {
+      if (iy < 0 || iy >= p.in_h) continue;
+      const T* row = in + ((mj * p.in_h + iy) * int64_t(p.in_w)) * p.minor + mi;
+      for (int tx = tap_x0, ix = in_x0; tx < p.kw; tx += p.up_x, ++ix) {
+        if (ix < 0 || ix >= p.in_w) continue;
+        acc += to_acc(row[int64_t(ix) * p.minor]) * A(sk[ty * p.kw + tx]);
+      }
+    }
+    out[idx] = from_acc<T, A>(acc);
+  }
+}
+
+// ---- hot case: planes, up = down = 1, FIR zero-extended to 4x4 --------------------------------
+constexpr int FT_W = 128;           // output tile width  (32 threads x 4)
+constexpr int FT_H = 32;            // output tile height ( 8 threads x 4)
+constexpr int FT_IW = FT_W + 3;     // input tile width incl. halo
+constexpr int FT_IH = FT_H + 3;
+constexpr int FT_PITCH = FT_W + 4;  // shared row pitch (multiple of 4 words -> 16-byte LDS)
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+fir_planes_tiled(T* __restrict__ out, const T* __restrict__ in, const float* __restrict__ fir,
+                 UpfirdnParams p, int tiles_x, int tiles_y, int64_t n_tiles) {
+  using A = typename Acc<T>::type;
+  __shared__ __align__(16) A sx[FT_IH][FT_PITCH];
+  __shared__ A sk[4][4];
+  if (threadIdx.x < 16) {
+    int ky = threadIdx.x >> 2, kx = threadIdx.x & 3;
+    // flipped taps, zero-extended on the high side when kh/kw < 4
+    sk[ky][kx] = (ky < p.kh && kx < p.kw) ? A(fir[(p.kh - 1 - ky) * p.kw + (p.kw - 1 - kx)]) : A(0);
+  }
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const bool vec_store = (p.out_w % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
+                         (sizeof(T) * 4 <= 16);
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    int64_t r = tile;
+    const int tcol = int(r % tiles_x); r /= tiles_x;
+    const int trow = int(r % tiles_y); r /= tiles_y;
+    const int64_t plane = r;
+    const int ox0 = tcol * FT_W, oy0 = trow * FT_H;
+    const int ix0 = ox0 - p.pad_x0, iy0 = oy0 - p.pad_y0;
+    const T* src = in + plane * int64_t(p.in_h) * p.in_w;
+    __syncthreads();  // previous tile fully consumed (also orders the sk writes)
+    for (int e = threadIdx.x; e < FT_IH * FT_IW; e += 256) {
+      const int ry = e / FT_IW, rx = e - ry * FT_IW;
+      const int iy = iy0 + ry, ix = ix0 + rx;
+      A v = A(0);
+      if (iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w) v = to_acc(src[int64_t(iy) * p.in_w + ix]);
+      sx[ry][rx] = v;
+    }
+    __syncthreads();
+    A acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = A(0);
+#pragma unroll
+    for (int ry = 0; ry < 7; ++ry) {
+      A rowv[8];
+      const A* rp = &sx[ty * 4 + ry][tx * 4];
+#pragma unroll
+      for (int j = 0; j < 7; ++j) rowv[j] = rp[j];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int ky = ry - a;  // out row a uses input row a+ky
+        if (ky >= 0 && ky < 4) {
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int kx = 0; kx < 4; ++kx) acc[a][b] += rowv[b + kx] * sk[ky][kx];
+        }
+      }
+    }
+    T* dst = out + plane * int64_t(p.out_h) * p.out_w;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int oy = oy0 + ty * 4 + a;
+      const int ox = ox0 + tx * 4;
+      if (oy >= p.out_h || ox >= p.out_w) continue;
+      T* q = dst + int64_t(oy) * p.out_w + ox;
+      if (vec_store && ox + 3 < p.out_w) {
+        struct alignas(sizeof(T) * 4) V4 { T v[4]; } o;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) o.v[b] = from_acc<T, A>(acc[a][b]);
+        *reinterpret_cast<V4*>(q) = o;
+      } else {
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          if (ox + b < p.out_w) q[b] = from_acc<T, A>(acc[a][b]);
+      }
+    }
+  }
+}
+
+template <typename T>
+static int upfirdn2d_typed(void* out_, const void* in_, const float* fir, const UpfirdnParams& p,
+                           cudaStream_t st) {
+  T* out = static_cast<T*>(out_);
+  const T* in = static_cast<const T*>(in_);
+  const int64_t total = p.major * p.out_h * int64_t(p.out_w) * p.minor;
+  if (total == 0) return TE_OK;
+  const bool hot = p.up_x == 1 && p.up_y == 1 && p.down_x == 1 && p.down_y == 1 && p.minor == 1 &&
+                   p.kh <= 4 && p.kw <= 4 && p.out_w >= 32 && p.out_h >= 8 && sizeof(T) <= 4;
+  if (hot) {
+    const int tiles_x = (p.out_w + FT_W - 1) / FT_W;
+    const int tiles_y = (p.out_h + FT_H - 1) / FT_H;
+    const int64_t n_tiles = p.major * tiles_x * tiles_y;
+    int64_t blocks = n_tiles < int64_t(kNumSMs) * 8 ? n_tiles : int64_t(kNumSMs) * 8;
+    fir_planes_tiled<T><<<unsigned(blocks), 256, 0, st>>>(out, in, fir, p, tiles_x, tiles_y, n_tiles);
+  } else {
+    upfirdn2d_generic<T><<<grid_for(total, 256, 32), 256, 0, st>>>(out, in, fir, p, total);
+  }
+  TE_CHECK_LAUNCH();
+  return TE_OK;
+}
+
+}  // namespace te
+
+extern "C" int te_upfirdn2d(void* out, const void* in, const float* fir, int64_t major, int in_h,
+                            int in_w, int minor, int kh, int kw, int up_x, int up_y, int down_x,
+                            int down_y, int pad_x0, int pad_x1, int pad_y0, int pad_y1, int dtype,
+                            void* stream) {
+  using namespace te;
+  TE_CHECK_ARG(out && in && fir, "upfirdn2d: null pointer");
+  TE_CHECK_ARG(major >= 0 && in_h > 0 && in_w > 0 && minor > 0, "upfirdn2d: bad input shape");
+  TE_CHECK_ARG(kh >= 1 && kw >= 1 && kh <= 16 && kw <= 16, "upfirdn2d: FIR must be 1..16 taps per axis");
+  TE_CHECK_ARG(up_x >= 1 && up_y >= 1 && down_x >= 1 && down_y >= 1, "upfirdn2d: up/down must be >= 1");
+  UpfirdnParams p;
+  p.major = major; p.in_h = in_h; p.in_w = in_w; p.minor = minor; p.kh = kh; p.kw = kw;
+  p.up_x = up_x; p.up_y = up_y; p.down_x = down_x; p.down_y = down_y;
+  p.pad_x0 = pad_x0; p.pad_y0 = pad_y0;
+  // output size, utils/op/upfirdn2d_kernel.cu:167-168
+  p.out_h = (in_h * up_y + pad_y0 + pad_y1 - kh) / down_y + 1;
+  p.out_w = (in_w * up_x + pad_x0 + pad_x1 - kw) / down_x + 1;
+  TE_CHECK_ARG(p.out_h > 0 && p.out_w > 0, "upfirdn2d: empty output (%d x %d)", p.out_h, p.out_w);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (dtype) {
+    case TE_F32: return upfirdn2d_typed<float>(out, in, fir, p, st);
+    case TE_BF16: return upfirdn2d_typed<__nv_bfloat16>(out, in, fir, p, st);
+    case TE_F16: return upfirdn2d_typed<__half>(out, in, fir, p, st);
+    case TE_F64: return upfirdn2d_typed<double>(out, in, fir, p, st);
+  }
+  set_error("upfirdn2d: unknown dtype %d", dtype);
+  return TE_ERR_INVALID;
+}

@@ -1,0 +1,159 @@
+"""ctypes binding of libte_b200.so (the C ABI declared in include/te_b200.h).
+
+There is NO fallback: if the shared library is missing or a tensor is not on a CUDA
+device, these functions raise.  Tensors are passed as raw device pointers; kernels are
+enqueued on torch's current CUDA stream; outputs are allocated by the caller with
+torch.empty (PyTorch is plumbing here: memory, streams, autograd bookkeeping).
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libte_b200.so")
+
+TE_F32, TE_BF16, TE_F16, TE_F64 = 0, 1, 2, 3
+_DTYPES = {torch.float32: TE_F32, torch.bfloat16: TE_BF16, torch.float16: TE_F16,
+           torch.float64: TE_F64}
+
+
+class ConvGeom(ctypes.Structure):
+    """Mirror of te_conv_geom."""
+    _fields_ = [("batch", ctypes.c_int), ("cin", ctypes.c_int), ("hin", ctypes.c_int),
+                ("win", ctypes.c_int), ("cout", ctypes.c_int), ("hout", ctypes.c_int),
+                ("wout", ctypes.c_int), ("kh", ctypes.c_int), ("kw", ctypes.c_int),
+                ("up", ctypes.c_int), ("down", ctypes.c_int), ("pad_y", ctypes.c_int),
+                ("pad_x", ctypes.c_int), ("flip", ctypes.c_int),
+                ("w_so", ctypes.c_int64), ("w_si", ctypes.c_int64),
+                ("act", ctypes.c_int), ("noise_bstride", ctypes.c_int64)]
+
+
+_P, _I, _L, _F = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
+_SIGNATURES = {
+    "te_version": ([], _I),
+    "te_last_error": ([], ctypes.c_char_p),
+    "te_fused_bias_act": ([_P, _P, _P, _P, _I, _I, _F, _F, _L, _L, _L, _I, _P], _I),
+    "te_fused_bias_act_bwd": ([_P, _P, _P, _P, _F, _F, _L, _L, _L, _I, _P], _I),
+    "te_upfirdn2d": ([_P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P], _I),
+    "te_conv2d_simt": ([_P, _P, _P, _P, _P, _P, _P, _P, ctypes.POINTER(ConvGeom), _I, _P], _I),
+    "te_conv2d_wgrad_simt": ([_P, _P, _P, _P, _P, ctypes.POINTER(ConvGeom), _I, _P], _I),
+    "te_adam_ema": ([_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _F, _P], _I),
+    "te_conv2d_tc": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _L, _P], _I),
+    "te_gemm_tc_selftest": ([_P, _P, _P, _I, _I, _I, _P], _I),
+    "te_attn_core": ([_P, _P, _P, _P, _P, _I, _I, _P], _I),
+}
+
+_lib = None
+launch_count = 0  # number of te_* kernel launches issued through this binding (bench.py reads it)
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "transeditor_b200: %s is missing — run `python -m transeditor_b200.build` "
+            "(there is no CPU or PyTorch fallback for the hot path)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (argtypes, restype) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the build is stale
+        fn.argtypes = argtypes
+        fn.restype = restype
+    _lib = lib
+    return lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        msg = load().te_last_error().decode("utf-8", "replace")
+        raise RuntimeError("transeditor_b200.%s failed (status %d): %s" % (what, rc, msg))
+
+
+def dtype_code(t):
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise TypeError("transeditor_b200: unsupported dtype %s" % t.dtype)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("transeditor_b200: expected a CUDA tensor, got device '%s' "
+                               "(the hot path has no CPU fallback)" % t.device)
+
+
+def ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _count(n=1):
+    global launch_count
+    launch_count += n
+
+
+# ----------------------------------------------------------------------------- thin wrappers
+def fused_bias_act(out, x, bias, ref, act, grad, alpha, scale, step_b, size_b):
+    _check(load().te_fused_bias_act(ptr(out), ptr(x), ptr(bias), ptr(ref), act, grad, alpha, scale,
+                                    x.numel(), step_b, size_b, dtype_code(x), stream()),
+           "fused_bias_act")
+    _count()
+
+
+def fused_bias_act_bwd(grad_in, grad_bias, g, ref, alpha, scale, step_b, size_b):
+    _check(load().te_fused_bias_act_bwd(ptr(grad_in), ptr(grad_bias), ptr(g), ptr(ref), alpha, scale,
+                                        g.numel(), step_b, size_b, dtype_code(g), stream()),
+           "fused_bias_act_bwd")
+    _count()
+
+
+def upfirdn2d(out, x, fir, major, in_h, in_w, minor, up_x, up_y, down_x, down_y, px0, px1, py0, py1):
+    kh, kw = fir.shape
+    _check(load().te_upfirdn2d(ptr(out), ptr(x), ptr(fir), major, in_h, in_w, minor, kh, kw, up_x, up_y,
+                               down_x, down_y, px0, px1, py0, py1, dtype_code(x), stream()),
+           "upfirdn2d")
+    _count()
+
+
+def conv2d_simt(y, x, w, in_scale, out_scale, bias, noise, noise_w, geom):
+    _check(load().te_conv2d_simt(ptr(y), ptr(x), ptr(w), ptr(in_scale), ptr(out_scale), ptr(bias),
+                                 ptr(noise), ptr(noise_w), ctypes.byref(geom), dtype_code(x), stream()),
+           "conv2d_simt")
+    _count()
+
+
+def conv2d_wgrad_simt(gw, x, gy, in_scale, out_scale, geom):
+    _check(load().te_conv2d_wgrad_simt(ptr(gw), ptr(x), ptr(gy), ptr(in_scale), ptr(out_scale),
+                                       ctypes.byref(geom), dtype_code(x), stream()),
+           "conv2d_wgrad_simt")
+    _count()
+
+
+def adam_ema(p, g, m, v, ema, lr, beta1, beta2, eps, step, ema_decay, grad_scale):
+    _check(load().te_adam_ema(ptr(p), ptr(g), ptr(m), ptr(v), ptr(ema), p.numel(), lr, beta1, beta2,
+                              eps, step, ema_decay, grad_scale, stream()), "adam_ema")
+    _count()
+
+
+def attn_core(out, sim, q, k, v, batch, tokens):
+    _check(load().te_attn_core(ptr(out), ptr(sim), ptr(q), ptr(k), ptr(v), batch, tokens, stream()),
+           "attn_core")
+    _count()
+
+
+def conv2d_tc(y, x, w, out_scale, bias, batch, hin, win, cin, cout, kh, kw, act, w_bstride):
+    _check(load().te_conv2d_tc(ptr(y), ptr(x), ptr(w), ptr(out_scale), ptr(bias), batch, hin, win, cin,
+                               cout, kh, kw, act, w_bstride, stream()), "conv2d_tc")
+    _count()
+
+
+def gemm_tc_selftest(d, a, b, m, n, k):
+    _check(load().te_gemm_tc_selftest(ptr(d), ptr(a), ptr(b), m, n, k, stream()), "gemm_tc_selftest")
+    _count()

@@ -1,0 +1,613 @@
+"""Generator / Discriminator of TransEditor on the B200 kernels.
+
+Host-side mirror of /root/reference/model_spatial_query.py: same class names, constructor
+and forward signatures, return conventions and `state_dict` layout, so
+the reference's train_spatial_query.py / test_spatial_query.py and the authors' checkpoints
+work unmodified.  What differs is everything underneath:
+
+* ModulatedConv2d never materialises per-sample weights (reference :299-317 writes a
+  [B*Cout, Cin, k, k] tensor and calls cuDNN with groups=B).  It runs the shared-weight form
+  d * conv(x * s, W) on our own convolution kernels.
+* All convolutions, upfirdn2d, bias+activation and the attention core are hand-written
+  sm_100a kernels behind the C ABI (include/te_b200.h); there is no CPU path.
+* The 2 x 16 per-column mapping linears run as one batched GEMM each instead of 32 small
+  GEMMs + 32 slice copies (reference :626-646).
+
+Citations `:N` are into the reference's model_spatial_query.py.
+"""
+import math
+
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from . import op
+from .op import FusedLeakyReLU, fused_leaky_relu, upfirdn2d
+
+_SQRT2 = math.sqrt(2.0)
+
+
+def _grad_needed(*tensors):
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
+class PixelNorm(nn.Module):
+    """:75-81"""
+
+    def __init__(self, pixel_norm_op_dim):
+        super().__init__()
+        self.pixel_norm_op_dim = pixel_norm_op_dim
+
+    def forward(self, input):
+        ms = input.square().mean(dim=self.pixel_norm_op_dim, keepdim=True)
+        return input * torch.rsqrt(ms + 1e-8)
+
+
+def make_kernel(k):
+    """:84-92 — separable FIR as a normalised outer product."""
+    k = torch.as_tensor(k, dtype=torch.float32)
+    if k.ndim == 1:
+        k = torch.outer(k, k)
+    return k / k.sum()
+
+
+class Upsample(nn.Module):
+    """:95-113"""
+
+    def __init__(self, kernel, factor=2):
+        super().__init__()
+        self.factor = factor
+        self.register_buffer("kernel", make_kernel(kernel) * (factor ** 2))
+        p = self.kernel.shape[0] - factor
+        self.pad = ((p + 1) // 2 + factor - 1, p // 2)
+
+    def forward(self, input):
+        return upfirdn2d(input, self.kernel, up=self.factor, down=1, pad=self.pad)
+
+
+class Downsample(nn.Module):
+    """:116-134 (unused by G/D, kept for API completeness)"""
+
+    def __init__(self, kernel, factor=2):
+        super().__init__()
+        self.factor = factor
+        self.register_buffer("kernel", make_kernel(kernel))
+        p = self.kernel.shape[0] - factor
+        self.pad = ((p + 1) // 2, p // 2)
+
+    def forward(self, input):
+        return upfirdn2d(input, self.kernel, up=1, down=self.factor, pad=self.pad)
+
+
+class Blur(nn.Module):
+    """:137-153"""
+
+    def __init__(self, kernel, pad, upsample_factor=1):
+        super().__init__()
+        kernel = make_kernel(kernel)
+        if upsample_factor > 1:
+            kernel = kernel * (upsample_factor ** 2)
+        self.register_buffer("kernel", kernel)
+        self.pad = pad
+
+    def forward(self, input):
+        return upfirdn2d(input, self.kernel, pad=self.pad)
+
+
+class EqualConv2d(nn.Module):
+    """:156-191 — conv2d with the equalised-lr weight scale 1/sqrt(Cin k^2)."""
+
+    def __init__(self, in_channel, out_channel, kernel_size, stride=1, padding=0, bias=True):
+        super().__init__()
+        self.weight = nn.Parameter(torch.randn(out_channel, in_channel, kernel_size, kernel_size))
+        self.scale = 1 / math.sqrt(in_channel * kernel_size ** 2)
+        self.stride = stride
+        self.padding = padding
+        self.bias = nn.Parameter(torch.zeros(out_channel)) if bias else None
+
+    def forward(self, input):
+        out = op.conv2d(input, self.weight * self.scale, stride=self.stride, padding=self.padding)
+        if self.bias is not None:
+            out = out + self.bias.view(1, -1, 1, 1)
+        return out
+
+    def __repr__(self):
+        return (f"{self.__class__.__name__}({self.weight.shape[1]}, {self.weight.shape[0]},"
+                f" {self.weight.shape[2]}, stride={self.stride}, padding={self.padding})")
+
+
+class EqualLinear(nn.Module):
+    """:194-226"""
+
+    def __init__(self, in_dim, out_dim, bias=True, bias_init=0, lr_mul=1.0, activation=None):
+        super().__init__()
+        self.weight = nn.Parameter(torch.randn(out_dim, in_dim).div_(lr_mul))
+        self.bias = nn.Parameter(torch.zeros(out_dim).fill_(bias_init)) if bias else None
+        self.activation = activation
+        self.scale = (1 / math.sqrt(in_dim)) * lr_mul
+        self.lr_mul = lr_mul
+
+    def forward(self, input):
+        w = self.weight * self.scale
+        if self.activation:
+            return fused_leaky_relu(F.linear(input, w), self.bias * self.lr_mul)
+        return F.linear(input, w, bias=None if self.bias is None else self.bias * self.lr_mul)
+
+    def __repr__(self):
+        return f"{self.__class__.__name__}({self.weight.shape[1]}, {self.weight.shape[0]})"
+
+
+class ScaledLeakyReLU(nn.Module):
+    """:229-238"""
+
+    def __init__(self, negative_slope=0.2):
+        super().__init__()
+        self.negative_slope = negative_slope
+
+    def forward(self, input):
+        return fused_leaky_relu(input, None, self.negative_slope, _SQRT2)
+
+
+class ModulatedConv2d(nn.Module):
+    """:241-337.  Shared-weight formulation: with Wn = W/sqrt(Cin k^2), s = modulation(style),
+    d[b,o] = rsqrt(sum_i s[b,i]^2 * sum_k Wn[o,i,k]^2 + 1e-8):
+
+        plain     y = d * conv(x * s, Wn, pad k//2)
+        upsample  y = blur( d * conv_transpose(x * s, Wn, stride 2) )   (blur is linear, d is
+                                                                         per-channel: they commute)
+        downsample (unused by G) y = d * conv(blur(x * s), Wn, stride 2)
+    """
+
+    def __init__(self, in_channel, out_channel, kernel_size, style_dim, demodulate=True,
+                 upsample=False, downsample=False, blur_kernel=[1, 3, 3, 1]):
+        super().__init__()
+        self.eps = 1e-8
+        self.kernel_size = kernel_size
+        self.in_channel = in_channel
+        self.out_channel = out_channel
+        self.upsample = upsample
+        self.downsample = downsample
+        if upsample:
+            factor = 2
+            p = (len(blur_kernel) - factor) - (kernel_size - 1)
+            self.blur = Blur(blur_kernel, pad=((p + 1) // 2 + factor - 1, p // 2 + 1),
+                             upsample_factor=factor)
+        if downsample:
+            factor = 2
+            p = (len(blur_kernel) - factor) + (kernel_size - 1)
+            self.blur = Blur(blur_kernel, pad=((p + 1) // 2, p // 2))
+        self.scale = 1 / math.sqrt(in_channel * kernel_size ** 2)
+        self.padding = kernel_size // 2
+        self.weight = nn.Parameter(torch.randn(1, out_channel, in_channel, kernel_size, kernel_size))
+        self.modulation = EqualLinear(style_dim, in_channel, bias_init=1)
+        self.demodulate = demodulate
+
+    def __repr__(self):
+        return (f"{self.__class__.__name__}({self.in_channel}, {self.out_channel}, {self.kernel_size}, "
+                f"upsample={self.upsample}, downsample={self.downsample})")
+
+    def scales(self, style):
+        """(s [B,Cin], d [B,Cout] or None, Wn [Cout,Cin,k,k])"""
+        s = self.modulation(style)
+        wn = self.weight[0] * self.scale
+        d = None
+        if self.demodulate:
+            energy = wn.square().sum(dim=(2, 3))  # [Cout, Cin]
+            d = torch.rsqrt(s.square() @ energy.t() + self.eps)
+        return s, d, wn
+
+    def forward(self, input, style, bias=None, noise=None, noise_weight=None, activate=False):
+        """`bias`/`noise`/`activate` let StyledConv hand its epilogue to the conv kernel on the
+        inference path; reference callers pass only (input, style)."""
+        s, d, wn = self.scales(style)
+        fused_ok = not _grad_needed(input, s, wn, bias, noise_weight)
+        if self.upsample:
+            if fused_ok:
+                out = op.conv2d_fused(input, wn, in_scale=s, out_scale=d, transpose_stride=2)
+            else:
+                out = op.conv_transpose2d(input * s[:, :, None, None], wn, stride=2)
+                if d is not None:
+                    out = out * d[:, :, None, None]
+            out = self.blur(out)
+            return _epilogue(out, bias, noise, noise_weight, activate)
+        if self.downsample:
+            x = self.blur(input * s[:, :, None, None])
+            out = op.conv2d(x, wn, stride=2, padding=0)
+            if d is not None:
+                out = out * d[:, :, None, None]
+            return _epilogue(out, bias, noise, noise_weight, activate)
+        if fused_ok:
+            return op.conv2d_fused(input, wn, in_scale=s, out_scale=d, bias=bias, noise=noise,
+                                   noise_w=noise_weight, act=activate, padding=self.padding)
+        out = op.conv2d(input * s[:, :, None, None], wn, stride=1, padding=self.padding)
+        if d is not None:
+            out = out * d[:, :, None, None]
+        return _epilogue(out, bias, noise, noise_weight, activate)
+
+
+def _epilogue(out, bias, noise, noise_weight, activate):
+    if noise is not None:
+        out = out + noise_weight * noise
+    if activate:
+        return fused_leaky_relu(out, bias)
+    if bias is not None:
+        out = out + bias.view(1, -1, 1, 1)
+    return out
+
+
+class NoiseInjection(nn.Module):
+    """:340-351"""
+
+    def __init__(self):
+        super().__init__()
+        self.weight = nn.Parameter(torch.zeros(1))
+
+    def forward(self, image, noise=None):
+        if noise is None:
+            batch, _, height, width = image.shape
+            noise = image.new_empty(batch, 1, height, width).normal_()
+        return image + self.weight * noise
+
+
+class ConstantInput(nn.Module):
+    """:354-364 (unused: the P code is the 4x4 input)"""
+
+    def __init__(self, channel, size=4):
+        super().__init__()
+        self.input = nn.Parameter(torch.randn(1, channel, size, size))
+
+    def forward(self, input):
+        return self.input.repeat(input.shape[0], 1, 1, 1)
+
+
+class StyledConv(nn.Module):
+    """:367-403 — modulated conv -> [noise] -> bias + leaky relu * sqrt(2)."""
+
+    def __init__(self, in_channel, out_channel, kernel_size, style_dim, upsample=False,
+                 blur_kernel=[1, 3, 3, 1], demodulate=True, layer_noise_injection=True):
+        super().__init__()
+        self.conv = ModulatedConv2d(in_channel, out_channel, kernel_size, style_dim,
+                                    upsample=upsample, blur_kernel=blur_kernel, demodulate=demodulate)
+        self.layer_noise_injection = layer_noise_injection
+        self.noise = NoiseInjection()
+        self.activate = FusedLeakyReLU(out_channel)
+
+    def forward(self, input, style, noise=None):
+        if self.layer_noise_injection:
+            if noise is None:
+                b, _, h, w = input.shape
+                f = 2 if self.conv.upsample else 1
+                noise = input.new_empty(b, 1, h * f, w * f).normal_()
+            return self.conv(input, style, bias=self.activate.bias, noise=noise,
+                             noise_weight=self.noise.weight, activate=True)
+        return self.conv(input, style, bias=self.activate.bias, activate=True)
+
+
+class ToRGB(nn.Module):
+    """:406-425"""
+
+    def __init__(self, in_channel, style_dim, upsample=True, blur_kernel=[1, 3, 3, 1]):
+        super().__init__()
+        if upsample:
+            self.upsample = Upsample(blur_kernel)
+        self.conv = ModulatedConv2d(in_channel, 3, 1, style_dim, demodulate=False)
+        self.bias = nn.Parameter(torch.zeros(1, 3, 1, 1))
+
+    def forward(self, input, style, skip=None):
+        out = self.conv(input, style, bias=self.bias.view(-1))
+        if skip is not None:
+            out = out + self.upsample(skip)
+        return out
+
+
+class Attention(nn.Module):
+    """:862-901 — queries from the P tokens, keys/values from the (normalised) Z tokens."""
+
+    def __init__(self, in_dim, param_dim, out_dim, lr_mul=1.0, groups=4, compress=4):
+        assert out_dim % (groups * compress) == 0
+        super().__init__()
+        self.in_dim, self.param_dim, self.out_dim = in_dim, param_dim, out_dim
+        self.compress, self.groups = compress, groups
+        self.planes = out_dim // compress
+        self.group_planes = self.planes // groups
+        self.scale = self.planes ** -0.5
+        self.q_transform = EqualLinear(param_dim, self.planes, lr_mul=lr_mul)
+        self.k_transform = EqualLinear(in_dim, self.planes, lr_mul=lr_mul)
+        self.v_transform = EqualLinear(in_dim, self.planes, lr_mul=lr_mul)
+        self.proj = EqualLinear(self.planes, out_dim, lr_mul=lr_mul)
+
+    def forward(self, attention, op_param, return_similarity=False):
+        n, l, _ = attention.shape
+        m = op_param.shape[1]
+        q = self.q_transform(op_param)
+        k = self.k_transform(attention)
+        v = self.v_transform(attention)
+        if m == l and self.groups == 4:
+            stacked, similarity = op.attn_core(q, k, v)
+        else:  # general token counts: literal form of :888-894
+            g, gp = self.groups, self.group_planes
+            qh = q.reshape(n, m, g, gp).permute(0, 2, 3, 1)
+            kh = k.reshape(n, l, g, gp).permute(0, 2, 3, 1)
+            vh = v.reshape(n, l, g, gp).permute(0, 2, 3, 1)
+            similarity = F.softmax(torch.einsum("abcd,abce->abde", qh, kh) * self.scale, dim=3)
+            sv = torch.einsum("abcd,abed->abec", similarity, vh)
+            stacked = sv.reshape(n, self.planes, l).permute(0, 2, 1)
+        output = self.proj(stacked)
+        return (output, similarity) if return_similarity else output
+
+
+class AttentionBlock(nn.Module):
+    """:904-936 — joint (tokens x channels) LayerNorm, no affine."""
+
+    def __init__(self, in_dim, param_dim, out_dim, lr_mul=1.0, groups=4):
+        super().__init__()
+        self.in_dim, self.out_dim, self.param_dim = in_dim, out_dim, param_dim
+        self.atten = Attention(in_dim, param_dim, out_dim, lr_mul=lr_mul, groups=groups)
+        self.mlp = nn.Sequential(EqualLinear(out_dim, out_dim, lr_mul=lr_mul), nn.GELU(),
+                                 EqualLinear(out_dim, out_dim, lr_mul=lr_mul))
+        if out_dim != in_dim:
+            self.proj = EqualLinear(in_dim, out_dim, lr_mul=lr_mul)
+
+    def forward(self, x, op_param, return_similarity=False):
+        normed = F.layer_norm(x, x.shape[1:])
+        attention, similarity = self.atten(normed, op_param, return_similarity=True)
+        x = (self.proj(x) if self.out_dim != self.in_dim else x) + attention
+        x = x + self.mlp(F.layer_norm(x, x.shape[1:]))
+        return (x, similarity) if return_similarity else x
+
+
+class Generator(nn.Module):
+    """:428-728"""
+
+    def __init__(self, size, style_dim, param_dim, token_dim, channel_multiplier=2,
+                 blur_kernel=[1, 3, 3, 1], lr_mlp=0.01, layer_noise_injection=False,
+                 use_spatial_mapping=True, num_region=1, n_trans=4, pixel_norm_op_dim=2,
+                 no_trans=False):
+        super().__init__()
+        self.size = size
+        self.lr_mlp = lr_mlp
+        self.n_trans = n_trans
+        self.no_trans = no_trans
+        self.style_dim = style_dim
+        self.param_dim = param_dim
+        self.token_dim = token_dim
+        self.layer_noise_injection = layer_noise_injection
+        self.style = None
+        self.use_spatial_mapping = use_spatial_mapping
+        self.num_region = num_region
+        self.num_spatial_mapping = int(16 / num_region)
+        self.num_style_mapping = self.num_spatial_mapping
+        self.pixel_norm_op_dim = pixel_norm_op_dim
+
+        if self.use_spatial_mapping:
+            self.spatial_mapping_network = self.spatial_mapping()
+        self.style_mapping_network = self.style_mapping()
+
+        self.channels = {4: 512, 8: 512, 16: 512, 32: 512, 64: 256 * channel_multiplier,
+                         128: 128 * channel_multiplier, 256: 64 * channel_multiplier,
+                         512: 32 * channel_multiplier, 1024: 16 * channel_multiplier}
+        self.adjust_style = EqualLinear(in_dim=16, out_dim=self.token_dim)
+        self.conv1 = StyledConv(self.channels[4], self.channels[4], 3, style_dim,
+                                blur_kernel=blur_kernel,
+                                layer_noise_injection=self.layer_noise_injection)
+        self.to_rgb1 = ToRGB(self.channels[4], style_dim, upsample=False)
+        self.log_size = int(math.log(size, 2))
+        self.num_layers = (self.log_size - 2) * 2 + 1
+        self.convs = nn.ModuleList()
+        self.upsamples = nn.ModuleList()
+        self.to_rgbs = nn.ModuleList()
+        self.noises = nn.Module()
+        for layer_idx in range(self.num_layers):
+            res = (layer_idx + 5) // 2
+            self.noises.register_buffer(f"noise_{layer_idx}", torch.randn(1, 1, 2 ** res, 2 ** res))
+        in_channel = self.channels[4]
+        for i in range(3, self.log_size + 1):
+            out_channel = self.channels[2 ** i]
+            self.convs.append(StyledConv(in_channel, out_channel, 3, style_dim, upsample=True,
+                                         blur_kernel=blur_kernel,
+                                         layer_noise_injection=self.layer_noise_injection))
+            self.convs.append(StyledConv(out_channel, out_channel, 3, style_dim,
+                                         blur_kernel=blur_kernel,
+                                         layer_noise_injection=self.layer_noise_injection))
+            self.to_rgbs.append(ToRGB(out_channel, style_dim))
+            in_channel = out_channel
+        self.n_latent = self.log_size * 2 - 2
+        self.register_buffer("token", torch.eye(self.token_dim))
+        self.register_buffer("token_spatial", torch.eye(16))
+        self.trans_interact = not self.no_trans
+        if self.trans_interact:
+            self.interact = self.interaction_network()
+
+    # -- sub-network builders (names are part of the reference API, :546-577)
+    def _mapping(self, count):
+        layers = [PixelNorm(self.pixel_norm_op_dim)]
+        layers += [EqualLinear(in_dim=self.style_dim, out_dim=self.style_dim, lr_mul=self.lr_mlp,
+                               activation="fused_lrelu") for _ in range(count)]
+        return nn.Sequential(*layers)
+
+    def style_mapping(self):
+        return self._mapping(self.num_style_mapping)
+
+    def spatial_mapping(self):
+        return self._mapping(self.num_spatial_mapping)
+
+    def interaction_network(self):
+        blocks = [AttentionBlock(in_dim=self.style_dim + 16, param_dim=self.param_dim + 16,
+                                 out_dim=self.style_dim, lr_mul=self.lr_mlp)]
+        blocks += [AttentionBlock(in_dim=self.style_dim, param_dim=self.param_dim,
+                                  out_dim=self.style_dim, lr_mul=self.lr_mlp)
+                   for _ in range(1, self.n_trans)]
+        return nn.Sequential(*blocks)
+
+    def make_noise(self):
+        """:579-588 (the reference hard-codes device='cuda')"""
+        device = self.token.device if self.token.is_cuda else "cuda"
+        noises = [torch.randn(1, 1, 4, 4, device=device)]
+        for i in range(3, self.log_size + 1):
+            noises += [torch.randn(1, 1, 2 ** i, 2 ** i, device=device) for _ in range(2)]
+        return noises
+
+    def _map_columns(self, code, network, count):
+        """:626-646 as ONE batched GEMM: column i of `code` [B,D,C] goes through its own
+        EqualLinear(+fused lrelu).  Returns [B,D,C]."""
+        code = network[0](code)
+        layers = [network[i + 1] for i in range(count)]
+        w = torch.stack([l.weight for l in layers]) * layers[0].scale          # [C, out, in]
+        bias = torch.stack([l.bias for l in layers]) * layers[0].lr_mul        # [C, out]
+        cols = code.permute(2, 0, 1)[:count]                                   # [C, B, in]
+        y = torch.bmm(cols, w.transpose(1, 2))                                 # [C, B, out]
+        y = fused_leaky_relu(y.permute(1, 0, 2).reshape(code.shape[0], -1), bias.reshape(-1))
+        y = y.reshape(code.shape[0], count, -1).permute(0, 2, 1)               # [B, out, C]
+        if count == code.shape[2]:
+            return y
+        out = torch.zeros_like(code)  # num_region > 1: untouched columns stay zero (:630)
+        out[:, :, :count] = y
+        return out
+
+    def forward(self, style, op_param, return_latents=False, input_is_latent=False, noise=None,
+                randomize_noise=True, return_style=False, return_p_latent=False,
+                return_only_style=False, return_only_style_latent=False,
+                return_only_mapped_p=False, return_only_mapped_z=False, use_spatial_mapping=True,
+                use_style_mapping=True, trans_interact=True, return_mapped_codes=False):
+        if self.no_trans:
+            trans_interact = False
+        if input_is_latent:  # :618-621
+            use_spatial_mapping, use_style_mapping, trans_interact = True, False, False
+
+        if use_spatial_mapping:
+            spatialcode = self._map_columns(op_param, self.spatial_mapping_network, self.num_spatial_mapping)
+        else:
+            spatialcode = op_param
+        if use_style_mapping:
+            stylecode = self._map_columns(style, self.style_mapping_network, self.num_style_mapping)
+        else:
+            stylecode = style
+
+        if return_mapped_codes:
+            return stylecode, spatialcode
+        if return_only_mapped_p:
+            return spatialcode
+        if return_only_mapped_z:
+            return stylecode
+
+        if noise is None:
+            if randomize_noise:
+                noise = [None] * self.num_layers
+            else:
+                noise = [getattr(self.noises, f"noise_{i}") for i in range(self.num_layers)]
+
+        stylecode = stylecode.permute(0, 2, 1)      # [B, 16, 512]
+        spatialcode = spatialcode.permute(0, 2, 1)  # [B, 16, 512]
+        if trans_interact:
+            eye = self.token_spatial.repeat(stylecode.size(0), 1, 1)
+            x = self.interact[0](torch.cat([stylecode, eye], 2), torch.cat([spatialcode, eye], 2))
+            for i in range(1, self.n_trans):
+                x = self.interact[i](x, spatialcode)
+
+        if self.no_trans:
+            latent = self.adjust_style(stylecode.permute(0, 2, 1)).permute(0, 2, 1)
+        elif not input_is_latent:
+            if not trans_interact:
+                raise NameError("trans_interact=False without no_trans/input_is_latent leaves the "
+                                "latent undefined (the reference raises here too, :686)")
+            latent = self.adjust_style(x.permute(0, 2, 1)).permute(0, 2, 1)  # [B, T, 512]
+        else:
+            latent = style
+
+        if return_only_style_latent or return_only_style:
+            return latent
+
+        batch = spatialcode.shape[0]
+        out = spatialcode.permute(0, 2, 1).reshape(batch, 512, 4, 4)
+        out = self.conv1(out, latent[:, 0], noise=noise[0])
+        skip = self.to_rgb1(out, latent[:, 1])
+        i = 1
+        for conv1, conv2, noise1, noise2, to_rgb in zip(self.convs[::2], self.convs[1::2],
+                                                        noise[1::2], noise[2::2], self.to_rgbs):
+            out = conv1(out, latent[:, i], noise=noise1)
+            out = conv2(out, latent[:, i + 1], noise=noise2)
+            skip = to_rgb(out, latent[:, i + 2], skip)
+            i += 2
+        image = skip
+
+        if return_style:
+            return image, latent
+        if return_p_latent:
+            return image, spatialcode
+        if return_latents:
+            return image, latent, None
+        return image, None, None
+
+
+class ConvLayer(nn.Sequential):
+    """:731-777"""
+
+    def __init__(self, in_channel, out_channel, kernel_size, downsample=False,
+                 blur_kernel=[1, 3, 3, 1], bias=True, activate=True):
+        layers = []
+        if downsample:
+            factor = 2
+            p = (len(blur_kernel) - factor) + (kernel_size - 1)
+            layers.append(Blur(blur_kernel, pad=((p + 1) // 2, p // 2)))
+            stride = 2
+            self.padding = 0
+        else:
+            stride = 1
+            self.padding = kernel_size // 2
+        layers.append(EqualConv2d(in_channel, out_channel, kernel_size, padding=self.padding,
+                                  stride=stride, bias=bias and not activate))
+        if activate:
+            layers.append(FusedLeakyReLU(out_channel) if bias else ScaledLeakyReLU(0.2))
+        super().__init__(*layers)
+
+
+class ResBlock(nn.Module):
+    """:780-798"""
+
+    def __init__(self, in_channel, out_channel, blur_kernel=[1, 3, 3, 1]):
+        super().__init__()
+        self.conv1 = ConvLayer(in_channel, in_channel, 3, blur_kernel=blur_kernel)
+        self.conv2 = ConvLayer(in_channel, out_channel, 3, downsample=True, blur_kernel=blur_kernel)
+        self.skip = ConvLayer(in_channel, out_channel, 1, downsample=True, blur_kernel=blur_kernel,
+                              bias=False, activate=False)
+
+    def forward(self, input):
+        out = self.conv2(self.conv1(input))
+        return (out + self.skip(input)) / _SQRT2
+
+
+class Discriminator(nn.Module):
+    """:801-859"""
+
+    def __init__(self, size, channel_multiplier=2, blur_kernel=[1, 3, 3, 1]):
+        super().__init__()
+        channels = {4: 512, 8: 512, 16: 512, 32: 512, 64: 256 * channel_multiplier,
+                    128: 128 * channel_multiplier, 256: 64 * channel_multiplier,
+                    512: 32 * channel_multiplier, 1024: 16 * channel_multiplier}
+        convs = [ConvLayer(3, channels[size], 1)]
+        log_size = int(math.log(size, 2))
+        in_channel = channels[size]
+        for i in range(log_size, 2, -1):
+            out_channel = channels[2 ** (i - 1)]
+            convs.append(ResBlock(in_channel, out_channel, blur_kernel))
+            in_channel = out_channel
+        self.convs = nn.Sequential(*convs)
+        self.stddev_group = 4
+        self.stddev_feat = 1
+        self.final_conv = ConvLayer(in_channel + 1, channels[4], 3)
+        self.final_linear = nn.Sequential(
+            EqualLinear(channels[4] * 4 * 4, channels[4], activation="fused_lrelu"),
+            EqualLinear(channels[4], 1))
+
+    def forward(self, input):
+        out = self.convs(input)
+        batch, channel, height, width = out.shape
+        group = min(batch, self.stddev_group)
+        # minibatch standard deviation, one scalar per sub-batch (:844-852)
+        grouped = out.view(group, -1, self.stddev_feat, channel // self.stddev_feat, height, width)
+        stddev = torch.sqrt(grouped.var(0, unbiased=False) + 1e-8)
+        stddev = stddev.mean([2, 3, 4], keepdim=True).squeeze(2)
+        stddev = stddev.repeat(group, 1, height, width)
+        out = torch.cat([out, stddev], 1)
+        out = self.final_conv(out)
+        return self.final_linear(out.view(batch, -1))

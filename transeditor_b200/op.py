@@ -1,0 +1,427 @@
+"""Operator layer: the reference's `utils.op` surface (fused_leaky_relu, FusedLeakyReLU,
+upfirdn2d) plus the convolution primitives, all as twice-differentiable autograd
+Functions over the C ABI of libte_b200.so.
+
+Reference interfaces mirrored (argument names, defaults, error behaviour):
+  utils/op/fused_act.py:18-90   FusedLeakyReLUFunction(+Backward), FusedLeakyReLU, fused_leaky_relu
+  utils/op/upfirdn2d.py:17-148  UpFirDn2d(+Backward), upfirdn2d
+
+Every backward is itself expressed through differentiable Functions of this file, so
+R1 (double backward through D) and path-length regularisation (double backward through
+G) work — SURVEY.md fact 5.
+"""
+import math
+
+import torch
+from torch import nn
+from torch.autograd import Function
+
+from . import lib
+
+# --------------------------------------------------------------------------------------------
+# layout helpers
+
+
+def _is_channels_last(t):
+    return (t.dim() == 4 and t.shape[1] > 1 and not t.is_contiguous()
+            and t.is_contiguous(memory_format=torch.channels_last))
+
+
+def _canonical(t):
+    """Return (tensor, channels_last_flag) with the storage dense in one of the two layouts."""
+    if _is_channels_last(t):
+        return t, True
+    return t.contiguous(), False
+
+
+def _bias_geometry(x, channels_last):
+    """(step_b, size_b) of te_fused_bias_act: bias indexes dim 1 of x."""
+    c = x.shape[1] if x.dim() > 1 else x.shape[0]
+    if channels_last or x.dim() <= 2:
+        return 1, c
+    return int(math.prod(x.shape[2:])), c
+
+
+# --------------------------------------------------------------------------------------------
+# fused bias + leaky relu
+
+
+def _bias_act(x, bias, ref, act, grad, alpha, scale):
+    lib.require_cuda(x, bias, ref)
+    x, cl = _canonical(x)
+    if ref is not None:
+        ref = ref.contiguous(memory_format=torch.channels_last) if cl else ref.contiguous()
+    if bias is not None:
+        bias = bias.to(x.dtype).contiguous()
+    out = torch.empty_like(x)
+    step_b, size_b = _bias_geometry(x, cl)
+    lib.fused_bias_act(out, x, bias, ref, act, grad, float(alpha), float(scale), step_b, size_b)
+    return out
+
+
+class FusedLeakyReLUFunctionBackward(Function):
+    """grad_input = scale * (out > 0 ? g : slope*g); grad_bias = per-channel sum — ONE kernel
+    (the reference runs fused_bias_act and then a separate .sum(), fused_act.py:27-36)."""
+
+    @staticmethod
+    def forward(ctx, grad_output, out, has_bias, negative_slope, scale):
+        lib.require_cuda(grad_output, out)
+        ctx.save_for_backward(out)
+        ctx.negative_slope = negative_slope
+        ctx.scale = scale
+        ctx.has_bias = has_bias
+        g, cl = _canonical(grad_output)
+        ref = out.contiguous(memory_format=torch.channels_last) if cl else out.contiguous()
+        grad_input = torch.empty_like(g)
+        step_b, size_b = _bias_geometry(g, cl)
+        if has_bias:
+            acc_dtype = torch.float64 if g.dtype == torch.float64 else torch.float32
+            grad_bias = torch.zeros(size_b, dtype=acc_dtype, device=g.device)
+            lib.fused_bias_act_bwd(grad_input, grad_bias, g, ref, float(negative_slope), float(scale),
+                                   step_b, size_b)
+            grad_bias = grad_bias.to(g.dtype)
+        else:
+            lib.fused_bias_act_bwd(grad_input, None, g, ref, float(negative_slope), float(scale),
+                                   step_b, size_b)
+            grad_bias = grad_input.new_zeros(0)
+        return grad_input, grad_bias
+
+    @staticmethod
+    def backward(ctx, gradgrad_input, gradgrad_bias):
+        (out,) = ctx.saved_tensors
+        if gradgrad_input is None:
+            gradgrad_input = torch.zeros_like(out)
+        gb = gradgrad_bias if (ctx.has_bias and gradgrad_bias is not None) else None
+        gradgrad_out = _bias_act(gradgrad_input, gb, out, 3, 1, ctx.negative_slope, ctx.scale)
+        return gradgrad_out, None, None, None, None
+
+
+class FusedLeakyReLUFunction(Function):
+    """Saves only its OUTPUT, like the reference (fused_act.py:52-59)."""
+
+    @staticmethod
+    def forward(ctx, input, bias, negative_slope, scale):
+        out = _bias_act(input, bias, None, 3, 0, negative_slope, scale)
+        ctx.save_for_backward(out)
+        ctx.negative_slope = negative_slope
+        ctx.scale = scale
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        (out,) = ctx.saved_tensors
+        grad_input, grad_bias = FusedLeakyReLUFunctionBackward.apply(
+            grad_output, out, ctx.has_bias, ctx.negative_slope, ctx.scale)
+        return grad_input, (grad_bias if ctx.has_bias else None), None, None
+
+
+def fused_leaky_relu(input, bias, negative_slope=0.2, scale=2 ** 0.5):
+    """utils/op/fused_act.py:89-90."""
+    return FusedLeakyReLUFunction.apply(input, bias, negative_slope, scale)
+
+
+class FusedLeakyReLU(nn.Module):
+    """utils/op/fused_act.py:72-86 — parameter name `bias`, shape [channel]."""
+
+    def __init__(self, channel, bias=True, negative_slope=0.2, scale=2 ** 0.5):
+        super().__init__()
+        self.bias = nn.Parameter(torch.zeros(channel)) if bias else None
+        self.negative_slope = negative_slope
+        self.scale = scale
+
+    def forward(self, input):
+        return fused_leaky_relu(input, self.bias, self.negative_slope, self.scale)
+
+
+# --------------------------------------------------------------------------------------------
+# upfirdn2d
+
+
+def _fir_f32(kernel):
+    return kernel.detach().to(torch.float32).contiguous()
+
+
+def _upfirdn2d_native(x, fir, up, down, pad, out_hw=None):
+    """x: [N,C,H,W] in either dense layout -> [N,C,H',W'] in the same layout."""
+    lib.require_cuda(x, fir)
+    x, cl = _canonical(x)
+    n, c, h, w = x.shape
+    up_x, up_y = up
+    down_x, down_y = down
+    px0, px1, py0, py1 = pad
+    kh, kw = fir.shape
+    out_h = (h * up_y + py0 + py1 - kh) // down_y + 1
+    out_w = (w * up_x + px0 + px1 - kw) // down_x + 1
+    if out_hw is not None and (out_h, out_w) != tuple(out_hw):
+        raise RuntimeError("upfirdn2d: size mismatch %s vs %s" % ((out_h, out_w), tuple(out_hw)))
+    if out_h <= 0 or out_w <= 0:
+        raise RuntimeError("upfirdn2d: empty output")
+    if cl:
+        out = torch.empty((n, c, out_h, out_w), dtype=x.dtype, device=x.device,
+                          memory_format=torch.channels_last)
+        major, minor = n, c
+    else:
+        out = torch.empty((n, c, out_h, out_w), dtype=x.dtype, device=x.device)
+        major, minor = n * c, 1
+    lib.upfirdn2d(out, x, _fir_f32(fir), major, h, w, minor, up_x, up_y, down_x, down_y, px0, px1, py0, py1)
+    return out
+
+
+class UpFirDn2dBackward(Function):
+    """utils/op/upfirdn2d.py:17-83: the input gradient is the same operator with up and down
+    swapped, the flipped FIR and g_pad; its own backward is the forward operator again."""
+
+    @staticmethod
+    def forward(ctx, grad_output, kernel, grad_kernel, up, down, pad, g_pad, in_size, out_size):
+        grad_input = _upfirdn2d_native(grad_output, grad_kernel, down, up, g_pad,
+                                       out_hw=(in_size[2], in_size[3]))
+        ctx.save_for_backward(kernel)
+        ctx.up, ctx.down, ctx.pad = up, down, pad
+        ctx.out_size = out_size
+        return grad_input
+
+    @staticmethod
+    def backward(ctx, gradgrad_input):
+        (kernel,) = ctx.saved_tensors
+        gradgrad_out = _upfirdn2d_native(gradgrad_input, kernel, ctx.up, ctx.down, ctx.pad,
+                                         out_hw=ctx.out_size)
+        return gradgrad_out, None, None, None, None, None, None, None, None
+
+
+class UpFirDn2d(Function):
+    """utils/op/upfirdn2d.py:86-140."""
+
+    @staticmethod
+    def forward(ctx, input, kernel, up, down, pad):
+        up_x, up_y = up
+        down_x, down_y = down
+        pad_x0, pad_x1, pad_y0, pad_y1 = pad
+        kernel_h, kernel_w = kernel.shape
+        _, _, in_h, in_w = input.shape
+        ctx.in_size = tuple(input.shape)
+        out = _upfirdn2d_native(input, kernel, up, down, pad)
+        out_h, out_w = out.shape[2], out.shape[3]
+        ctx.save_for_backward(kernel, torch.flip(kernel, [0, 1]))
+        ctx.out_size = (out_h, out_w)
+        ctx.up, ctx.down, ctx.pad = up, down, pad
+        # padding of the gradient operator (upfirdn2d.py:109-112)
+        ctx.g_pad = (kernel_w - pad_x0 - 1,
+                     in_w * up_x - out_w * down_x + pad_x0 - up_x + 1,
+                     kernel_h - pad_y0 - 1,
+                     in_h * up_y - out_h * down_y + pad_y0 - up_y + 1)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        kernel, grad_kernel = ctx.saved_tensors
+        grad_input = UpFirDn2dBackward.apply(grad_output, kernel, grad_kernel, ctx.up, ctx.down,
+                                             ctx.pad, ctx.g_pad, ctx.in_size, ctx.out_size)
+        return grad_input, None, None, None, None
+
+
+def upfirdn2d(input, kernel, up=1, down=1, pad=(0, 0)):
+    """utils/op/upfirdn2d.py:143-148 — same pad on both axes."""
+    return UpFirDn2d.apply(input, kernel, (up, up), (down, down), (pad[0], pad[1], pad[0], pad[1]))
+
+
+# --------------------------------------------------------------------------------------------
+# gather convolution primitives (f32 / f64, NCHW) — see include/te_b200.h
+
+
+class Geometry:
+    """up/down/pad/flip of one gather convolution; weights are STORED [O, I, kh, kw] relative to
+    the forward op and `transposed` says the kernel should read them as [I, O]."""
+
+    __slots__ = ("kh", "kw", "up", "down", "pad_y", "pad_x", "flip", "transposed", "out_hw")
+
+    def __init__(self, kh, kw, up, down, pad_y, pad_x, flip, transposed, out_hw):
+        self.kh, self.kw, self.up, self.down = kh, kw, up, down
+        self.pad_y, self.pad_x, self.flip, self.transposed = pad_y, pad_x, flip, transposed
+        self.out_hw = (int(out_hw[0]), int(out_hw[1]))
+
+    def adjoint(self, in_hw):
+        """Geometry of the data gradient (maps output-shaped tensors back to `in_hw`)."""
+        return Geometry(self.kh, self.kw, self.down, self.up, self.kh - 1 - self.pad_y,
+                        self.kw - 1 - self.pad_x, not self.flip, not self.transposed, in_hw)
+
+    def c_struct(self, x, w, act=0, noise_bstride=0):
+        b, cin, hin, win = x.shape
+        o_store, i_store = w.shape[0], w.shape[1]
+        kk = self.kh * self.kw
+        if self.transposed:
+            cout, w_so, w_si, w_cin = i_store, kk, i_store * kk, o_store
+        else:
+            cout, w_so, w_si, w_cin = o_store, i_store * kk, kk, i_store
+        if w_cin != cin:
+            raise RuntimeError("conv: weight expects %d input channels, tensor has %d" % (w_cin, cin))
+        return lib.ConvGeom(b, cin, hin, win, cout, self.out_hw[0], self.out_hw[1], self.kh, self.kw,
+                            self.up, self.down, self.pad_y, self.pad_x, int(self.flip),
+                            w_so, w_si, act, noise_bstride)
+
+
+def _conv_forward(x, w, geom, in_scale=None, out_scale=None, bias=None, noise=None, noise_w=None, act=0):
+    lib.require_cuda(x, w, in_scale, out_scale, bias, noise, noise_w)
+    if x.dtype not in (torch.float32, torch.float64):
+        raise TypeError("conv2d_simt: f32/f64 only, got %s" % x.dtype)
+    x = x.contiguous()
+    w = w.to(x.dtype).contiguous()
+    nb = 0
+    if noise is not None:
+        noise = noise.to(x.dtype).contiguous()
+        nb = 0 if noise.shape[0] == 1 else geom.out_hw[0] * geom.out_hw[1]
+        noise_w = noise_w.to(x.dtype).contiguous()
+    cs = geom.c_struct(x, w, act, nb)
+    y = torch.empty((cs.batch, cs.cout, cs.hout, cs.wout), dtype=x.dtype, device=x.device)
+    prep = lambda t: None if t is None else t.to(x.dtype).contiguous()  # noqa: E731
+    lib.conv2d_simt(y, x, w, prep(in_scale), prep(out_scale), prep(bias), noise, noise_w, cs)
+    return y
+
+
+def _conv_wgrad(x, gy, geom, w_shape, in_scale=None, out_scale=None):
+    lib.require_cuda(x, gy)
+    x = x.contiguous()
+    gy = gy.to(x.dtype).contiguous()
+    gw = torch.zeros(w_shape, dtype=x.dtype, device=x.device)
+    cs = geom.c_struct(x, gw)
+    if (cs.hout, cs.wout) != (gy.shape[2], gy.shape[3]) or cs.cout != gy.shape[1]:
+        raise RuntimeError("conv wgrad: gradient shape %s does not match geometry" % (tuple(gy.shape),))
+    prep = lambda t: None if t is None else t.to(x.dtype).contiguous()  # noqa: E731
+    lib.conv2d_wgrad_simt(gw, x, gy, prep(in_scale), prep(out_scale), cs)
+    return gw
+
+
+class ConvGather(Function):
+    """y = conv(x, w; geom).  backward: data grad = ConvGather with the adjoint geometry,
+    weight grad = ConvWeightGrad — both differentiable again."""
+
+    @staticmethod
+    def forward(ctx, x, w, geom):
+        ctx.save_for_backward(x, w)
+        ctx.geom = geom
+        return _conv_forward(x, w, geom)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        geom = ctx.geom
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            gx = ConvGather.apply(gy, w, geom.adjoint((x.shape[2], x.shape[3])))
+        if ctx.needs_input_grad[1]:
+            gw = ConvWeightGrad.apply(x, gy, geom, tuple(w.shape))
+        return gx, gw, None
+
+
+class ConvWeightGrad(Function):
+    """gw = wgrad(x, gy; geom) — bilinear, so its backward is two ConvGather calls."""
+
+    @staticmethod
+    def forward(ctx, x, gy, geom, w_shape):
+        ctx.save_for_backward(x, gy)
+        ctx.geom = geom
+        return _conv_wgrad(x, gy, geom, w_shape)
+
+    @staticmethod
+    def backward(ctx, ggw):
+        x, gy = ctx.saved_tensors
+        geom = ctx.geom
+        g_x = g_gy = None
+        if ctx.needs_input_grad[0]:
+            g_x = ConvGather.apply(gy, ggw, geom.adjoint((x.shape[2], x.shape[3])))
+        if ctx.needs_input_grad[1]:
+            g_gy = ConvGather.apply(x, ggw, geom)
+        return g_x, g_gy, None, None
+
+
+def conv2d(x, w, stride=1, padding=0):
+    """F.conv2d(x, w, stride=stride, padding=padding) (cross-correlation), w [O, I, kh, kw]."""
+    kh, kw = w.shape[2], w.shape[3]
+    oh = (x.shape[2] + 2 * padding - kh) // stride + 1
+    ow = (x.shape[3] + 2 * padding - kw) // stride + 1
+    geom = Geometry(kh, kw, 1, stride, padding, padding, False, False, (oh, ow))
+    return ConvGather.apply(x, w, geom)
+
+
+def conv_transpose2d(x, w_oi, stride=2):
+    """F.conv_transpose2d(x, w_oi.transpose(0,1), stride=stride, padding=0) with the weight kept in
+    the modulated-conv storage order [O, I, kh, kw] (model_spatial_query.py:315-318)."""
+    kh, kw = w_oi.shape[2], w_oi.shape[3]
+    oh = (x.shape[2] - 1) * stride + kh
+    ow = (x.shape[3] - 1) * stride + kw
+    geom = Geometry(kh, kw, stride, 1, kh - 1, kw - 1, True, False, (oh, ow))
+    return ConvGather.apply(x, w_oi, geom)
+
+
+def conv2d_fused(x, w, in_scale=None, out_scale=None, bias=None, noise=None, noise_w=None,
+                 act=False, stride=1, padding=0, transpose_stride=0):
+    """Inference-only fused form: act(out_scale * conv(x * in_scale, w) + noise_w*noise + bias).
+    Not differentiable (callers use it under no_grad)."""
+    kh, kw = w.shape[2], w.shape[3]
+    if transpose_stride:
+        oh = (x.shape[2] - 1) * transpose_stride + kh
+        ow = (x.shape[3] - 1) * transpose_stride + kw
+        geom = Geometry(kh, kw, transpose_stride, 1, kh - 1, kw - 1, True, False, (oh, ow))
+    else:
+        oh = (x.shape[2] + 2 * padding - kh) // stride + 1
+        ow = (x.shape[3] + 2 * padding - kw) // stride + 1
+        geom = Geometry(kh, kw, 1, stride, padding, padding, False, False, (oh, ow))
+    return _conv_forward(x, w, geom, in_scale, out_scale, bias, noise, noise_w, 1 if act else 0)
+
+
+# --------------------------------------------------------------------------------------------
+# cross-attention core
+
+
+class AttnCore(Function):
+    """q,k,v [B,16,128] -> (out [B,16,128], sim [B,4,16,16]) in one kernel
+    (model_spatial_query.py:888-894).  Backward recomputes with differentiable torch ops so
+    higher-order gradients (spatial path regularisation) stay available."""
+
+    @staticmethod
+    def forward(ctx, q, k, v):
+        lib.require_cuda(q, k, v)
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        b, t, c = q.shape
+        out = torch.empty_like(q)
+        sim = torch.empty((b, 4, t, t), dtype=q.dtype, device=q.device)
+        lib.attn_core(out, sim, q, k, v, b, t)
+        ctx.save_for_backward(q, k, v)
+        ctx.mark_non_differentiable(sim)
+        return out, sim
+
+    @staticmethod
+    def backward(ctx, g_out, _g_sim):
+        # closed-form softmax-attention gradient written with differentiable torch ops
+        q, k, v = ctx.saved_tensors
+        b, t, c = q.shape
+        h, d = 4, c // 4
+        scale = c ** -0.5
+        split = lambda z: z.reshape(b, t, h, d).permute(0, 2, 1, 3)  # noqa: E731
+        merge = lambda z: z.permute(0, 2, 1, 3).reshape(b, t, c)  # noqa: E731
+        qh, kh, vh, go = split(q), split(k), split(v), split(g_out)
+        sim = torch.softmax(qh @ kh.transpose(-1, -2) * scale, dim=-1)
+        g_v = sim.transpose(-1, -2) @ go
+        g_sim = go @ vh.transpose(-1, -2)
+        g_logit = sim * (g_sim - (g_sim * sim).sum(-1, keepdim=True)) * scale
+        g_q = g_logit @ kh
+        g_k = g_logit.transpose(-1, -2) @ qh
+        return merge(g_q), merge(g_k), merge(g_v)
+
+
+def attn_core_reference(q, k, v):
+    """Same math with torch ops (used for the recompute backward only)."""
+    b, t, c = q.shape
+    h, d = 4, c // 4
+    qh = q.reshape(b, t, h, d).permute(0, 2, 1, 3)
+    kh = k.reshape(b, t, h, d).permute(0, 2, 1, 3)
+    vh = v.reshape(b, t, h, d).permute(0, 2, 1, 3)
+    sim = torch.softmax(qh @ kh.transpose(-1, -2) * (c ** -0.5), dim=-1)
+    out = (sim @ vh).permute(0, 2, 1, 3).reshape(b, t, c)
+    return out, sim
+
+
+def attn_core(q, k, v):
+    if q.dtype != torch.float32 or q.shape[1] != 16 or q.shape[2] != 128:
+        return attn_core_reference(q, k, v)  # f64 gradcheck / unusual token counts
+    return AttnCore.apply(q, k, v)
