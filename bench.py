@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: 256^2 images/sec of the full G+D train step (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A "step" is one iteration of the reference's training loop (train_spatial_query.py:166-306):
+D step (+ lazy R1 when i % 16 == 0), G step (+ lazy path-length regularisation when i % 4 == 0),
+EMA.  Per-rank batch 16, synthetic images / latents, random-init weights (same seed on all ranks),
+weak scaling.  Prints ONE JSON line on rank 0.
+
+  value     device-resident inputs, CUDA-event timed, max over ranks
+  e2e       the same steps through Trainer.step_from_host: pinned host images copied H2D and the
+            loss scalars read back D2H inside the timed region
+  roofline  dominant kernel of the step, measured live with CUDA events in one instrumented step
+  cpu_baseline  the oracle's CPU train iteration on a bounded sample (rank 0, N=1)
+
+--impl reference times the CPU port of the reference loop (the reference itself is CUDA-only
+and has no tests or CPU path: SURVEY.md facts 7, 9) on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "images_per_sec_256_gd_train_step"
+UNIT = "img/s"
+WORKLOAD = "G+D full train step 256^2, batch=16/GPU, num_trans=8, synthetic images (BASELINE configs[1])"
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "tf_burst": p["bf16_tflops"],
+                "tf_sustained": p["bf16_tflops_sustained"], "source": "MEASURED_PEAKS.json"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        with open(self.path) as f:
+            for line in f:
+                parts = [x.strip() for x in line.split(",")]
+                if len(parts) < 9:
+                    continue
+                try:
+                    sm.append(float(parts[1]))
+                    smax.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for nm, val in zip(names, parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------ kernel accounting
+class KernelMeter:
+    """Wraps the ctypes wrappers of transeditor_b200.lib for ONE instrumented step: a CUDA event pair
+    around every launch (on torch's current stream, the stream the kernels are enqueued on) plus the
+    algorithmic FLOPs / bytes of the call (DESIGN.md gives the formulas)."""
+
+    def __init__(self):
+        self.records = []
+        self._saved = {}
+
+    @staticmethod
+    def _work(name, args):
+        es = lambda t: t.element_size()  # noqa: E731
+        if name in ("conv2d_simt", "conv2d_wgrad_simt"):
+            g = args[-1]
+            macs = g.batch * g.cout * g.cin * g.kh * g.kw * g.hout * g.wout / (g.up * g.up)
+            t = args[1]
+            byts = es(t) * (g.batch * g.cin * g.hin * g.win + g.batch * g.cout * g.hout * g.wout
+                            + g.cout * g.cin * g.kh * g.kw)
+            return 2.0 * macs, float(byts)
+        if name == "fused_bias_act":
+            return 0.0, 2.0 * args[1].numel() * es(args[1])
+        if name == "fused_bias_act_bwd":
+            return 0.0, 3.0 * args[2].numel() * es(args[2])
+        if name == "upfirdn2d":
+            return 0.0, float((args[0].numel() + args[1].numel()) * es(args[1]))
+        if name == "adam_ema":
+            return 0.0, 7.0 * args[0].numel() * 4
+        return 0.0, 0.0
+
+    def install(self):
+        from transeditor_b200 import lib
+        for name in ("fused_bias_act", "fused_bias_act_bwd", "upfirdn2d", "conv2d_simt",
+                     "conv2d_wgrad_simt", "adam_ema", "attn_core", "conv2d_tc"):
+            fn = getattr(lib, name)
+            self._saved[name] = fn
+
+            def wrapped(*args, _fn=fn, _name=name):
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                _fn(*args)
+                e1.record()
+                flops, byts = self._work(_name, args)
+                self.records.append((_name, e0, e1, flops, byts))
+            setattr(lib, name, wrapped)
+
+    def uninstall(self):
+        from transeditor_b200 import lib
+        for name, fn in self._saved.items():
+            setattr(lib, name, fn)
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for name, e0, e1, flops, byts in self.records:
+            a = agg.setdefault(name, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            a["launches"] += 1
+            a["ms"] += e0.elapsed_time(e1)
+            a["flops"] += flops
+            a["bytes"] += byts
+        return agg
+
+
+def roofline_from(agg, peaks):
+    if not agg:
+        return None, {}
+    total = sum(a["ms"] for a in agg.values())
+    top = max(agg, key=lambda k: agg[k]["ms"])
+    a = agg[top]
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(top)
+    if a["flops"] > 0:
+        achieved = a["flops"] / (a["ms"] * 1e-3) / 1e12
+        peak = peaks["tf_sustained"]
+        roof = {"kernel": "te_" + top, "bound": "tensor", "achieved": round(achieved, 2), "peak": peak,
+                "unit": "TFLOP/s", "frac": round(achieved / peak, 4), "traffic": traffic,
+                "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a step)",
+                "launches": a["launches"], "avg_launch_ms": round(a["ms"] / a["launches"], 4),
+                "share_of_kernel_time": round(a["ms"] / total, 3)}
+    else:
+        achieved = a["bytes"] / (a["ms"] * 1e-3) / 1e9
+        peak = peaks["hbm_gbs"]
+        roof = {"kernel": "te_" + top, "bound": "hbm", "achieved": round(achieved, 1), "peak": peak,
+                "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
+                "peak_source": peaks["source"] + " hbm_gbs",
+                "launches": a["launches"], "avg_launch_ms": round(a["ms"] / a["launches"], 4),
+                "share_of_kernel_time": round(a["ms"] / total, 3)}
+    table = {}
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+        row = {"launches": v["launches"], "ms": round(v["ms"], 3), "share": round(v["ms"] / total, 3)}
+        if v["flops"] > 0:
+            row["tflops"] = round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2)
+        if v["bytes"] > 0:
+            row["gbs"] = round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1)
+        table["te_" + k] = row
+    return roof, table
+
+
+# ------------------------------------------------------------------------------ CPU baseline / reference arm
+def cpu_train_rate(steps, warmup, batch=1, seconds_cap=None):
+    """images/sec of the oracle's CPU train iteration on a bounded sample (batch `batch` per step)."""
+    from oracle.train_cpu import CpuTrainer
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    tr = CpuTrainer(size=256, batch=batch)
+    tr.it = 1  # warm-up steps without the lazy regularisers
+    real = torch.rand(batch, 3, 256, 256) * 2 - 1
+    for _ in range(warmup):
+        tr.step(real)
+    tr.it = 0
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        tr.step(real)
+        done += 1
+        if seconds_cap and time.perf_counter() - t0 > seconds_cap:
+            break
+    dt = time.perf_counter() - t0
+    return done * batch / dt, cores, done, dt
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    rate, cores, done, dt = cpu_train_rate(args.steps, min(args.warmup, 1), batch=1)
+    sample = ("oracle CPU port of the train loop (oracle/train_cpu.py), 256^2, batch 1 per step, "
+              "%d timed steps incl. lazy R1 (i%%16==0) and path (i%%4==0), fp32, %d torch threads" % (done, cores))
+    line = {"impl": "reference", "metric": METRIC, "value": round(rate, 4), "unit": UNIT,
+            "n_gpus": args.gpus, "steps": done, "warmup": min(args.warmup, 1),
+            "ms_per_step": round(dt / done * 1e3, 1), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": "batch 1 per step on host cores"},
+            "cpu_baseline": {"value": round(rate, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": round(rate, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------ our arm
+def run_ours(args, rank, local_rank, world):
+    import torch.distributed as dist
+    from transeditor_b200 import lib
+    from transeditor_b200.train_step import TrainConfig, Trainer
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = TrainConfig(size=args.size, batch=args.batch)
+    trainer = Trainer(cfg, dev, seed=0)
+
+    gen = torch.Generator().manual_seed(4321 + rank)
+    real_host = (torch.rand(cfg.batch, 3, cfg.size, cfg.size, generator=gen) * 2 - 1).pin_memory()
+    real_dev = real_host.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, arg, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.launch_count
+        e0.record()
+        for _ in range(steps):
+            fn(arg)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), lib.launch_count - l0
+
+    for _ in range(args.warmup):
+        trainer.step(real_dev)
+    # align the lazy-regulariser cadence so every run times the same mix
+    trainer.iteration = 0
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, launches = timed(trainer.step, real_dev, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    trainer.iteration = 0
+    ms_e2e, _ = timed(trainer.step_from_host, real_host, args.steps)
+
+    # one instrumented step (plain D+G, plus the lazy regularisers) for the per-kernel roofline
+    meter = KernelMeter()
+    meter.install()
+    trainer.iteration = 0
+    trainer.step(real_dev)
+    meter.uninstall()
+    roof, table = roofline_from(meter.summary(), _peaks())
+
+    images = args.steps * cfg.batch * world
+    line = {"metric": METRIC, "value": round(images / (ms * 1e-3), 3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": cfg.batch * world, "per_gpu_batch": cfg.batch,
+                       "size": cfg.size, "num_trans": cfg.num_trans, "parallelism": "dp%d" % world,
+                       "precision": "fp32 storage and arithmetic (parity mode)",
+                       "lazy_regularisers": "R1 on i%16==0, path-length on i%4==0, cadence restarted at i=0 "
+                                            "for the timed region",
+                       "l2": "no explicit flush: each step streams several GB of activations, far above the 126 MB L2"},
+            "e2e": {"value": round(images / (ms_e2e * 1e-3), 3), "unit": UNIT,
+                    "h2d_bytes_per_step": real_host.numel() * 4, "d2h_bytes_per_step": 4 * len(trainer.losses),
+                    "ms_per_step": round(ms_e2e / args.steps, 3)},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": table}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, cores, done, dt = cpu_train_rate(2, 0, batch=1, seconds_cap=30)
+        line["cpu_baseline"] = {"value": round(rate, 4), "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "oracle CPU port (oracle/train_cpu.py), 256^2, batch 1 per step, %d steps "
+                                          "(first incl. R1 + path regularisers), %.1f s" % (done, dt)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, local_rank, world)
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

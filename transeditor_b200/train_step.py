@@ -1,0 +1,276 @@
+"""Data-parallel G+D train step (the loop body of train_spatial_query.py:166-306) as an engine.
+
+One process per GPU.  What the reference does with DistributedDataParallel + torch.optim.Adam +
+a Python EMA loop, this does with
+
+  * parameters, gradients, Adam moments and the EMA copy living in FLAT f32 buffers (one per
+    model), so the gradient exchange is ONE NCCL all-reduce per optimiser step (G 172 MB,
+    D 115 MB) and the optimiser + EMA is ONE te_adam_ema launch instead of ~650 tiny kernels;
+  * the same losses, lazy-regularisation cadence and learning-rate / beta corrections
+    (train_spatial_query.py:69-105,196-250,461-473).
+
+Sharding: batch only (replicated weights, per-rank batch a multiple of 4 so the minibatch-stddev
+groups match DDP semantics, model_spatial_query.py:845-852).  The only data-path collective is
+the gradient sum (averaged by world size like DDP).
+"""
+import math
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from . import lib
+from .model import Discriminator, Generator
+
+
+class TrainConfig:
+    """Defaults = train_spatial_query.py:379-415."""
+
+    def __init__(self, **kw):
+        self.size = 256
+        self.batch = 16
+        self.latent = 512
+        self.para_num = 16
+        self.channel_multiplier = 2
+        self.num_trans = 8
+        self.pixel_norm_op_dim = 1
+        self.inject_noise = False
+        self.lr = 0.002
+        self.r1 = 10.0
+        self.path_regularize = 2.0
+        self.path_batch_shrink = 2
+        self.d_reg_every = 16
+        self.g_reg_every = 4
+        self.ema_decay = 0.5 ** (32 / (10 * 1000))  # :157
+        for k, v in kw.items():
+            if not hasattr(self, k):
+                raise TypeError("unknown TrainConfig field %r" % k)
+            setattr(self, k, v)
+
+    @property
+    def token(self):
+        return 2 * (int(math.log2(self.size)) - 1)  # :432
+
+
+class FlatParams:
+    """Re-homes a module's parameters into one contiguous buffer (parameters become views) with a
+    matching flat gradient buffer.  `tail_groups` is a list of predicates on the parameter name;
+    matching parameters are placed, group by group, after everything else so that an optimiser
+    step can leave them out (parameters the reference's Adam skips because their .grad is None)."""
+
+    def __init__(self, module, tail_groups=()):
+        named = list(module.named_parameters())
+        buckets = [[] for _ in range(len(tail_groups) + 1)]
+        for name, p in named:
+            for gi, pred in enumerate(tail_groups):
+                if pred(name):
+                    buckets[gi + 1].append((name, p))
+                    break
+            else:
+                buckets[0].append((name, p))
+        ordered = [x for b in buckets for x in b]
+        # every segment starts on a 16-byte boundary so the vectorised optimiser can run on ranges
+        self.offsets, off = {}, 0
+        self.group_end = []
+        for b in buckets:
+            for name, p in b:
+                self.offsets[name] = off
+                off += (p.numel() + 3) // 4 * 4
+            self.group_end.append(off)
+        self.numel = off
+        dev, dt = ordered[0][1].device, ordered[0][1].dtype
+        self.data = torch.zeros(off, dtype=dt, device=dev)
+        self.grad = torch.zeros(off, dtype=dt, device=dev)
+        self.params = []
+        for name, p in ordered:
+            o, n = self.offsets[name], p.numel()
+            self.data[o:o + n].copy_(p.data.reshape(-1))
+            p.data = self.data[o:o + n].view(p.shape)
+            p.grad = self.grad[o:o + n].view(p.shape)
+            self.params.append((name, p))
+
+    def rebind_grads(self):
+        for name, p in self.params:
+            o, n = self.offsets[name], p.numel()
+            if p.grad is None or p.grad.data_ptr() != self.grad[o:o + n].data_ptr():
+                p.grad = self.grad[o:o + n].view(p.shape)
+
+
+class FlatAdam:
+    """torch.optim.Adam semantics on a FlatParams through te_adam_ema."""
+
+    def __init__(self, flat, lr, betas, eps=1e-8):
+        self.flat = flat
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.m = torch.zeros_like(flat.data)
+        self.v = torch.zeros_like(flat.data)
+        # per-range step counters: Adam's bias correction counts the updates a parameter received
+        self.steps = [0] * len(flat.group_end)
+
+    def step(self, n_groups, grad_scale=1.0):
+        """Update parameter groups [0, n_groups) (the main group is group 0)."""
+        lo = 0
+        for gi in range(n_groups):
+            hi = self.flat.group_end[gi]
+            if hi > lo:
+                self.steps[gi] += 1
+                sl = slice(lo, hi)
+                lib.adam_ema(self.flat.data[sl], self.flat.grad[sl], self.m[sl], self.v[sl], None,
+                             self.lr, self.betas[0], self.betas[1], self.eps, self.steps[gi], 0.0,
+                             grad_scale)
+            lo = hi
+
+
+def d_logistic_loss(real_pred, fake_pred):
+    """train_spatial_query.py:69-73"""
+    return F.softplus(-real_pred).mean() + F.softplus(fake_pred).mean()
+
+
+def d_r1_loss(real_pred, real_img):
+    """train_spatial_query.py:76-83"""
+    (grad_real,) = torch.autograd.grad(outputs=real_pred.sum(), inputs=real_img, create_graph=True)
+    return grad_real.pow(2).reshape(grad_real.shape[0], -1).sum(1).mean()
+
+
+def g_nonsaturating_loss(fake_pred):
+    """train_spatial_query.py:86-89"""
+    return F.softplus(-fake_pred).mean()
+
+
+def g_path_regularize(fake_img, latents, mean_path_length, decay=0.01):
+    """train_spatial_query.py:92-105"""
+    noise = torch.randn_like(fake_img) / math.sqrt(fake_img.shape[2] * fake_img.shape[3])
+    (grad,) = torch.autograd.grad(outputs=(fake_img * noise).sum(), inputs=latents, create_graph=True)
+    path_lengths = torch.sqrt(grad.pow(2).sum(2).mean(1))
+    path_mean = mean_path_length + decay * (path_lengths.mean() - mean_path_length)
+    path_penalty = (path_lengths - path_mean).pow(2).mean()
+    return path_penalty, path_mean.detach(), path_lengths
+
+
+def _set_requires_grad(flat, flag):
+    for _, p in flat.params:
+        p.requires_grad_(flag)
+
+
+class Trainer:
+    def __init__(self, cfg, device, seed=0):
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        torch.manual_seed(seed)  # identical initial weights on every rank
+        mk = lambda: Generator(cfg.size, cfg.latent, cfg.latent, cfg.token,  # noqa: E731
+                               channel_multiplier=cfg.channel_multiplier,
+                               layer_noise_injection=cfg.inject_noise, n_trans=cfg.num_trans,
+                               pixel_norm_op_dim=cfg.pixel_norm_op_dim)
+        self.generator = mk().to(self.device)
+        self.discriminator = Discriminator(cfg.size, channel_multiplier=cfg.channel_multiplier).to(self.device)
+        self.g_ema = mk().to(self.device).eval()
+        rgb_bias = lambda n: n.startswith("to_rgb") and n.endswith(".bias") and ".conv." not in n  # noqa: E731
+        noise_w = lambda n: n.endswith("noise.weight")  # noqa: E731
+        tails = [rgb_bias] if cfg.inject_noise else [rgb_bias, noise_w]
+        self.g_flat = FlatParams(self.generator, tails)
+        self.d_flat = FlatParams(self.discriminator)
+        self.ema_flat = FlatParams(self.g_ema, tails)
+        self.ema_flat.data.copy_(self.g_flat.data)  # accumulate(g_ema, generator, 0), :456
+        for _, p in self.ema_flat.params:
+            p.requires_grad_(False)
+            p.grad = None
+        self.ema_flat.grad = None
+        g_ratio = cfg.g_reg_every / (cfg.g_reg_every + 1)
+        d_ratio = cfg.d_reg_every / (cfg.d_reg_every + 1)
+        self.g_optim = FlatAdam(self.g_flat, cfg.lr * g_ratio, (0 ** g_ratio, 0.99 ** g_ratio))
+        self.d_optim = FlatAdam(self.d_flat, cfg.lr * d_ratio, (0 ** d_ratio, 0.99 ** d_ratio))
+        torch.manual_seed(1234 + self.rank)  # per-rank latent / noise streams
+        self.mean_path_length = torch.zeros((), device=self.device)
+        self.iteration = 0
+        self.losses = {}
+
+    # ------------------------------------------------------------------ pieces of one iteration
+    def _latents(self, n):
+        c = self.cfg
+        z = torch.randn(n, c.latent, c.para_num, device=self.device)  # utils/sample.py:19
+        p = torch.randn(n, c.latent, c.para_num, device=self.device)  # utils/sample.py:10
+        return z, p
+
+    def _reduce_and_step(self, flat, optim, n_groups):
+        if self.world > 1:
+            dist.all_reduce(flat.grad, op=dist.ReduceOp.SUM)
+        optim.step(n_groups, grad_scale=1.0 / self.world)
+
+    def d_step(self, real_img):
+        _set_requires_grad(self.g_flat, False)
+        _set_requires_grad(self.d_flat, True)
+        z, p = self._latents(self.cfg.batch)
+        fake_img, _, _ = self.generator(z, p)
+        fake_pred = self.discriminator(fake_img)
+        real_pred = self.discriminator(real_img)
+        d_loss = d_logistic_loss(real_pred, fake_pred)
+        self.d_flat.grad.zero_()
+        d_loss.backward()
+        self._reduce_and_step(self.d_flat, self.d_optim, 1)
+        self.losses.update(d=d_loss.detach(), real_score=real_pred.mean().detach(),
+                           fake_score=fake_pred.mean().detach())
+
+    def d_regularize(self, real_img):
+        real_img = real_img.detach().requires_grad_(True)
+        real_pred = self.discriminator(real_img)
+        r1_loss = d_r1_loss(real_pred, real_img)
+        self.d_flat.grad.zero_()
+        (self.cfg.r1 / 2 * r1_loss * self.cfg.d_reg_every + 0 * real_pred[0]).backward()
+        self._reduce_and_step(self.d_flat, self.d_optim, 1)
+        self.losses["r1"] = r1_loss.detach()
+
+    def g_step(self):
+        _set_requires_grad(self.g_flat, True)
+        _set_requires_grad(self.d_flat, False)
+        z, p = self._latents(self.cfg.batch)
+        fake_img, _, _ = self.generator(z, p)
+        g_loss = g_nonsaturating_loss(self.discriminator(fake_img))
+        self.g_flat.grad.zero_()
+        g_loss.backward()
+        # noise strengths receive no gradient when noise injection is off (reference: grad None)
+        self._reduce_and_step(self.g_flat, self.g_optim, 2)
+        self.losses["g"] = g_loss.detach()
+
+    def g_regularize(self):
+        c = self.cfg
+        n = max(1, c.batch // c.path_batch_shrink)
+        z, p = self._latents(n)
+        fake_img, latents, _ = self.generator(z, p, return_latents=True)
+        path_loss, self.mean_path_length, path_lengths = g_path_regularize(
+            fake_img, latents, self.mean_path_length)
+        self.g_flat.grad.zero_()
+        weighted = c.path_regularize * c.g_reg_every * path_loss
+        if c.path_batch_shrink:
+            weighted = weighted + 0 * fake_img[0, 0, 0, 0]
+        weighted.backward()
+        # to_rgb biases get no gradient from the path penalty -> skipped like Adam skips grad=None
+        self._reduce_and_step(self.g_flat, self.g_optim, 1)
+        self.losses.update(path=path_loss.detach(), path_length=path_lengths.mean().detach())
+
+    def ema_update(self):
+        """accumulate(g_ema, g_module, 0.5 ** (32 / 10000)), train_spatial_query.py:56-61,294"""
+        self.ema_flat.data.lerp_(self.g_flat.data, 1.0 - self.cfg.ema_decay)
+
+    # ------------------------------------------------------------------ one iteration
+    def step(self, real_img):
+        """real_img: [B,3,S,S] on the device, range [-1,1]."""
+        i = self.iteration
+        self.d_step(real_img)
+        if i % self.cfg.d_reg_every == 0:
+            self.d_regularize(real_img)
+        self.g_step()
+        if i % self.cfg.g_reg_every == 0:
+            self.g_regularize()
+        self.ema_update()
+        self.iteration += 1
+        return self.losses
+
+    def step_from_host(self, real_pinned):
+        """End-to-end form: host (pinned) images in, host loss scalars out."""
+        real = real_pinned.to(self.device, non_blocking=True)
+        losses = self.step(real)
+        keys = sorted(losses)
+        host = torch.stack([losses[k].float() for k in keys]).cpu()  # D2H + sync, like the .item()s at :298-306
+        return dict(zip(keys, host.tolist()))
