@@ -425,3 +425,36 @@ def attn_core(q, k, v):
     if q.dtype != torch.float32 or q.shape[1] != 16 or q.shape[2] != 128:
         return attn_core_reference(q, k, v)  # f64 gradcheck / unusual token counts
     return AttnCore.apply(q, k, v)
+
+
+# --------------------------------------------------------------------------------------------
+# tensor-core (tcgen05) convolution, bf16 channels-last
+
+
+def pack_weight_tc(w):
+    """[O, I, kh, kw] (any float dtype) -> tap-major bf16 [kh*kw, O, I] (K contiguous) for te_conv2d_tc.
+    A leading batch dim ([B, O, I, kh, kw] -> [B, kh*kw, O, I]) gives per-sample weights."""
+    if w.dim() == 5:
+        b, o, i, kh, kw = w.shape
+        return w.permute(0, 3, 4, 1, 2).reshape(b, kh * kw, o, i).to(torch.bfloat16).contiguous()
+    o, i, kh, kw = w.shape
+    return w.permute(2, 3, 0, 1).reshape(kh * kw, o, i).to(torch.bfloat16).contiguous()
+
+
+def conv2d_tc(x, w_packed, ksize, out_scale=None, bias=None, act=False):
+    """x: [B, Cin, H, W] bf16 with channels-last strides; stride 1, padding ksize//2.
+    Returns [B, Cout, H, W] bf16 channels-last.  Not differentiable by itself."""
+    lib.require_cuda(x, w_packed, out_scale, bias)
+    if x.dtype != torch.bfloat16:
+        raise TypeError("conv2d_tc: bf16 activations required, got %s" % x.dtype)
+    b, cin, h, w = x.shape
+    x = x.contiguous(memory_format=torch.channels_last)
+    per_sample = w_packed.dim() == 4
+    cout = w_packed.shape[-2]
+    if w_packed.shape[-1] != cin or w_packed.shape[-3] != ksize * ksize:
+        raise RuntimeError("conv2d_tc: weight %s does not match Cin=%d k=%d" % (tuple(w_packed.shape), cin, ksize))
+    y = torch.empty((b, cout, h, w), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+    f32 = lambda t: None if t is None else t.to(torch.float32).contiguous()  # noqa: E731
+    lib.conv2d_tc(y, x, w_packed, f32(out_scale), f32(bias), b, h, w, cin, cout, ksize, ksize,
+                  1 if act else 0, ksize * ksize * cout * cin if per_sample else 0)
+    return y
