@@ -286,6 +286,14 @@ def run_ours(args, rank, local_rank, world):
 
     for _ in range(args.warmup):
         trainer.step(real_dev)
+    if args.ncu:
+        trainer.iteration = 1  # a plain D step + G step
+        for _ in range(args.steps):
+            trainer.step(real_dev)
+        torch.cuda.synchronize()
+        if rank == 0:
+            print("ncu aid: %d launches per step" % (lib.launch_count // (args.warmup + args.steps)))
+        return
     # align the lazy-regulariser cadence so every run times the same mix
     trainer.iteration = 0
     sampler = ClockSampler(local_rank)
@@ -337,8 +345,10 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu", action="store_true",
+                    help="profiling aid: W warm-up + K steps only, prints no bench line (numbers under ncu are never bench values)")
     args = ap.parse_args()
-    if args.warmup < 3 and args.impl == "ours":
+    if args.warmup < 3 and args.impl == "ours" and not args.ncu:
         args.warmup = 3
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
