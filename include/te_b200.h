@@ -125,15 +125,46 @@ int te_adam_ema(float* p, const float* g, float* m, float* v, float* ema, int64_
 
 /* ---------------------------------------------------------------------------------------------
  * Tensor-core (tcgen05 + TMA + TMEM) implicit-GEMM convolution, bf16 operands / f32 accumulate,
- * channels-last.  The speed path of ModulatedConv2d / EqualConv2d (same reference lines as
- * te_conv2d_simt).  See DESIGN.md §kernels.
- *   x  [B, Hin, Win, Cin] bf16 ; w [kh*kw, Cout, Cin] bf16 (tap-major, K contiguous)
- *   y  [B, Hout, Wout, Cout] bf16
- *   y = act( out_scale[b,o] * conv(x, w)[b,oy,ox,o] + bias[o] ), stride 1, pad = k/2
- * in_scale is NOT applied here (the modulation is folded into x by the caller's producer
- * kernel or into per-sample weights: w_bstride != 0 selects w + b*w_bstride for sample b).
- * Requirements: Cin % 64 == 0, Cout % 64 == 0.
+ * channels-last: the speed path of ModulatedConv2d / EqualConv2d (same reference call sites as
+ * te_conv2d_simt: model_spatial_query.py:177-183,318,327,333) and of their data gradients.
+ *
+ * Geometry = a TAP TABLE over an ANCHOR grid (a = (ay, ax), 0 <= ay < grid_h, 0 <= ax < grid_w):
+ *   y[b, ay*out_stride + out_off_y, ax*out_stride + out_off_x, :] =
+ *       act( out_scale[b,:] * SUM_t  x[b, ay*in_stride + tap_dy[t], ax*in_stride + tap_dx[t], :] . W[tap_w[t]]^T
+ *            + bias[:] )
+ *   x [batch, hin, win, cin] bf16 ; W [w_slices, cout, cin] bf16 (K contiguous) ; y [batch, hout, wout, cout]
+ *   bf16 (out_f32: float).  Reads outside x are zeros (that is the padding).
+ *   conv2d stride 1:      in_stride 1, out_stride 1, taps (ky-p, kx-p)
+ *   conv2d stride 2:      in_stride 2, out_stride 1, taps (ky, kx)
+ *   conv_transpose2d s2:  in_stride 1, out_stride 2, one call per output parity class (out_off)
+ * in_scale is not applied here: the caller folds the modulation into x or into per-sample weights
+ * (w_bstride != 0: sample b uses W + b*w_bstride, requires >= 128 anchors per sample).
+ * Requirements: cin % 8 == 0, cout % 8 == 0, 16-byte aligned pointers.
  */
+typedef struct {
+  int batch, hin, win, cin;
+  int hout, wout, cout;
+  int ntaps;                 /* 1..9 */
+  int tap_dy[9], tap_dx[9];  /* input offset of tap t */
+  int tap_w[9];              /* weight slice of tap t */
+  int w_slices;              /* slices in W (per sample when w_bstride != 0) */
+  int in_stride, out_stride, out_off_y, out_off_x;
+  int grid_h, grid_w;
+  int act;                   /* 0 identity, 1 leaky_relu(0.2)*sqrt(2) */
+  int out_f32;
+  int64_t w_bstride;
+} te_tc_conv_desc;
+
+int te_conv_tc(void* y, const void* x, const void* w, const float* out_scale, const float* bias,
+               const te_tc_conv_desc* d, void* stream);
+
+/* Weight gradient for the same geometry (act/out_f32/w_bstride ignored):
+ *   gw[tap_w[t]][m][n] += SUM_{b, a} g[b, a*out_stride + out_off, m] * x[b, a*in_stride + tap_d[t], n]
+ * g [batch, hout, wout, cout] bf16, x [batch, hin, win, cin] bf16, gw [w_slices, cout, cin] FLOAT32,
+ * accumulated (caller zeroes it).  Replaces autograd's convolution weight gradient. */
+int te_conv_wgrad_tc(float* gw, const void* g, const void* x, const te_tc_conv_desc* d, void* stream);
+
+/* Convenience form: stride 1, padding k/2, kh = kw in {1,3}, bf16 output. */
 int te_conv2d_tc(void* y, const void* x, const void* w, const float* out_scale, const float* bias,
                  int batch, int hin, int win, int cin, int cout, int kh, int kw, int act,
                  int64_t w_bstride, void* stream);

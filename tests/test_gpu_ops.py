@@ -345,5 +345,5 @@ def test_adam_ema_matches_torch_adam():
         q.grad = g.clone()
         opt.step()
         ema_ref.mul_(0.998).add_(q.detach(), alpha=0.002)
-    assert (p - q.detach()).abs().max().item() < 1e-6
-    assert (ema - ema_ref).abs().max().item() < 1e-6
+    assert (p - q.detach()).abs().max().item() < 5e-6
+    assert (ema - ema_ref).abs().max().item() < 5e-6

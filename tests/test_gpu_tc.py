@@ -1,0 +1,148 @@
+"""Tensor-core (tcgen05) convolution engine vs torch references computed in f32 from the same
+bf16-rounded operands: every mode (stride-1, stride-2, transposed stride-2), data gradients, weight
+gradients (MN-major tcgen05 kernel) and second order.  Tolerances = bf16 output rounding."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+def _bf(x):
+    return x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+
+
+def _ref(x, w, kind):
+    if kind == "s1":
+        return F.conv2d(x, w, padding=w.shape[2] // 2)
+    if kind == "down":
+        return F.conv2d(x, w, stride=2)
+    return F.conv_transpose2d(x, w.transpose(0, 1), stride=2)
+
+
+def _ours(x, w, kind):
+    from transeditor_b200 import tc
+    if kind == "up":
+        return tc.conv_transpose2d(x, w)
+    return tc.conv2d(x, w, stride=1 if kind == "s1" else 2)
+
+
+def _close(a, r, what, rel=1.2e-2):
+    a, r = a.float(), r.float()
+    tol = rel * max(1.0, r.abs().max().item())
+    err = (a - r).abs().max().item()
+    assert err <= tol, "%s: err %.3e tol %.3e" % (what, err, tol)
+
+
+FWD_CASES = [
+    # b, cin, cout, h, w, k, kind
+    (2, 64, 64, 16, 16, 3, "s1"), (3, 128, 64, 8, 8, 3, "s1"), (5, 64, 128, 4, 4, 3, "s1"),
+    (2, 8, 64, 32, 32, 1, "s1"), (2, 64, 8, 32, 32, 1, "s1"), (1, 576, 512, 4, 4, 3, "s1"),
+    (2, 64, 64, 17, 17, 3, "down"), (2, 128, 64, 33, 33, 3, "down"), (2, 64, 128, 15, 15, 1, "down"),
+    (3, 64, 64, 9, 9, 3, "down"), (2, 64, 64, 8, 8, 3, "up"), (2, 128, 64, 16, 16, 3, "up"),
+    (5, 64, 64, 4, 4, 3, "up"), (2, 64, 64, 8, 8, 1, "up"), (1, 64, 64, 64, 64, 3, "up"),
+    (1, 64, 64, 129, 129, 3, "down"),
+]
+
+
+@pytest.mark.parametrize("case", FWD_CASES)
+def test_tc_forward_modes(case):
+    b, cin, cout, h, w_, k, kind = case
+    x = _rand(b, cin, h, w_, seed=1)
+    w = _rand(cout, cin, k, k, seed=2, scale=1.0 / math.sqrt(cin * k * k))
+    xb, wb = _bf(x), w.to(torch.bfloat16).float()
+    with torch.no_grad():
+        y = _ours(xb, w, kind)
+    ref = _ref(xb.float(), wb, kind)
+    assert y.shape == ref.shape and y.dtype == torch.bfloat16
+    _close(y, ref, "fwd %s" % (case,))
+
+
+GRAD_CASES = [
+    (2, 64, 64, 16, 16, 3, "s1"), (2, 128, 64, 8, 8, 3, "s1"), (2, 64, 128, 32, 32, 1, "s1"),
+    (2, 64, 64, 17, 17, 3, "down"), (2, 64, 128, 15, 15, 1, "down"), (2, 64, 64, 33, 33, 3, "down"),
+    (2, 64, 64, 8, 8, 3, "up"), (2, 128, 64, 16, 16, 3, "up"), (4, 64, 64, 4, 4, 3, "up"),
+    (2, 8, 64, 16, 16, 1, "s1"), (2, 64, 8, 16, 16, 1, "s1"),
+]
+
+
+@pytest.mark.parametrize("case", GRAD_CASES)
+def test_tc_data_gradient(case):
+    """dgrad runs the SAME kernel with transposed / flipped weight slices (mode.adjoint)."""
+    b, cin, cout, h, w_, k, kind = case
+    x = _rand(b, cin, h, w_, seed=3)
+    w = _rand(cout, cin, k, k, seed=4, scale=1.0 / math.sqrt(cin * k * k))
+    xb = _bf(x).requires_grad_(True)
+    y = _ours(xb, w, kind)
+    gy = _bf(_rand(*y.shape, seed=5))
+    (gx,) = torch.autograd.grad(y, xb, gy)
+    xr = xb.detach().float().requires_grad_(True)
+    yr = _ref(xr, w.to(torch.bfloat16).float(), kind)
+    (gxr,) = torch.autograd.grad(yr, xr, gy.float())
+    assert gx.shape == gxr.shape
+    _close(gx, gxr, "dgrad %s" % (case,))
+
+
+@pytest.mark.parametrize("case", GRAD_CASES)
+def test_tc_weight_gradient(case):
+    b, cin, cout, h, w_, k, kind = case
+    x = _rand(b, cin, h, w_, seed=6)
+    w = _rand(cout, cin, k, k, seed=7, scale=1.0 / math.sqrt(cin * k * k)).requires_grad_(True)
+    xb = _bf(x)
+    y = _ours(xb, w, kind)
+    gy = _bf(_rand(*y.shape, seed=8))
+    (gw,) = torch.autograd.grad(y, w, gy)
+    wr = w.detach().clone().requires_grad_(True)
+    yr = _ref(xb.float(), wr, kind)
+    (gwr,) = torch.autograd.grad(yr, wr, gy.float())
+    assert gw.shape == gwr.shape and gw.dtype == torch.float32
+    _close(gw, gwr, "wgrad %s" % (case,), rel=5e-3)
+
+
+@pytest.mark.parametrize("case", [(2, 64, 64, 16, 16, 3, "s1"), (2, 64, 64, 17, 17, 3, "down"),
+                                  (2, 64, 64, 8, 8, 3, "up"), (2, 64, 128, 15, 15, 1, "down")])
+def test_tc_second_order(case):
+    """R1 / path-length style double backward: grads of <gx, u> + <gw, v> w.r.t. gy, x and w."""
+    b, cin, cout, h, w_, k, kind = case
+    x = _rand(b, cin, h, w_, seed=9)
+    w = _rand(cout, cin, k, k, seed=10, scale=1.0 / math.sqrt(cin * k * k))
+
+    def run(fn, xin, win, cast):
+        xx = xin.clone().requires_grad_(True)
+        ww = win.clone().requires_grad_(True)
+        y = fn(xx, ww, kind)
+        gy = cast(_rand(*y.shape, seed=11)).requires_grad_(True)
+        gx, gw = torch.autograd.grad(y, (xx, ww), gy, create_graph=True)
+        u = cast(_rand(*gx.shape, seed=12))
+        v = _rand(*gw.shape, seed=13)
+        s = (gx.float() * u.float()).sum() + (gw * v).sum()
+        return [t.detach().float() for t in torch.autograd.grad(s, (gy, xx, ww))]
+
+    got = run(_ours, _bf(x), w, _bf)
+    ref = run(_ref, _bf(x).float(), w.to(torch.bfloat16).float(), lambda t: _bf(t).float())
+    for a, r, nm in zip(got, ref, ("h_gy", "h_x", "h_w")):
+        _close(a, r, "%s %s" % (nm, case), rel=2e-2)
+
+
+def test_tc_flagship_wgrad_and_dgrad_shapes():
+    """BASELINE flagship layer 128->128 @256^2 B=16: gradient kernels at full size (linearity check)."""
+    from transeditor_b200 import tc
+    x = _bf(torch.randn(16, 128, 256, 256, device=DEV))
+    w = torch.randn(128, 128, 3, 3, device=DEV) / 34
+    gy = _bf(torch.randn(16, 128, 256, 256, device=DEV))
+    mode = tc.Mode("s1", 3)
+    gw = tc.wgrad_raw(gy, x, mode, (128, 128, 3, 3))
+    gw2 = tc.wgrad_raw(gy[:8], x[:8], mode, (128, 128, 3, 3)) + tc.wgrad_raw(gy[8:], x[8:], mode, (128, 128, 3, 3))
+    assert torch.isfinite(gw).all()
+    assert (gw - gw2).abs().max().item() < 2e-3 * gw.abs().max().item()
+    ref = torch.nn.grad.conv2d_weight(x[:1].float(), (128, 128, 3, 3), gy[:1].float(), padding=1)
+    got = tc.wgrad_raw(gy[:1], x[:1], mode, (128, 128, 3, 3))
+    _close(got, ref, "flagship wgrad sample 0", rel=5e-3)

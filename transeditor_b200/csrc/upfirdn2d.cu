@@ -66,44 +66,85 @@ upfirdn2d_generic(T* __restrict__ out, const T* __restrict__ in, const float* __
 }
 
 // ---- hot case: planes, up = down = 1, FIR zero-extended to 4x4 --------------------------------
-constexpr int FT_W = 128;           // output tile width  (32 threads x 4)
-constexpr int FT_H = 32;            // output tile height ( 8 threads x 4)
-constexpr int FT_IW = FT_W + 3;     // input tile width incl. halo
-constexpr int FT_IH = FT_H + 3;
-constexpr int FT_PITCH = FT_W + 4;  // shared row pitch (multiple of 4 words -> 16-byte LDS)
+// 256 threads arranged threads_x x threads_y (chosen per launch so that odd widths such as 257 split
+// into equal tiles: 257 -> 3 tiles of 88 columns, 22 x 11 threads), each thread a 4x4 output block.
+constexpr int FT_THREADS = 256;
+constexpr int FT_MAX_SMEM_ELEMS = 6144;  // (tile_h + 3) * pitch upper bound for every layout below
+
+struct FirTiling {
+  int threads_x, threads_y, tile_w, tile_h, pitch, tiles_x, tiles_y;
+};
+
+static FirTiling fir_tiling(int out_w, int out_h) {
+  FirTiling t;
+  const int nx = (out_w + 127) / 128;
+  int tw = ((out_w + nx - 1) / nx + 3) / 4 * 4;  // equalised tile width, multiple of 4
+  if (tw < 4) tw = 4;
+  t.threads_x = tw / 4;
+  t.tile_w = tw;
+  t.threads_y = FT_THREADS / t.threads_x;
+  int max_ty = ((out_h + 3) / 4);
+  if (t.threads_y > max_ty) t.threads_y = max_ty;
+  if (t.threads_y < 1) t.threads_y = 1;
+  t.tile_h = t.threads_y * 4;
+  t.pitch = t.tile_w + 4;
+  while ((t.tile_h + 3) * t.pitch > FT_MAX_SMEM_ELEMS) {  // very narrow images: shorten the tile
+    t.threads_y -= 1;
+    t.tile_h = t.threads_y * 4;
+  }
+  t.tiles_x = (out_w + t.tile_w - 1) / t.tile_w;
+  t.tiles_y = (out_h + t.tile_h - 1) / t.tile_h;
+  return t;
+}
 
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(FT_THREADS)
 fir_planes_tiled(T* __restrict__ out, const T* __restrict__ in, const float* __restrict__ fir,
-                 UpfirdnParams p, int tiles_x, int tiles_y, int64_t n_tiles) {
+                 UpfirdnParams p, FirTiling tl, int64_t n_tiles) {
   using A = typename Acc<T>::type;
-  __shared__ __align__(16) A sx[FT_IH][FT_PITCH];
+  extern __shared__ __align__(16) unsigned char fir_smem[];
+  A* sx = reinterpret_cast<A*>(fir_smem);
   __shared__ A sk[4][4];
   if (threadIdx.x < 16) {
     int ky = threadIdx.x >> 2, kx = threadIdx.x & 3;
     // flipped taps, zero-extended on the high side when kh/kw < 4
     sk[ky][kx] = (ky < p.kh && kx < p.kw) ? A(fir[(p.kh - 1 - ky) * p.kw + (p.kw - 1 - kx)]) : A(0);
   }
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const bool vec_store = (p.out_w % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
-                         (sizeof(T) * 4 <= 16);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tx = threadIdx.x % tl.threads_x, ty = threadIdx.x / tl.threads_x;
+  const bool worker = ty < tl.threads_y;
+  const int rows_in = tl.tile_h + 3, cols_in = tl.tile_w + 3;
+  const bool vec_store = (p.out_w % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     int64_t r = tile;
-    const int tcol = int(r % tiles_x); r /= tiles_x;
-    const int trow = int(r % tiles_y); r /= tiles_y;
+    const int tcol = int(r % tl.tiles_x); r /= tl.tiles_x;
+    const int trow = int(r % tl.tiles_y); r /= tl.tiles_y;
     const int64_t plane = r;
-    const int ox0 = tcol * FT_W, oy0 = trow * FT_H;
+    const int ox0 = tcol * tl.tile_w, oy0 = trow * tl.tile_h;
     const int ix0 = ox0 - p.pad_x0, iy0 = oy0 - p.pad_y0;
     const T* src = in + plane * int64_t(p.in_h) * p.in_w;
     __syncthreads();  // previous tile fully consumed (also orders the sk writes)
-    for (int e = threadIdx.x; e < FT_IH * FT_IW; e += 256) {
-      const int ry = e / FT_IW, rx = e - ry * FT_IW;
-      const int iy = iy0 + ry, ix = ix0 + rx;
-      A v = A(0);
-      if (iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w) v = to_acc(src[int64_t(iy) * p.in_w + ix]);
-      sx[ry][rx] = v;
+    // stage the input tile: one warp per row, 32 consecutive columns per step, loads issued in
+    // batches of 5 before the stores so several are in flight per thread
+    for (int ry = warp; ry < rows_in; ry += FT_THREADS / 32) {
+      const int iy = iy0 + ry;
+      const bool row_ok = iy >= 0 && iy < p.in_h;
+      const T* srow = src + int64_t(iy) * p.in_w + ix0;
+      A v[5];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const int c = lane + 32 * j;
+        const int ix = ix0 + c;
+        v[j] = (row_ok && c < cols_in && ix >= 0 && ix < p.in_w) ? to_acc(srow[c]) : A(0);
+      }
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const int c = lane + 32 * j;
+        if (c < cols_in) sx[ry * tl.pitch + c] = v[j];
+      }
     }
     __syncthreads();
+    if (!worker) continue;
     A acc[4][4];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
@@ -111,10 +152,17 @@ fir_planes_tiled(T* __restrict__ out, const T* __restrict__ in, const float* __r
       for (int b = 0; b < 4; ++b) acc[a][b] = A(0);
 #pragma unroll
     for (int ry = 0; ry < 7; ++ry) {
+      const A* rp = sx + (ty * 4 + ry) * tl.pitch + tx * 4;
       A rowv[8];
-      const A* rp = &sx[ty * 4 + ry][tx * 4];
+      if (sizeof(A) == 4) {  // two 16-byte shared loads (pitch and tx*4 are multiples of 4 words)
+        const float4 q0 = *reinterpret_cast<const float4*>(rp);
+        const float4 q1 = *reinterpret_cast<const float4*>(rp + 4);
+        rowv[0] = q0.x; rowv[1] = q0.y; rowv[2] = q0.z; rowv[3] = q0.w;
+        rowv[4] = q1.x; rowv[5] = q1.y; rowv[6] = q1.z; rowv[7] = q1.w;
+      } else {
 #pragma unroll
-      for (int j = 0; j < 7; ++j) rowv[j] = rp[j];
+        for (int j = 0; j < 7; ++j) rowv[j] = rp[j];
+      }
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
         const int ky = ry - a;  // out row a uses input row a+ky
@@ -155,13 +203,13 @@ static int upfirdn2d_typed(void* out_, const void* in_, const float* fir, const 
   const int64_t total = p.major * p.out_h * int64_t(p.out_w) * p.minor;
   if (total == 0) return TE_OK;
   const bool hot = p.up_x == 1 && p.up_y == 1 && p.down_x == 1 && p.down_y == 1 && p.minor == 1 &&
-                   p.kh <= 4 && p.kw <= 4 && p.out_w >= 32 && p.out_h >= 8 && sizeof(T) <= 4;
+                   p.kh <= 4 && p.kw <= 4 && p.out_w >= 16 && p.out_h >= 8 && sizeof(T) <= 4;
   if (hot) {
-    const int tiles_x = (p.out_w + FT_W - 1) / FT_W;
-    const int tiles_y = (p.out_h + FT_H - 1) / FT_H;
-    const int64_t n_tiles = p.major * tiles_x * tiles_y;
+    const FirTiling tl = fir_tiling(p.out_w, p.out_h);
+    const int64_t n_tiles = p.major * tl.tiles_x * tl.tiles_y;
+    const size_t smem = size_t(tl.tile_h + 3) * tl.pitch * sizeof(typename Acc<T>::type);
     int64_t blocks = n_tiles < int64_t(kNumSMs) * 8 ? n_tiles : int64_t(kNumSMs) * 8;
-    fir_planes_tiled<T><<<unsigned(blocks), 256, 0, st>>>(out, in, fir, p, tiles_x, tiles_y, n_tiles);
+    fir_planes_tiled<T><<<unsigned(blocks), FT_THREADS, smem, st>>>(out, in, fir, p, tl, n_tiles);
   } else {
     upfirdn2d_generic<T><<<grid_for(total, 256, 32), 256, 0, st>>>(out, in, fir, p, total);
   }

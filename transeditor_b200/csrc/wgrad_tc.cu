@@ -1,0 +1,243 @@
+// Tensor-core weight gradient for sm_100a (tcgen05, bf16 operands, f32 accumulate).
+//
+// For the anchor/tap geometry of te_tc_conv_desc (see conv_tc.cu):
+//     gw[w_t][m][n] += SUM_{b, anchors a}  g[b, a*os + oo, m] * x[b, a*is + d_t, n]
+// i.e. per tap a GEMM  D[cout, cin] = G^T . X  whose reduction dimension is the PIXELS.  Both operands are
+// read by TMA as [anchor rows x 64 channels] boxes straight from the channels-last tensors, which makes
+// them MN-major UMMA operands (the channel dimension is contiguous): no transpose pass exists anywhere.
+//   * CTA tile: 128 (cout) x 128 (cin), up to 4 taps resident (4 x 128 TMEM columns = all 512).
+//   * stage = 64 anchors of ONE tap: G tile 2 x [64 x 64ch] + X tile 2 x [64 x 64ch] = 32 KB, 5-stage ring.
+//   * 4 x tcgen05.mma (M128, N128, K16 anchors) per stage.
+//   * split-K over anchor tiles (grid.z) so the chip is filled even when Cout*Cin is one tile;
+//     partial sums are combined with vectorised f32 reductions (red.global.add.v4.f32).
+//   * Out-of-range anchors / padding taps / channel tails are zero-filled by the TMA unit.
+#include "tc_common.cuh"
+
+namespace te {
+
+constexpr int WG_M = 128, WG_N = 128;
+constexpr int WG_KA = 64;              // anchors per stage
+constexpr int WG_STAGES = 5;
+constexpr int WG_TAPS = 4;             // taps resident in TMEM
+constexpr int WG_THREADS = 192;
+constexpr int WG_HALF_BYTES = WG_KA * 128;          // one [64 anchors x 64 ch] box = 8 KB
+constexpr int WG_STAGE_BYTES = 4 * WG_HALF_BYTES;   // G lo, G hi, X lo, X hi = 32 KB
+constexpr int WG_BAR_OFFSET = WG_STAGES * WG_STAGE_BYTES;
+constexpr int WG_SMEM_TOTAL = WG_BAR_OFFSET + 128 + 1024;
+
+struct WgParams {
+  int batch, cin, cout;
+  int ntaps;
+  int tap_dy[9], tap_dx[9], tap_w[9];
+  int in_stride, out_stride, out_off_y, out_off_x;
+  int tw, th, nb;                 // anchor tile patch; nb*th*tw == 64
+  int tiles_w, tiles_h, tiles_b, n_tiles;
+  int tiles_per_split;
+  int use_atomics;
+  float* gw;                      // [w_slices, cout, cin]
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_x,
+                const __grid_constant__ WgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + WG_BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + WG_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + WG_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_blocks = (p.cin + WG_N - 1) / WG_N;
+  const int m0 = (blockIdx.x / n_blocks) * WG_M, n0 = (blockIdx.x % n_blocks) * WG_N;
+  const int tap0 = blockIdx.y * WG_TAPS;
+  const int ntap = min(WG_TAPS, p.ntaps - tap0);
+  const int tile_lo = blockIdx.z * p.tiles_per_split;
+  const int tile_hi = min(p.n_tiles, tile_lo + p.tiles_per_split);
+  const int num_it = (tile_hi - tile_lo) * ntap;  // pipeline iterations: (tile, tap) pairs
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_g)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
+    for (int s = 0; s < WG_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      for (int it = 0; it < num_it; ++it) {
+        const int s = it % WG_STAGES;
+        const uint32_t ph = (it / WG_STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        const int tl = it / ntap, tp = it - tl * ntap;
+        int t = tile_lo + tl;
+        const int tile_w = t % p.tiles_w; t /= p.tiles_w;
+        const int tile_h = t % p.tiles_h; t /= p.tiles_h;
+        const int b0 = t * p.nb, ay0 = tile_h * p.th, ax0 = tile_w * p.tw;
+        const int tap = tap0 + tp;
+        uint8_t* dst = smem + s * WG_STAGE_BYTES;
+        mbar_expect_tx(&full_bar[s], WG_STAGE_BYTES);
+        const int gx = ax0 * p.out_stride + p.out_off_x, gy = ay0 * p.out_stride + p.out_off_y;
+        tma_load_4d(dst, &map_g, &full_bar[s], m0, gx, gy, b0);
+        tma_load_4d(dst + WG_HALF_BYTES, &map_g, &full_bar[s], m0 + 64, gx, gy, b0);
+        const int xx = ax0 * p.in_stride + p.tap_dx[tap], xy = ay0 * p.in_stride + p.tap_dy[tap];
+        tma_load_4d(dst + 2 * WG_HALF_BYTES, &map_x, &full_bar[s], n0, xx, xy, b0);
+        tma_load_4d(dst + 3 * WG_HALF_BYTES, &map_x, &full_bar[s], n0 + 64, xx, xy, b0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = make_idesc_bf16_mn(WG_M, WG_N);
+      for (int it = 0; it < num_it; ++it) {
+        const int s = it % WG_STAGES;
+        const uint32_t ph = (it / WG_STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tcgen05_fence_after();
+        const int tl = it / ntap, tp = it - tl * ntap;
+        const uint32_t base = smem_u32(smem + s * WG_STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < WG_KA / 16; ++k) {
+          // 16 anchors = two 8-row groups = 2048 bytes further down the tile
+          const uint64_t da = make_sw128_mn_desc(base + k * 2048, WG_HALF_BYTES);
+          const uint64_t db = make_sw128_mn_desc(base + 2 * WG_HALF_BYTES + k * 2048, WG_HALF_BYTES);
+          umma_bf16(tmem_base + tp * WG_N, da, db, idesc, (tl | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    // ===== epilogue =====
+    const int quarter = warp & 3;
+    const int m = m0 + quarter * 32 + lane;
+    mbar_wait(tmem_full_bar, 0);
+    tcgen05_fence_after();
+    if (num_it > 0) {
+      for (int tp = 0; tp < ntap; ++tp) {
+        float* row = p.gw + (static_cast<int64_t>(p.tap_w[tap0 + tp]) * p.cout + m) * p.cin + n0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < WG_N; c0 += 32) {
+          if (n0 + c0 >= p.cin) break;
+          uint32_t v[32];
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + tp * WG_N + c0, v);
+          if (m < p.cout) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (n0 + c0 + 4 * j >= p.cin) continue;
+              float a0 = __uint_as_float(v[4 * j]), a1 = __uint_as_float(v[4 * j + 1]);
+              float a2 = __uint_as_float(v[4 * j + 2]), a3 = __uint_as_float(v[4 * j + 3]);
+              if (p.use_atomics)
+                red_add_v4(row + c0 + 4 * j, a0, a1, a2, a3);
+              else {
+                float4* q = reinterpret_cast<float4*>(row + c0 + 4 * j);
+                float4 old = *q;
+                *q = make_float4(old.x + a0, old.y + a1, old.z + a2, old.w + a3);
+              }
+            }
+          }
+        }
+      }
+    }
+    tcgen05_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+}  // namespace te
+
+extern "C" int te_conv_wgrad_tc(float* gw, const void* g, const void* x, const te_tc_conv_desc* dp, void* stream) {
+  using namespace te;
+  TE_CHECK_ARG(gw && g && x && dp, "conv_wgrad_tc: null pointer");
+  const te_tc_conv_desc& d = *dp;
+  TE_CHECK_ARG(d.cin % 8 == 0 && d.cout % 8 == 0 && d.cin >= 8 && d.cout >= 8,
+               "conv_wgrad_tc: channel counts must be multiples of 8 (got %d, %d)", d.cin, d.cout);
+  TE_CHECK_ARG(d.ntaps >= 1 && d.ntaps <= 9, "conv_wgrad_tc: 1..9 taps");
+  TE_CHECK_ARG((d.in_stride == 1 || d.in_stride == 2) && (d.out_stride == 1 || d.out_stride == 2),
+               "conv_wgrad_tc: strides must be 1 or 2");
+  TE_CHECK_ARG(d.grid_h > 0 && d.grid_w > 0 && d.batch > 0, "conv_wgrad_tc: empty anchor grid");
+  TE_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(gw) & 15) == 0 && d.cin % 4 == 0,
+               "conv_wgrad_tc: pointers must be 16-byte aligned");
+  WgParams p;
+  p.batch = d.batch; p.cin = d.cin; p.cout = d.cout; p.ntaps = d.ntaps;
+  for (int t = 0; t < 9; ++t) {
+    p.tap_dy[t] = t < d.ntaps ? d.tap_dy[t] : 0;
+    p.tap_dx[t] = t < d.ntaps ? d.tap_dx[t] : 0;
+    p.tap_w[t] = t < d.ntaps ? d.tap_w[t] : 0;
+    if (t < d.ntaps) TE_CHECK_ARG(d.tap_w[t] >= 0 && d.tap_w[t] < d.w_slices, "conv_wgrad_tc: tap weight index out of range");
+  }
+  p.in_stride = d.in_stride; p.out_stride = d.out_stride; p.out_off_y = d.out_off_y; p.out_off_x = d.out_off_x;
+  p.tw = next_pow2(d.grid_w) < 16 ? next_pow2(d.grid_w) : 16;
+  int th = WG_KA / p.tw;
+  p.th = next_pow2(d.grid_h) < th ? next_pow2(d.grid_h) : th;
+  p.nb = WG_KA / (p.tw * p.th);
+  p.tiles_w = (d.grid_w + p.tw - 1) / p.tw;
+  p.tiles_h = (d.grid_h + p.th - 1) / p.th;
+  p.tiles_b = (d.batch + p.nb - 1) / p.nb;
+  p.n_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
+  p.gw = gw;
+  const int out_tiles = ((d.cout + WG_M - 1) / WG_M) * ((d.cin + WG_N - 1) / WG_N);
+  const int tap_groups = (d.ntaps + WG_TAPS - 1) / WG_TAPS;
+  // split the anchor reduction so that about one wave of CTAs exists, at least 8 tiles per split
+  int splits = (kNumSMs + out_tiles * tap_groups - 1) / (out_tiles * tap_groups);
+  int max_splits = (p.n_tiles + 7) / 8;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  p.tiles_per_split = (p.n_tiles + splits - 1) / splits;
+  splits = (p.n_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  p.use_atomics = splits > 1 ? 1 : 0;
+
+  CUtensorMap mg, mx;
+  {
+    const uint32_t os = uint32_t(d.out_stride);
+    uint64_t dims[4] = {uint64_t(d.cout), uint64_t(d.wout), uint64_t(d.hout), uint64_t(d.batch)};
+    uint64_t strides[3] = {uint64_t(d.cout) * 2, uint64_t(d.wout) * d.cout * 2, uint64_t(d.hout) * d.wout * d.cout * 2};
+    uint32_t box[4] = {64, uint32_t(p.tw) * os, uint32_t(p.th) * os, uint32_t(p.nb)};
+    uint32_t estr[4] = {1, os, os, 1};
+    int rc = encode_map_bf16(&mg, g, 4, dims, strides, box, estr);
+    if (rc) return rc;
+  }
+  {
+    const uint32_t is = uint32_t(d.in_stride);
+    uint64_t dims[4] = {uint64_t(d.cin), uint64_t(d.win), uint64_t(d.hin), uint64_t(d.batch)};
+    uint64_t strides[3] = {uint64_t(d.cin) * 2, uint64_t(d.win) * d.cin * 2, uint64_t(d.hin) * d.win * d.cin * 2};
+    uint32_t box[4] = {64, uint32_t(p.tw) * is, uint32_t(p.th) * is, uint32_t(p.nb)};
+    uint32_t estr[4] = {1, is, is, 1};
+    int rc = encode_map_bf16(&mx, x, 4, dims, strides, box, estr);
+    if (rc) return rc;
+  }
+  static bool configured = false;
+  if (!configured) {
+    TE_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_TOTAL));
+    configured = true;
+  }
+  dim3 grid(out_tiles, tap_groups, splits);
+  wgrad_tc_kernel<<<grid, WG_THREADS, WG_SMEM_TOTAL, static_cast<cudaStream_t>(stream)>>>(mg, mx, p);
+  TE_CHECK_LAUNCH();
+  return TE_OK;
+}

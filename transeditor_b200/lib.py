@@ -29,6 +29,18 @@ class ConvGeom(ctypes.Structure):
                 ("act", ctypes.c_int), ("noise_bstride", ctypes.c_int64)]
 
 
+class TcConvDesc(ctypes.Structure):
+    """Mirror of te_tc_conv_desc."""
+    _fields_ = [("batch", ctypes.c_int), ("hin", ctypes.c_int), ("win", ctypes.c_int), ("cin", ctypes.c_int),
+                ("hout", ctypes.c_int), ("wout", ctypes.c_int), ("cout", ctypes.c_int),
+                ("ntaps", ctypes.c_int), ("tap_dy", ctypes.c_int * 9), ("tap_dx", ctypes.c_int * 9),
+                ("tap_w", ctypes.c_int * 9), ("w_slices", ctypes.c_int),
+                ("in_stride", ctypes.c_int), ("out_stride", ctypes.c_int),
+                ("out_off_y", ctypes.c_int), ("out_off_x", ctypes.c_int),
+                ("grid_h", ctypes.c_int), ("grid_w", ctypes.c_int),
+                ("act", ctypes.c_int), ("out_f32", ctypes.c_int), ("w_bstride", ctypes.c_int64)]
+
+
 _P, _I, _L, _F = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
 _SIGNATURES = {
     "te_version": ([], _I),
@@ -39,6 +51,8 @@ _SIGNATURES = {
     "te_conv2d_simt": ([_P, _P, _P, _P, _P, _P, _P, _P, ctypes.POINTER(ConvGeom), _I, _P], _I),
     "te_conv2d_wgrad_simt": ([_P, _P, _P, _P, _P, ctypes.POINTER(ConvGeom), _I, _P], _I),
     "te_adam_ema": ([_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _F, _P], _I),
+    "te_conv_tc": ([_P, _P, _P, _P, _P, ctypes.POINTER(TcConvDesc), _P], _I),
+    "te_conv_wgrad_tc": ([_P, _P, _P, ctypes.POINTER(TcConvDesc), _P], _I),
     "te_conv2d_tc": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _L, _P], _I),
     "te_gemm_tc_selftest": ([_P, _P, _P, _I, _I, _I, _P], _I),
     "te_attn_core": ([_P, _P, _P, _P, _P, _I, _I, _P], _I),
@@ -151,6 +165,17 @@ def attn_core(out, sim, q, k, v, batch, tokens):
 def conv2d_tc(y, x, w, out_scale, bias, batch, hin, win, cin, cout, kh, kw, act, w_bstride):
     _check(load().te_conv2d_tc(ptr(y), ptr(x), ptr(w), ptr(out_scale), ptr(bias), batch, hin, win, cin,
                                cout, kh, kw, act, w_bstride, stream()), "conv2d_tc")
+    _count()
+
+
+def conv_tc(y, x, w, out_scale, bias, desc):
+    _check(load().te_conv_tc(ptr(y), ptr(x), ptr(w), ptr(out_scale), ptr(bias), ctypes.byref(desc), stream()),
+           "conv_tc")
+    _count()
+
+
+def conv_wgrad_tc(gw, g, x, desc):
+    _check(load().te_conv_wgrad_tc(ptr(gw), ptr(g), ptr(x), ctypes.byref(desc), stream()), "conv_wgrad_tc")
     _count()
 
 

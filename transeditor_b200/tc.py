@@ -1,0 +1,208 @@
+"""Tensor-core (tcgen05) convolution engine, bf16 channels-last: forward, data gradient and weight
+gradient of every convolution on the path, as twice-differentiable autograd Functions.
+
+Three geometries ("modes"), written for one axis (K taps, p = K // 2):
+    s1    y[a]      = sum_k x[a + k - p] . Wsel[k]       stride-1 "same" convolution
+    down  y[a]      = sum_k x[2a + k]    . Wsel[k]       stride-2 convolution, no padding
+    up    y[2i + k] += x[i]              . Wsel[k]       transposed stride-2 convolution (full)
+where Wsel[k] = W[k] or W[K-1-k] (`flip`) taken as [Cout, Cin] or transposed (`transposed`) slices of
+the master weight W [O, I, K, K].  The set is closed under differentiation:
+    adjoint(s1)   = s1   with transposed^, flip^
+    adjoint(down) = up   with transposed^
+    adjoint(up)   = down with transposed^
+and the weight gradient of each mode is one te_conv_wgrad_tc call per launch of the forward geometry.
+`up` is issued as one launch per output parity class (polyphase), so no zero-inserted tensor exists.
+
+Reference call sites replaced: F.conv2d / F.conv_transpose2d in model_spatial_query.py:177-183,318,327,333
+and their autograd gradients.
+"""
+import torch
+from torch.autograd import Function
+
+from . import lib
+
+
+def _pad8(c):
+    return (c + 7) // 8 * 8
+
+
+class Mode:
+    """Geometry of one launch family."""
+    __slots__ = ("kind", "k", "transposed", "flip", "out_hw")
+
+    def __init__(self, kind, k, transposed=False, flip=False, out_hw=None):
+        self.kind, self.k, self.transposed, self.flip = kind, k, transposed, flip
+        self.out_hw = None if out_hw is None else (int(out_hw[0]), int(out_hw[1]))
+
+    def adjoint(self, in_hw):
+        if self.kind == "s1":
+            return Mode("s1", self.k, not self.transposed, not self.flip, in_hw)
+        if self.kind == "down":
+            return Mode("up", self.k, not self.transposed, self.flip, in_hw)
+        return Mode("down", self.k, not self.transposed, self.flip, in_hw)
+
+    def output_hw(self, hin, win):
+        k = self.k
+        if self.out_hw is not None:
+            return self.out_hw
+        if self.kind == "s1":
+            return hin, win
+        if self.kind == "down":
+            return (hin - k) // 2 + 1, (win - k) // 2 + 1
+        return (hin - 1) * 2 + k, (win - 1) * 2 + k
+
+    def launches(self, hin, win, hout, wout):
+        """List of (taps, in_stride, out_stride, off_y, off_x, grid_h, grid_w); taps = [(dy, dx, widx)]."""
+        k = self.k
+        sel = (lambda t: k - 1 - t) if self.flip else (lambda t: t)
+        widx = lambda ky, kx: sel(ky) * k + sel(kx)  # noqa: E731
+        if self.kind == "s1":
+            taps = [(ky - k // 2, kx - k // 2, widx(ky, kx)) for ky in range(k) for kx in range(k)]
+            return [(taps, 1, 1, 0, 0, hout, wout)]
+        if self.kind == "down":
+            taps = [(ky, kx, widx(ky, kx)) for ky in range(k) for kx in range(k)]
+            return [(taps, 2, 1, 0, 0, hout, wout)]
+        out = []
+        for ry in (0, 1):
+            for rx in (0, 1):
+                gh, gw = (hout - ry + 1) // 2, (wout - rx + 1) // 2
+                taps = [(-(ky - ry) // 2, -(kx - rx) // 2, widx(ky, kx))
+                        for ky in range(ry, k, 2) for kx in range(rx, k, 2)]
+                if taps and gh > 0 and gw > 0:
+                    out.append((taps, 1, 2, ry, rx, gh, gw))
+        return out
+
+    def covers_output(self):
+        """False when some output positions receive no tap (k=1 transposed: only even positions)."""
+        return not (self.kind == "up" and self.k == 1)
+
+
+def pack_weight(w, transposed):
+    """Master weight [O, I, K, K] (f32) -> bf16 slices [K*K, Cout, Cin] (Cin contiguous), channel counts
+    padded to multiples of 8 with zeros."""
+    o, i, k, _ = w.shape
+    if transposed:
+        w = w.transpose(0, 1)
+        o, i = i, o
+    wp = w.permute(2, 3, 0, 1).reshape(k * k, o, i).to(torch.bfloat16)
+    po, pi = _pad8(o), _pad8(i)
+    if po != o or pi != i:
+        full = torch.zeros((k * k, po, pi), dtype=torch.bfloat16, device=w.device)
+        full[:, :o, :i] = wp
+        return full
+    return wp.contiguous()
+
+
+def _desc(x, cout, hout, wout, launch, w_slices, act=0, out_f32=0):
+    taps, ist, ost, oy, ox, gh, gw = launch
+    b, cin, hin, win = x.shape
+    d = lib.TcConvDesc()
+    d.batch, d.hin, d.win, d.cin = b, hin, win, cin
+    d.hout, d.wout, d.cout = hout, wout, cout
+    d.ntaps = len(taps)
+    for t, (dy, dx, wi) in enumerate(taps):
+        d.tap_dy[t], d.tap_dx[t], d.tap_w[t] = dy, dx, wi
+    d.w_slices = w_slices
+    d.in_stride, d.out_stride, d.out_off_y, d.out_off_x = ist, ost, oy, ox
+    d.grid_h, d.grid_w = gh, gw
+    d.act, d.out_f32, d.w_bstride = act, out_f32, 0
+    return d
+
+
+def _cl_bf16(x):
+    if x.dtype != torch.bfloat16:
+        raise TypeError("tensor-core conv needs bf16 activations, got %s" % x.dtype)
+    if x.shape[1] % 8:
+        raise RuntimeError("tensor-core conv needs channel counts that are multiples of 8 (got %d)" % x.shape[1])
+    return x.contiguous(memory_format=torch.channels_last)
+
+
+def conv_raw(x, wp, mode, out_scale=None, bias=None, act=False):
+    """x [B, Cin, H, W] bf16 channels-last, wp = pack_weight(...).  Returns bf16 channels-last."""
+    lib.require_cuda(x, wp, out_scale, bias)
+    x = _cl_bf16(x)
+    b, cin, hin, win = x.shape
+    cout = wp.shape[1]
+    if wp.shape[2] != cin:
+        raise RuntimeError("conv_tc: weight expects %d input channels, tensor has %d" % (wp.shape[2], cin))
+    hout, wout = mode.output_hw(hin, win)
+    alloc = torch.empty if mode.covers_output() else torch.zeros
+    y = alloc((b, cout, hout, wout), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+    f32 = lambda t: None if t is None else t.to(torch.float32).contiguous()  # noqa: E731
+    osc, bi = f32(out_scale), f32(bias)
+    for launch in mode.launches(hin, win, hout, wout):
+        lib.conv_tc(y, x, wp, osc, bi, _desc(x, cout, hout, wout, launch, wp.shape[0], 1 if act else 0))
+    return y
+
+
+def wgrad_raw(g, x, mode, w_shape):
+    """Gradient w.r.t. the master weight [O, I, K, K] (f32) of y = conv(x, W; mode) given g = dL/dy."""
+    lib.require_cuda(g, x)
+    g, x = _cl_bf16(g), _cl_bf16(x)
+    b, cin, hin, win = x.shape
+    cout, hout, wout = g.shape[1], g.shape[2], g.shape[3]
+    k = mode.k
+    gw = torch.zeros((k * k, cout, cin), dtype=torch.float32, device=x.device)
+    for launch in mode.launches(hin, win, hout, wout):
+        lib.conv_wgrad_tc(gw, g, x, _desc(x, cout, hout, wout, launch, k * k))
+    o, i = w_shape[0], w_shape[1]
+    if mode.transposed:   # logical (cout, cin) = (I_store, O_store)
+        return gw[:, :i, :o].permute(2, 1, 0).reshape(o, i, k, k).contiguous()
+    return gw[:, :o, :i].permute(1, 2, 0).reshape(o, i, k, k).contiguous()
+
+
+class TcConv(Function):
+    """y = conv(x, W; mode) on tensor cores; W is the f32 master weight [O, I, K, K]."""
+
+    @staticmethod
+    def forward(ctx, x, w, mode):
+        ctx.save_for_backward(x, w)
+        ctx.mode = mode
+        return conv_raw(x, pack_weight(w, mode.transposed), mode)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        mode = ctx.mode
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            gx = TcConv.apply(gy, w, mode.adjoint((x.shape[2], x.shape[3])))
+            if gx.shape[1] != x.shape[1]:
+                gx = gx[:, :x.shape[1]]
+        if ctx.needs_input_grad[1]:
+            gw = TcWeightGrad.apply(x, gy, mode, tuple(w.shape))
+        return gx, gw, None
+
+
+class TcWeightGrad(Function):
+    """gW = wgrad(x, gy; mode): bilinear, so its backward is two TcConv calls."""
+
+    @staticmethod
+    def forward(ctx, x, gy, mode, w_shape):
+        ctx.save_for_backward(x, gy)
+        ctx.mode = mode
+        return wgrad_raw(gy, x, mode, w_shape)
+
+    @staticmethod
+    def backward(ctx, ggw):
+        x, gy = ctx.saved_tensors
+        mode = ctx.mode
+        g_x = g_gy = None
+        if ctx.needs_input_grad[0]:
+            g_x = TcConv.apply(gy, ggw, mode.adjoint((x.shape[2], x.shape[3])))
+        if ctx.needs_input_grad[1]:
+            g_gy = TcConv.apply(x, ggw, Mode(mode.kind, mode.k, mode.transposed, mode.flip,
+                                             (gy.shape[2], gy.shape[3])))
+        return g_x, g_gy, None, None
+
+
+def conv2d(x, w, stride=1):
+    """F.conv2d(x, w, stride, padding = k//2 if stride == 1 else 0) in bf16 on tensor cores."""
+    k = w.shape[2]
+    return TcConv.apply(x, w, Mode("s1" if stride == 1 else "down", k))
+
+
+def conv_transpose2d(x, w_oi, stride=2):
+    """F.conv_transpose2d(x, w_oi.transpose(0, 1), stride=2, padding=0), weight kept [O, I, K, K]."""
+    assert stride == 2
+    return TcConv.apply(x, w_oi, Mode("up", w_oi.shape[2]))
