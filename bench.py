@@ -118,6 +118,13 @@ class KernelMeter:
             byts = es(t) * (g.batch * g.cin * g.hin * g.win + g.batch * g.cout * g.hout * g.wout
                             + g.cout * g.cin * g.kh * g.kw)
             return 2.0 * macs, float(byts)
+        if name in ("conv_tc", "conv_wgrad_tc"):
+            d = args[-1]
+            flops = 2.0 * d.batch * d.grid_h * d.grid_w * d.ntaps * d.cin * d.cout
+            byts = 2.0 * (d.batch * d.grid_h * d.grid_w * (d.cin + d.cout) + d.ntaps * d.cin * d.cout)
+            return flops, byts
+        if name in ("scale_bc", "dot_bc"):
+            return 0.0, 2.0 * args[1].numel() * es(args[1])
         if name == "fused_bias_act":
             return 0.0, 2.0 * args[1].numel() * es(args[1])
         if name == "fused_bias_act_bwd":
@@ -131,7 +138,8 @@ class KernelMeter:
     def install(self):
         from transeditor_b200 import lib
         for name in ("fused_bias_act", "fused_bias_act_bwd", "upfirdn2d", "conv2d_simt",
-                     "conv2d_wgrad_simt", "adam_ema", "attn_core", "conv2d_tc"):
+                     "conv2d_wgrad_simt", "adam_ema", "attn_core", "conv2d_tc", "conv_tc",
+                     "conv_wgrad_tc", "scale_bc", "dot_bc"):
             fn = getattr(lib, name)
             self._saved[name] = fn
 
@@ -258,6 +266,8 @@ def run_ours(args, rank, local_rank, world):
     torch.cuda.set_device(dev)
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
+    from transeditor_b200 import model as te_model
+    te_model.set_precision(args.precision)
     cfg = TrainConfig(size=args.size, batch=args.batch)
     trainer = Trainer(cfg, dev, seed=0)
 
@@ -315,11 +325,14 @@ def run_ours(args, rank, local_rank, world):
     images = args.steps * cfg.batch * world
     line = {"metric": METRIC, "value": round(images / (ms * 1e-3), 3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": cfg.batch * world, "per_gpu_batch": cfg.batch,
                        "size": cfg.size, "num_trans": cfg.num_trans, "parallelism": "dp%d" % world,
-                       "precision": "fp32 storage and arithmetic (parity mode)",
+                       "precision": ("bf16 activations / tcgen05 MMA with f32 accumulation, f32 master weights, "
+                                     "f32 mapping+transformer" if args.precision == "bf16"
+                                     else "fp32 storage and arithmetic (parity mode, SIMT kernels)"),
                        "lazy_regularisers": "R1 on i%16==0, path-length on i%4==0, cadence restarted at i=0 "
                                             "for the timed region",
                        "l2": "no explicit flush: each step streams several GB of activations, far above the 126 MB L2"},
@@ -344,6 +357,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
+                    help="bf16: tcgen05 tensor-core path (BASELINE configs[1]); fp32: SIMT parity path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ncu", action="store_true",
                     help="profiling aid: W warm-up + K steps only, prints no bench line (numbers under ncu are never bench values)")

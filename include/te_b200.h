@@ -169,6 +169,19 @@ int te_conv2d_tc(void* y, const void* x, const void* w, const float* out_scale, 
                  int batch, int hin, int win, int cin, int cout, int kh, int kw, int act,
                  int64_t w_bstride, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Channels-last per-(sample, channel) scaling and its gradient reduction: the modulation s[b,cin] and
+ * demodulation d[b,cout] multiplies of ModulatedConv2d applied to ACTIVATIONS instead of being folded
+ * into per-sample weights (model_spatial_query.py:299-304).
+ *   te_scale_bc:  y[b,p,c] = x[b,p,c] * s[b,c]            x,y [batch, pixels, channels], s FLOAT32
+ *   te_dot_bc:    out[b,c] += SUM_p a[b,p,c] * b[b,p,c]   out FLOAT32, zeroed by the caller
+ * dtypes: bf16, f16, f32; channels % (16/sizeof(T)) == 0.
+ */
+int te_scale_bc(void* y, const void* x, const float* s, int64_t batch, int64_t pixels, int channels,
+                int dtype, void* stream);
+int te_dot_bc(float* out, const void* a, const void* b, int64_t batch, int64_t pixels, int channels,
+              int dtype, void* stream);
+
 /* Self-test of the tcgen05 GEMM core: D[M,N] (f32) = A[M,K] (bf16, K-major) * B[N,K]^T (bf16). */
 int te_gemm_tc_selftest(float* d, const void* a, const void* b, int m, int n, int k, void* stream);
 

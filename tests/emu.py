@@ -133,8 +133,19 @@ def adam_ema(p, g, m, v, ema, lr, beta1, beta2, eps, step, ema_decay, grad_scale
         ema.mul_(ema_decay).add_(p, alpha=1 - ema_decay)
 
 
+def scale_bc(y, x, s, batch, pixels, channels):
+    xs = _storage_flat(x).reshape(batch, pixels, channels).to(torch.float64)
+    _store(y, (xs * s.reshape(batch, 1, channels).to(torch.float64)).reshape(-1))
+
+
+def dot_bc(out, a, b, batch, pixels, channels):
+    aa = _storage_flat(a).reshape(batch, pixels, channels).to(torch.float64)
+    bb = _storage_flat(b).reshape(batch, pixels, channels).to(torch.float64)
+    out.add_((aa * bb).sum(1).to(out.dtype))
+
+
 def install(monkeypatch):
     monkeypatch.setattr(lib, "require_cuda", lambda *a: None)
     for name in ("fused_bias_act", "fused_bias_act_bwd", "upfirdn2d", "conv2d_simt",
-                 "conv2d_wgrad_simt", "attn_core", "adam_ema"):
+                 "conv2d_wgrad_simt", "attn_core", "adam_ema", "scale_bc", "dot_bc"):
         monkeypatch.setattr(lib, name, globals()[name])

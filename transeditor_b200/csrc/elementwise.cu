@@ -1,0 +1,129 @@
+// Channels-last per-(sample, channel) scaling and its reduction: the modulation / demodulation
+// multiplies of ModulatedConv2d (model_spatial_query.py:299-304 folds them into per-sample weights;
+// here they act on activations) and the matching gradient reductions
+//     y[b,p,c] = x[b,p,c] * s[b,c]                 (te_scale_bc)
+//     out[b,c] = sum_p a[b,p,c] * b_[b,p,c]        (te_dot_bc)
+// HBM-streaming, 16-byte accesses, f32 math; tensors are [B, P, C] with C contiguous (P = H*W).
+#include "common.cuh"
+
+namespace te {
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+scale_bc_kernel(T* __restrict__ y, const T* __restrict__ x, const float* __restrict__ s, int64_t n_vec,
+                int64_t pc_vec /* P*C/VEC */, int c_vec /* C/VEC */) {
+  struct alignas(sizeof(T) * VEC) V { T v[VEC]; };
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t iv = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; iv < n_vec; iv += stride) {
+    const int64_t b = iv / pc_vec;
+    const int cv = int(iv % c_vec);
+    const float* sp = s + (b * c_vec + cv) * VEC;
+    V in = reinterpret_cast<const V*>(x)[iv];
+    V o;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) o.v[j] = from_acc<T, float>(float(to_acc(in.v[j])) * __ldg(sp + j));
+    reinterpret_cast<V*>(y)[iv] = o;
+  }
+}
+
+// one CTA = (sample b, pixel chunk); thread = VEC channels x strided pixels; smem reduce over the
+// pixel dimension of the CTA, then one atomic per channel.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+dot_bc_kernel(float* __restrict__ out, const T* __restrict__ a, const T* __restrict__ b_, int p_total, int c,
+              int pix_per_cta) {
+  struct alignas(sizeof(T) * VEC) V { T v[VEC]; };
+  extern __shared__ float red[];  // [rows][c]
+  const int c_vec = c / VEC;
+  const int b = blockIdx.y;
+  const int p_lo = blockIdx.x * pix_per_cta;
+  const int p_hi = min(p_total, p_lo + pix_per_cta);
+  const int rows = blockDim.x / c_vec > 0 ? blockDim.x / c_vec : 1;
+  const int cv = threadIdx.x % c_vec, row = threadIdx.x / c_vec;
+  float acc[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+  if (row < rows) {
+    const int64_t base = int64_t(b) * p_total * c;
+    for (int p = p_lo + row; p < p_hi; p += rows) {
+      const int64_t off = (base + int64_t(p) * c) / VEC + cv;
+      V va = reinterpret_cast<const V*>(a)[off];
+      V vb = reinterpret_cast<const V*>(b_)[off];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) acc[j] += float(to_acc(va.v[j])) * float(to_acc(vb.v[j]));
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) red[row * c + cv * VEC + j] = acc[j];
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float sum = 0.f;
+    for (int r = 0; r < rows; ++r) sum += red[r * c + ch];
+    atomicAdd(out + int64_t(b) * c + ch, sum);
+  }
+}
+
+template <typename T>
+static int scale_bc_typed(void* y, const void* x, const float* s, int64_t batch, int64_t pixels, int c,
+                          cudaStream_t st) {
+  constexpr int VEC = 16 / sizeof(T);
+  TE_CHECK_ARG(c % VEC == 0, "scale_bc: channel count %d must be a multiple of %d", c, VEC);
+  const int64_t n_vec = batch * pixels * c / VEC;
+  if (n_vec == 0) return TE_OK;
+  scale_bc_kernel<T, VEC><<<grid_for(n_vec, 256, 16), 256, 0, st>>>(
+      static_cast<T*>(y), static_cast<const T*>(x), s, n_vec, pixels * c / VEC, c / VEC);
+  TE_CHECK_LAUNCH();
+  return TE_OK;
+}
+
+template <typename T>
+static int dot_bc_typed(float* out, const void* a, const void* b, int64_t batch, int64_t pixels, int c,
+                        cudaStream_t st) {
+  constexpr int VEC = 16 / sizeof(T);
+  TE_CHECK_ARG(c % VEC == 0, "dot_bc: channel count %d must be a multiple of %d", c, VEC);
+  TE_CHECK_ARG(batch <= 65535 && pixels < (int64_t(1) << 31), "dot_bc: tensor too large");
+  if (batch * pixels == 0) return TE_OK;
+  const int c_vec = c / VEC;
+  int threads = 256;
+  if (c_vec > threads) threads = ((c_vec + 31) / 32) * 32;
+  TE_CHECK_ARG(threads <= 1024, "dot_bc: too many channels (%d)", c);
+  const int rows = threads / c_vec > 0 ? threads / c_vec : 1;
+  // enough CTAs to fill the chip, at least 4 pixels per thread row
+  int64_t want = (int64_t(kNumSMs) * 8 + batch - 1) / batch;
+  int64_t ppc = (pixels + want - 1) / want;
+  if (ppc < 4 * rows) ppc = 4 * rows;
+  const unsigned gx = unsigned((pixels + ppc - 1) / ppc);
+  dim3 grid(gx, unsigned(batch));
+  const size_t smem = size_t(rows) * c * sizeof(float);
+  TE_CHECK_ARG(smem <= 48 * 1024, "dot_bc: shared-memory footprint too large");
+  dot_bc_kernel<T, VEC><<<grid, threads, smem, st>>>(out, static_cast<const T*>(a), static_cast<const T*>(b),
+                                                     int(pixels), c, int(ppc));
+  TE_CHECK_LAUNCH();
+  return TE_OK;
+}
+
+}  // namespace te
+
+extern "C" int te_scale_bc(void* y, const void* x, const float* s, int64_t batch, int64_t pixels, int channels,
+                           int dtype, void* stream) {
+  using namespace te;
+  TE_CHECK_ARG(y && x && s, "scale_bc: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == TE_BF16) return scale_bc_typed<__nv_bfloat16>(y, x, s, batch, pixels, channels, st);
+  if (dtype == TE_F32) return scale_bc_typed<float>(y, x, s, batch, pixels, channels, st);
+  if (dtype == TE_F16) return scale_bc_typed<__half>(y, x, s, batch, pixels, channels, st);
+  set_error("scale_bc: unsupported dtype %d", dtype);
+  return TE_ERR_UNSUPPORTED;
+}
+
+extern "C" int te_dot_bc(float* out, const void* a, const void* b, int64_t batch, int64_t pixels, int channels,
+                         int dtype, void* stream) {
+  using namespace te;
+  TE_CHECK_ARG(out && a && b, "dot_bc: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == TE_BF16) return dot_bc_typed<__nv_bfloat16>(out, a, b, batch, pixels, channels, st);
+  if (dtype == TE_F32) return dot_bc_typed<float>(out, a, b, batch, pixels, channels, st);
+  if (dtype == TE_F16) return dot_bc_typed<__half>(out, a, b, batch, pixels, channels, st);
+  set_error("dot_bc: unsupported dtype %d", dtype);
+  return TE_ERR_UNSUPPORTED;
+}

@@ -53,6 +53,8 @@ _SIGNATURES = {
     "te_adam_ema": ([_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _F, _P], _I),
     "te_conv_tc": ([_P, _P, _P, _P, _P, ctypes.POINTER(TcConvDesc), _P], _I),
     "te_conv_wgrad_tc": ([_P, _P, _P, ctypes.POINTER(TcConvDesc), _P], _I),
+    "te_scale_bc": ([_P, _P, _P, _L, _L, _I, _I, _P], _I),
+    "te_dot_bc": ([_P, _P, _P, _L, _L, _I, _I, _P], _I),
     "te_conv2d_tc": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _L, _P], _I),
     "te_gemm_tc_selftest": ([_P, _P, _P, _I, _I, _I, _P], _I),
     "te_attn_core": ([_P, _P, _P, _P, _P, _I, _I, _P], _I),
@@ -176,6 +178,16 @@ def conv_tc(y, x, w, out_scale, bias, desc):
 
 def conv_wgrad_tc(gw, g, x, desc):
     _check(load().te_conv_wgrad_tc(ptr(gw), ptr(g), ptr(x), ctypes.byref(desc), stream()), "conv_wgrad_tc")
+    _count()
+
+
+def scale_bc(y, x, s, batch, pixels, channels):
+    _check(load().te_scale_bc(ptr(y), ptr(x), ptr(s), batch, pixels, channels, dtype_code(x), stream()), "scale_bc")
+    _count()
+
+
+def dot_bc(out, a, b, batch, pixels, channels):
+    _check(load().te_dot_bc(ptr(out), ptr(a), ptr(b), batch, pixels, channels, dtype_code(a), stream()), "dot_bc")
     _count()
 
 

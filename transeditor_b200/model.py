@@ -21,10 +21,35 @@ import torch
 from torch import nn
 from torch.nn import functional as F
 
-from . import op
+from . import op, tc
 from .op import FusedLeakyReLU, fused_leaky_relu, upfirdn2d
 
 _SQRT2 = math.sqrt(2.0)
+
+# Precision of the convolution stacks.  "fp32": NCHW f32 on the SIMT kernels — the parity mode, the
+# reference's own arithmetic.  "bf16": channels-last bf16 activations on the tcgen05 kernels (f32
+# accumulation, f32 master weights, f32 mapping / transformer / RGB skip path).  Layers dispatch on
+# the dtype of their input; this flag only decides the conversion at the model boundaries.
+_PRECISION = "fp32"
+
+
+def set_precision(name):
+    global _PRECISION
+    if name not in ("fp32", "bf16"):
+        raise ValueError("precision must be 'fp32' or 'bf16'")
+    _PRECISION = name
+
+
+def get_precision():
+    return _PRECISION
+
+
+def _to_bf16_cl(x, pad_to=8):
+    """f32/bf16 NCHW -> bf16 channels-last with the channel count padded to a multiple of 8."""
+    c = x.shape[1]
+    if c % pad_to:
+        x = F.pad(x, (0, 0, 0, 0, 0, pad_to - c % pad_to))
+    return x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
 
 
 def _grad_needed(*tensors):
@@ -106,7 +131,18 @@ class EqualConv2d(nn.Module):
         self.bias = nn.Parameter(torch.zeros(out_channel)) if bias else None
 
     def forward(self, input):
-        out = op.conv2d(input, self.weight * self.scale, stride=self.stride, padding=self.padding)
+        w = self.weight * self.scale
+        if input.dtype == torch.bfloat16:
+            k = w.shape[2]
+            if self.padding != (k // 2 if self.stride == 1 else 0) or self.stride not in (1, 2):
+                raise RuntimeError("tensor-core EqualConv2d supports stride 1 (pad k//2) and stride 2 (pad 0)")
+            if input.shape[1] != w.shape[1]:  # input channels were zero-padded to a multiple of 8
+                w = F.pad(w, (0, 0, 0, 0, 0, input.shape[1] - w.shape[1]))
+            out = tc.conv2d(input, w, stride=self.stride)
+            if self.bias is not None:
+                out = out + self.bias.view(1, -1, 1, 1).to(out.dtype)
+            return out
+        out = op.conv2d(input, w, stride=self.stride, padding=self.padding)
         if self.bias is not None:
             out = out + self.bias.view(1, -1, 1, 1)
         return out
@@ -201,6 +237,8 @@ class ModulatedConv2d(nn.Module):
         inference path; reference callers pass only (input, style)."""
         s, d, wn = self.scales(style)
         fused_ok = not _grad_needed(input, s, wn, bias, noise_weight)
+        if input.dtype == torch.bfloat16:
+            return self._forward_tc(input, s, d, wn, bias, noise, noise_weight, activate, fused_ok)
         if self.upsample:
             if fused_ok:
                 out = op.conv2d_fused(input, wn, in_scale=s, out_scale=d, transpose_stride=2)
@@ -225,13 +263,44 @@ class ModulatedConv2d(nn.Module):
         return _epilogue(out, bias, noise, noise_weight, activate)
 
 
+def _modconv_forward_tc(self, x, s, d, wn, bias, noise, noise_weight, activate, fused_ok):
+    """bf16 channels-last route on the tcgen05 kernels: y = d * conv(x * s, Wn) as
+    scale_bc -> conv (-> blur) -> scale_bc, every piece a twice-differentiable custom op.  Without
+    autograd the demodulation, bias and activation ride in the conv kernel's epilogue."""
+    if self.downsample:
+        raise RuntimeError("tensor-core ModulatedConv2d: downsample is not used by the generator")
+    k = self.kernel_size
+    cout = self.out_channel
+    if cout % 8:  # ToRGB: pad the 3 output channels to 8 (zero rows), sliced off below
+        wn = F.pad(wn, (0, 0, 0, 0, 0, 0, 0, 8 - cout % 8))
+        if d is not None:
+            d = F.pad(d, (0, 8 - cout % 8), value=1.0)
+    u = op.scale_bc(x, s)
+    if self.upsample:
+        v = self.blur(tc.conv_transpose2d(u, wn))
+    elif fused_ok and noise is None:
+        pb = None if bias is None else F.pad(bias.reshape(-1), (0, wn.shape[0] - cout))
+        v = tc.conv_raw(u, tc.pack_weight(wn, False), tc.Mode("s1", k), out_scale=d, bias=pb, act=activate)
+        return v if wn.shape[0] == cout else v[:, :cout]
+    else:
+        v = tc.conv2d(u, wn)
+    if d is not None:
+        v = op.scale_bc(v, d)
+    if wn.shape[0] != cout:
+        v = v[:, :cout]
+    return _epilogue(v, bias, noise, noise_weight, activate)
+
+
+ModulatedConv2d._forward_tc = _modconv_forward_tc
+
+
 def _epilogue(out, bias, noise, noise_weight, activate):
     if noise is not None:
-        out = out + noise_weight * noise
+        out = out + (noise_weight * noise).to(out.dtype)
     if activate:
         return fused_leaky_relu(out, bias)
     if bias is not None:
-        out = out + bias.view(1, -1, 1, 1)
+        out = out + bias.view(1, -1, 1, 1).to(out.dtype)
     return out
 
 
@@ -294,7 +363,11 @@ class ToRGB(nn.Module):
         self.bias = nn.Parameter(torch.zeros(1, 3, 1, 1))
 
     def forward(self, input, style, skip=None):
-        out = self.conv(input, style, bias=self.bias.view(-1))
+        if input.dtype == torch.bfloat16:
+            # the RGB skip path stays f32 NCHW (tiny tensors): slice the padded conv output and convert
+            out = self.conv(input, style).float().contiguous() + self.bias
+        else:
+            out = self.conv(input, style, bias=self.bias.view(-1))
         if skip is not None:
             out = out + self.upsample(skip)
         return out
@@ -519,6 +592,8 @@ class Generator(nn.Module):
 
         batch = spatialcode.shape[0]
         out = spatialcode.permute(0, 2, 1).reshape(batch, 512, 4, 4)
+        if _PRECISION == "bf16":
+            out = _to_bf16_cl(out)
         out = self.conv1(out, latent[:, 0], noise=noise[0])
         skip = self.to_rgb1(out, latent[:, 1])
         i = 1
@@ -600,7 +675,11 @@ class Discriminator(nn.Module):
             EqualLinear(channels[4], 1))
 
     def forward(self, input):
-        out = self.convs(input)
+        if _PRECISION == "bf16":
+            # conv stack in bf16 on tensor cores; the 4x4 tail (stddev, final conv, linears) in f32
+            out = self.convs(_to_bf16_cl(input)).float().contiguous()
+        else:
+            out = self.convs(input)
         batch, channel, height, width = out.shape
         group = min(batch, self.stddev_group)
         # minibatch standard deviation, one scalar per sub-batch (:844-852)

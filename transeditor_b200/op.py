@@ -64,7 +64,7 @@ class FusedLeakyReLUFunctionBackward(Function):
     (the reference runs fused_bias_act and then a separate .sum(), fused_act.py:27-36)."""
 
     @staticmethod
-    def forward(ctx, grad_output, out, has_bias, negative_slope, scale):
+    def forward(ctx, grad_output, out, has_bias, negative_slope, scale, bias_dtype=None):
         lib.require_cuda(grad_output, out)
         ctx.save_for_backward(out)
         ctx.negative_slope = negative_slope
@@ -79,7 +79,7 @@ class FusedLeakyReLUFunctionBackward(Function):
             grad_bias = torch.zeros(size_b, dtype=acc_dtype, device=g.device)
             lib.fused_bias_act_bwd(grad_input, grad_bias, g, ref, float(negative_slope), float(scale),
                                    step_b, size_b)
-            grad_bias = grad_bias.to(g.dtype)
+            grad_bias = grad_bias.to(bias_dtype or g.dtype)
         else:
             lib.fused_bias_act_bwd(grad_input, None, g, ref, float(negative_slope), float(scale),
                                    step_b, size_b)
@@ -93,7 +93,7 @@ class FusedLeakyReLUFunctionBackward(Function):
             gradgrad_input = torch.zeros_like(out)
         gb = gradgrad_bias if (ctx.has_bias and gradgrad_bias is not None) else None
         gradgrad_out = _bias_act(gradgrad_input, gb, out, 3, 1, ctx.negative_slope, ctx.scale)
-        return gradgrad_out, None, None, None, None
+        return gradgrad_out, None, None, None, None, None
 
 
 class FusedLeakyReLUFunction(Function):
@@ -106,13 +106,14 @@ class FusedLeakyReLUFunction(Function):
         ctx.negative_slope = negative_slope
         ctx.scale = scale
         ctx.has_bias = bias is not None
+        ctx.bias_dtype = bias.dtype if bias is not None else None
         return out
 
     @staticmethod
     def backward(ctx, grad_output):
         (out,) = ctx.saved_tensors
         grad_input, grad_bias = FusedLeakyReLUFunctionBackward.apply(
-            grad_output, out, ctx.has_bias, ctx.negative_slope, ctx.scale)
+            grad_output, out, ctx.has_bias, ctx.negative_slope, ctx.scale, ctx.bias_dtype)
         return grad_input, (grad_bias if ctx.has_bias else None), None, None
 
 
@@ -367,6 +368,62 @@ def conv2d_fused(x, w, in_scale=None, out_scale=None, bias=None, noise=None, noi
         ow = (x.shape[3] + 2 * padding - kw) // stride + 1
         geom = Geometry(kh, kw, 1, stride, padding, padding, False, False, (oh, ow))
     return _conv_forward(x, w, geom, in_scale, out_scale, bias, noise, noise_w, 1 if act else 0)
+
+
+# --------------------------------------------------------------------------------------------
+# per-(sample, channel) scale and its reduction on channels-last tensors (modulation / demodulation)
+
+
+def _cl(t):
+    return t.contiguous(memory_format=torch.channels_last)
+
+
+class ScaleBC(Function):
+    """y[b,c,h,w] = x[b,c,h,w] * s[b,c]  (x channels-last, s f32).  Differentiable to any order
+    together with DotBC."""
+
+    @staticmethod
+    def forward(ctx, x, s):
+        lib.require_cuda(x, s)
+        x = _cl(x)
+        b, c, h, w = x.shape
+        sf = s.to(torch.float32).contiguous()
+        y = torch.empty_like(x, memory_format=torch.channels_last)
+        lib.scale_bc(y, x, sf, b, h * w, c)
+        ctx.save_for_backward(x, s)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, s = ctx.saved_tensors
+        gx = ScaleBC.apply(gy, s) if ctx.needs_input_grad[0] else None
+        gs = DotBC.apply(gy, x).to(s.dtype) if ctx.needs_input_grad[1] else None
+        return gx, gs
+
+
+class DotBC(Function):
+    """out[b,c] = sum_hw a * b  (f32 accumulate, f32 result)."""
+
+    @staticmethod
+    def forward(ctx, a, b_):
+        lib.require_cuda(a, b_)
+        a, b_ = _cl(a), _cl(b_.to(a.dtype))
+        n, c, h, w = a.shape
+        out = torch.zeros((n, c), dtype=torch.float32, device=a.device)
+        lib.dot_bc(out, a, b_, n, h * w, c)
+        ctx.save_for_backward(a, b_)
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        a, b_ = ctx.saved_tensors
+        ga = ScaleBC.apply(b_, go) if ctx.needs_input_grad[0] else None
+        gb = ScaleBC.apply(a, go) if ctx.needs_input_grad[1] else None
+        return ga, gb
+
+
+def scale_bc(x, s):
+    return ScaleBC.apply(x, s)
 
 
 # --------------------------------------------------------------------------------------------

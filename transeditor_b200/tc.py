@@ -126,8 +126,9 @@ def conv_raw(x, wp, mode, out_scale=None, bias=None, act=False):
     if wp.shape[2] != cin:
         raise RuntimeError("conv_tc: weight expects %d input channels, tensor has %d" % (wp.shape[2], cin))
     hout, wout = mode.output_hw(hin, win)
-    alloc = torch.empty if mode.covers_output() else torch.zeros
-    y = alloc((b, cout, hout, wout), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+    y = torch.empty((b, cout, hout, wout), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+    if not mode.covers_output():
+        y.zero_()
     f32 = lambda t: None if t is None else t.to(torch.float32).contiguous()  # noqa: E731
     osc, bi = f32(out_scale), f32(bias)
     for launch in mode.launches(hin, win, hout, wout):
