@@ -70,7 +70,8 @@ def test_fused_bias_act_all_codes_golden():
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
 @pytest.mark.parametrize("shape,cl", [((3, 5, 4, 6), False), ((2, 8, 16, 16), True), ((7, 512), False),
-                                      ((2, 4, 70, 70), False), ((9, 12), False)])
+                                      ((2, 4, 70, 70), False), ((9, 12), False), ((3, 128, 9, 9), True),
+                                      ((2, 520, 4, 4), True)])
 def test_fused_leaky_relu_first_and_second_order(dtype, shape, cl):
     from utils.op import fused_leaky_relu
     x = _rand(*shape, dtype=dtype, seed=3)
@@ -134,7 +135,8 @@ def test_upfirdn2d_golden_all_parameter_sets():
     (2, 3, 40, 70, 1, 1, (1, 1)), (2, 3, 40, 70, 1, 1, (2, 2)), (1, 2, 129, 129, 1, 1, (1, 1)),
     (1, 2, 257, 257, 1, 1, (1, 1)), (1, 1, 33, 200, 1, 1, (2, 1)), (2, 3, 16, 16, 2, 1, (2, 1)),
     (2, 3, 32, 32, 1, 2, (1, 1)), (1, 4, 9, 9, 1, 1, (2, 2)), (1, 2, 64, 64, 1, 1, (0, 0)),
-    (1, 2, 40, 36, 1, 1, (-1, 2)),
+    (1, 2, 40, 36, 1, 1, (-1, 2)), (2, 16, 20, 24, 1, 1, (1, 1)), (1, 8, 33, 17, 1, 1, (2, 2)),
+    (2, 128, 9, 9, 1, 1, (2, 2)), (1, 24, 16, 16, 1, 1, (1, 1)),
 ])
 @pytest.mark.parametrize("cl", [False, True])
 def test_upfirdn2d_matches_oracle(dtype, case, cl):
@@ -152,6 +154,21 @@ def test_upfirdn2d_matches_oracle(dtype, case, cl):
     assert y.shape == ref.shape and y.dtype == dtype
     tol = {torch.float64: 1e-7, torch.float32: 2e-6, torch.float16: 2e-3, torch.bfloat16: 1.6e-2}[dtype]
     assert (y.double().cpu() - ref).abs().max().item() <= tol * max(1.0, ref.abs().max().item())
+
+
+def test_upfirdn2d_channels_last_nonseparable_fir():
+    """The vectorised channels-last kernel takes a separable fast path; a random (rank-4) FIR must go
+    through its general path and still match."""
+    from utils.op import upfirdn2d
+    x = _rand(2, 16, 21, 19, seed=16)
+    fir = _rand(4, 4, seed=17).abs()
+    y = upfirdn2d(x.to(DEV).contiguous(memory_format=torch.channels_last), fir.to(DEV), pad=(2, 1))
+    ref = ops_cpu.upfirdn2d(x.double(), fir.double(), 1, 1, (2, 1))
+    assert (y.double().cpu() - ref).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item())
+    fir3 = _rand(3, 3, seed=18).abs()
+    y = upfirdn2d(x.to(DEV).contiguous(memory_format=torch.channels_last), fir3.to(DEV), pad=(1, 1))
+    ref = ops_cpu.upfirdn2d(x.double(), fir3.double(), 1, 1, (1, 1))
+    assert (y.double().cpu() - ref).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item())
 
 
 @pytest.mark.parametrize("case", [(2, 3, 40, 70, 1, 1, (1, 1)), (2, 3, 12, 12, 2, 1, (2, 1)),

@@ -97,39 +97,54 @@ fused_bias_act_bwd_planes(T* __restrict__ gin, typename Acc<T>::type* __restrict
   }
 }
 
-// Backward, channels-last / [rows, C] (step_b == 1): each thread owns VEC fixed columns and walks
-// down a chunk of rows; one atomic per column per chunk.
+// Backward, channels-last / [rows, C] (step_b == 1): a 256-thread CTA covers `ctpb` column vectors x
+// (256 / ctpb) rows at a time; each thread keeps VEC fixed columns and walks down its rows of the
+// chunk; partial sums meet in shared memory and leave as one atomic per column per CTA.
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256)
 fused_bias_act_bwd_cols(T* __restrict__ gin, typename Acc<T>::type* __restrict__ gbias,
                         const T* __restrict__ g, const T* __restrict__ ref, float alpha_f,
-                        float scale_f, int64_t rows, int64_t cols, int rows_per_block) {
+                        float scale_f, int64_t rows, int64_t cols, int rows_per_block, int ctpb) {
   using A = typename Acc<T>::type;
   struct alignas(sizeof(T) * VEC) V { T v[VEC]; };
+  __shared__ A red[256 * VEC];
   const A alpha = A(alpha_f), scale = A(scale_f);
-  const int64_t c0 = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * VEC;
-  if (c0 >= cols) return;
+  const int tx = threadIdx.x % ctpb, ty = threadIdx.x / ctpb;
+  const int tys = blockDim.x / ctpb;
+  const int64_t c0 = (int64_t(blockIdx.x) * ctpb + tx) * VEC;
+  const bool col_ok = c0 < cols && ty < tys;
   const int64_t r_lo = int64_t(blockIdx.y) * rows_per_block;
   const int64_t r_hi = (r_lo + rows_per_block < rows) ? r_lo + rows_per_block : rows;
   A acc[VEC];
 #pragma unroll
   for (int j = 0; j < VEC; ++j) acc[j] = A(0);
-  for (int64_t r = r_lo; r < r_hi; ++r) {
-    const int64_t off = r * cols + c0;
-    V gv = *reinterpret_cast<const V*>(g + off);
-    V rv = *reinterpret_cast<const V*>(ref + off);
-    V o;
+  if (col_ok) {
+    for (int64_t r = r_lo + ty; r < r_hi; r += tys) {
+      const int64_t off = r * cols + c0;
+      V gv = *reinterpret_cast<const V*>(g + off);
+      V rv = *reinterpret_cast<const V*>(ref + off);
+      V o;
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      A gg = to_acc(gv.v[j]);
-      A y = (to_acc(rv.v[j]) > A(0) ? gg : gg * alpha) * scale;
-      o.v[j] = from_acc<T, A>(y);
-      acc[j] += y;
+      for (int j = 0; j < VEC; ++j) {
+        A gg = to_acc(gv.v[j]);
+        A y = (to_acc(rv.v[j]) > A(0) ? gg : gg * alpha) * scale;
+        o.v[j] = from_acc<T, A>(y);
+        acc[j] += y;
+      }
+      *reinterpret_cast<V*>(gin + off) = o;
     }
-    *reinterpret_cast<V*>(gin + off) = o;
   }
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) atomicAdd(gbias + c0 + j, acc[j]);
+  for (int j = 0; j < VEC; ++j) red[threadIdx.x * VEC + j] = acc[j];
+  __syncthreads();
+  if (ty == 0 && c0 < cols) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      A sum = A(0);
+      for (int r = 0; r < tys; ++r) sum += red[(r * ctpb + tx) * VEC + j];
+      atomicAdd(gbias + c0 + j, sum);
+    }
+  }
 }
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -207,21 +222,24 @@ static int fused_bias_act_bwd_typed(void* gin_, void* gbias_, const void* g_, co
     TE_CHECK_ARG(rows * cols == n, "fused_bias_act_bwd: n not a multiple of size_b");
     const bool v = al && cols % VEC == 0;
     const int vec = v ? VEC : 1;
-    const int threads = 128;
+    const int threads = 256;
     const int64_t col_threads = cols / vec;
-    const unsigned gx = unsigned((col_threads + threads - 1) / threads);
-    // enough row chunks to fill the chip, at least 8 rows each
+    int ctpb = 1;
+    while (ctpb < 256 && ctpb < col_threads) ctpb <<= 1;  // power of two <= 256 covering the columns
+    const unsigned gx = unsigned((col_threads + ctpb - 1) / ctpb);
+    const int tys = threads / ctpb;
+    // enough row chunks to fill the chip (~8 CTAs per SM), at least 8 rows per thread row
     int64_t want = (int64_t(kNumSMs) * 8 + gx - 1) / gx;
     int64_t rpb = (rows + want - 1) / want;
-    if (rpb < 8) rpb = 8;
+    if (rpb < 8 * tys) rpb = 8 * tys;
     const unsigned gy = unsigned((rows + rpb - 1) / rpb);
     dim3 grid(gx, gy);
     if (v)
       fused_bias_act_bwd_cols<T, VEC><<<grid, threads, 0, st>>>(gin, gbias, g, ref, alpha, scale,
-                                                                rows, cols, int(rpb));
+                                                                rows, cols, int(rpb), ctpb);
     else
       fused_bias_act_bwd_cols<T, 1><<<grid, threads, 0, st>>>(gin, gbias, g, ref, alpha, scale,
-                                                              rows, cols, int(rpb));
+                                                              rows, cols, int(rpb), ctpb);
     TE_CHECK_LAUNCH();
     return TE_OK;
   }

@@ -195,6 +195,122 @@ fir_planes_tiled(T* __restrict__ out, const T* __restrict__ in, const float* __r
   }
 }
 
+// ---- channels-last hot case: up = down = 1, FIR <= 4x4, minor % VEC == 0 --------------------------
+// Thread = one 16-byte channel vector of one output column, walking down FN_TY output rows with a
+// sliding window: every input row is loaded once (4 horizontally adjacent vectors) and contributes to
+// up to 4 output rows.  When the FIR is an outer product (every FIR on this path is make_kernel([1,3,3,1]),
+// model_spatial_query.py:84-92) the row is first reduced horizontally (4 FMA) and then scattered
+// vertically (4 FMA) instead of 16 FMA per element.
+constexpr int FN_TY = 8;
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+fir_nhwc_kernel(T* __restrict__ out, const T* __restrict__ in, const float* __restrict__ fir, UpfirdnParams p,
+                int strips, int64_t total) {
+  struct alignas(sizeof(T) * VEC) V { T v[VEC]; };
+  __shared__ float sk[4][4];   // flipped, zero-extended taps
+  __shared__ float s_row[4], s_col[4];
+  __shared__ int s_sep;
+  if (threadIdx.x < 16) {
+    int ky = threadIdx.x >> 2, kx = threadIdx.x & 3;
+    sk[ky][kx] = (ky < p.kh && kx < p.kw) ? fir[(p.kh - 1 - ky) * p.kw + (p.kw - 1 - kx)] : 0.f;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // rank-1 test: k[y][x] == col[y] * row[x] with the pivot at the largest |tap|
+    int py = 0, px = 0;
+    float best = 0.f;
+    for (int y = 0; y < 4; ++y)
+      for (int x = 0; x < 4; ++x)
+        if (fabsf(sk[y][x]) > best) { best = fabsf(sk[y][x]); py = y; px = x; }
+    int sep = best > 0.f;
+    for (int y = 0; y < 4 && sep; ++y)
+      for (int x = 0; x < 4; ++x)
+        if (fabsf(sk[y][x] - sk[y][px] * (sk[py][x] / sk[py][px])) > 1e-6f * best) { sep = 0; break; }
+    for (int i = 0; i < 4; ++i) {
+      s_col[i] = sk[i][px];
+      s_row[i] = best > 0.f ? sk[py][i] / sk[py][px] : 0.f;
+    }
+    s_sep = sep;
+  }
+  __syncthreads();
+  const bool sep = s_sep != 0;
+  const int cv = p.minor / VEC;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    int64_t r = idx;
+    const int c = int(r % cv); r /= cv;
+    const int ox = int(r % p.out_w); r /= p.out_w;
+    const int strip = int(r % strips); r /= strips;
+    const int64_t n = r;
+    const int oy0 = strip * FN_TY;
+    const int ix0 = ox - p.pad_x0, iy0 = oy0 - p.pad_y0;
+    const T* src = in + n * int64_t(p.in_h) * p.in_w * p.minor + int64_t(c) * VEC;
+    float acc[FN_TY][VEC];
+#pragma unroll
+    for (int a = 0; a < FN_TY; ++a)
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) acc[a][j] = 0.f;
+#pragma unroll
+    for (int ry = 0; ry < FN_TY + 3; ++ry) {
+      const int iy = iy0 + ry;
+      if (iy < 0 || iy >= p.in_h) continue;
+      if (oy0 + ry - 3 >= p.out_h) break;  // no remaining output row needs this input row
+      float xv[4][VEC];
+#pragma unroll
+      for (int kx = 0; kx < 4; ++kx) {
+        const int ix = ix0 + kx;
+        if (ix >= 0 && ix < p.in_w && kx < p.kw) {
+          V v = *reinterpret_cast<const V*>(src + (int64_t(iy) * p.in_w + ix) * p.minor);
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) xv[kx][j] = float(to_acc(v.v[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) xv[kx][j] = 0.f;
+        }
+      }
+      if (sep) {
+        float h[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+          h[j] = xv[0][j] * s_row[0] + xv[1][j] * s_row[1] + xv[2][j] * s_row[2] + xv[3][j] * s_row[3];
+#pragma unroll
+        for (int ky = 0; ky < 4; ++ky) {
+          const int a = ry - ky;  // output row a uses input row a + ky
+          if (a >= 0 && a < FN_TY) {
+            const float t = s_col[ky];
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) acc[a][j] += h[j] * t;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int ky = 0; ky < 4; ++ky) {
+          const int a = ry - ky;
+          if (a >= 0 && a < FN_TY) {
+#pragma unroll
+            for (int kx = 0; kx < 4; ++kx) {
+              const float t = sk[ky][kx];
+#pragma unroll
+              for (int j = 0; j < VEC; ++j) acc[a][j] += xv[kx][j] * t;
+            }
+          }
+        }
+      }
+    }
+    T* dst = out + n * int64_t(p.out_h) * p.out_w * p.minor + int64_t(c) * VEC;
+#pragma unroll
+    for (int a = 0; a < FN_TY; ++a) {
+      const int oy = oy0 + a;
+      if (oy >= p.out_h) break;
+      V o;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) o.v[j] = from_acc<T, float>(acc[a][j]);
+      *reinterpret_cast<V*>(dst + (int64_t(oy) * p.out_w + ox) * p.minor) = o;
+    }
+  }
+}
+
 template <typename T>
 static int upfirdn2d_typed(void* out_, const void* in_, const float* fir, const UpfirdnParams& p,
                            cudaStream_t st) {
@@ -204,7 +320,15 @@ static int upfirdn2d_typed(void* out_, const void* in_, const float* fir, const 
   if (total == 0) return TE_OK;
   const bool hot = p.up_x == 1 && p.up_y == 1 && p.down_x == 1 && p.down_y == 1 && p.minor == 1 &&
                    p.kh <= 4 && p.kw <= 4 && p.out_w >= 16 && p.out_h >= 8 && sizeof(T) <= 4;
-  if (hot) {
+  constexpr int NVEC = 16 / sizeof(T);
+  const bool hot_cl = p.up_x == 1 && p.up_y == 1 && p.down_x == 1 && p.down_y == 1 && p.minor > 1 &&
+                      p.minor % NVEC == 0 && p.kh <= 4 && p.kw <= 4 && sizeof(T) <= 4 &&
+                      (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+  if (hot_cl) {
+    const int strips = (p.out_h + FN_TY - 1) / FN_TY;
+    const int64_t work = p.major * strips * int64_t(p.out_w) * (p.minor / NVEC);
+    fir_nhwc_kernel<T, (sizeof(T) <= 4 ? NVEC : 1)><<<grid_for(work, 256, 8), 256, 0, st>>>(out, in, fir, p, strips, work);
+  } else if (hot) {
     const FirTiling tl = fir_tiling(p.out_w, p.out_h);
     const int64_t n_tiles = p.major * tl.tiles_x * tl.tiles_y;
     const size_t smem = size_t(tl.tile_h + 3) * tl.pitch * sizeof(typename Acc<T>::type);

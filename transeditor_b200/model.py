@@ -675,18 +675,20 @@ class Discriminator(nn.Module):
             EqualLinear(channels[4], 1))
 
     def forward(self, input):
-        if _PRECISION == "bf16":
-            # conv stack in bf16 on tensor cores; the 4x4 tail (stddev, final conv, linears) in f32
-            out = self.convs(_to_bf16_cl(input)).float().contiguous()
-        else:
-            out = self.convs(input)
+        bf16 = _PRECISION == "bf16"
+        # bf16: the whole conv stack incl. final_conv on tensor cores; statistics and linears in f32
+        out = self.convs(_to_bf16_cl(input) if bf16 else input)
         batch, channel, height, width = out.shape
         group = min(batch, self.stddev_group)
         # minibatch standard deviation, one scalar per sub-batch (:844-852)
-        grouped = out.view(group, -1, self.stddev_feat, channel // self.stddev_feat, height, width)
+        stat_in = out.float().contiguous() if bf16 else out
+        grouped = stat_in.view(group, -1, self.stddev_feat, channel // self.stddev_feat, height, width)
         stddev = torch.sqrt(grouped.var(0, unbiased=False) + 1e-8)
         stddev = stddev.mean([2, 3, 4], keepdim=True).squeeze(2)
         stddev = stddev.repeat(group, 1, height, width)
-        out = torch.cat([out, stddev], 1)
-        out = self.final_conv(out)
+        if bf16:
+            out = _to_bf16_cl(torch.cat([out, stddev.to(out.dtype)], 1))  # 513 -> 520 channels
+            out = self.final_conv(out).float().contiguous()
+        else:
+            out = self.final_conv(torch.cat([out, stddev], 1))
         return self.final_linear(out.view(batch, -1))
