@@ -123,6 +123,12 @@ int te_adam_ema(float* p, const float* g, float* m, float* v, float* ema, int64_
                 float beta1, float beta2, float eps, int step, float ema_decay, float grad_scale,
                 void* stream);
 
+/* Same update with the step count t read from DEVICE memory (*step_dev >= 1), so the launch can live
+ * inside a captured CUDA graph and be replayed every iteration. */
+int te_adam_ema_devstep(float* p, const float* g, float* m, float* v, float* ema, int64_t n, float lr,
+                        float beta1, float beta2, float eps, const int* step_dev, float ema_decay,
+                        float grad_scale, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Tensor-core (tcgen05 + TMA + TMEM) implicit-GEMM convolution, bf16 operands / f32 accumulate,
  * channels-last: the speed path of ModulatedConv2d / EqualConv2d (same reference call sites as

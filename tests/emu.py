@@ -144,8 +144,12 @@ def dot_bc(out, a, b, batch, pixels, channels):
     out.add_((aa * bb).sum(1).to(out.dtype))
 
 
+def adam_ema_devstep(p, g, m, v, ema, lr, beta1, beta2, eps, step_dev, ema_decay, grad_scale):
+    adam_ema(p, g, m, v, ema, lr, beta1, beta2, eps, int(step_dev.item()), ema_decay, grad_scale)
+
+
 def install(monkeypatch):
     monkeypatch.setattr(lib, "require_cuda", lambda *a: None)
     for name in ("fused_bias_act", "fused_bias_act_bwd", "upfirdn2d", "conv2d_simt",
-                 "conv2d_wgrad_simt", "attn_core", "adam_ema", "scale_bc", "dot_bc"):
+                 "conv2d_wgrad_simt", "attn_core", "adam_ema", "adam_ema_devstep", "scale_bc", "dot_bc"):
         monkeypatch.setattr(lib, name, globals()[name])

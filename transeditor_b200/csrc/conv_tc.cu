@@ -16,9 +16,11 @@
 //   * B operand = a [BLOCK_N x 64] box of the tap-major weight tensor; every CTA reads the same
 //     weights, so they stay L2-resident (the point of the shared-weight formulation).
 //   * K loop = taps x ceil(Cin/64); each step is 4 x tcgen05.mma (M128, N=BLOCK_N, K16).
-//   * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2-5 = epilogue
-//     (TMEM lane quarter = warp_id % 4).  2 CTAs/SM are co-resident (3 stages each) so one CTA's
-//     epilogue overlaps the other's main loop.
+//   * Persistent: one CTA per SM walks the tile list.  Warp 0 = TMA producer, warp 1 = MMA issuer
+//     (+ TMEM alloc), warps 2-5 = epilogue (TMEM lane quarter = warp_id % 4).  A 6-stage (8 at
+//     BLOCK_N=64) full/empty mbarrier ring feeds the MMAs; TWO accumulator buffers in TMEM
+//     (tmem_full / tmem_empty barriers) let the producer and the MMA issuer run into the next tile
+//     while the epilogue warps drain the previous one.
 //   * Epilogue: out = act(acc * out_scale[b,cout] + bias[cout]) -> bf16 (or f32), 16-byte stores.
 #include "tc_common.cuh"
 
@@ -27,8 +29,8 @@ namespace te {
 constexpr int TC_BLOCK_M = 128;
 constexpr int TC_BLOCK_K = 64;        // bf16 elements = 128 bytes = one swizzle row
 constexpr int TC_UMMA_K = 16;
-constexpr int TC_STAGES = 3;
 constexpr int TC_THREADS = 192;
+constexpr int TC_SMEM_BUDGET = 196608;  // operand ring: 6 stages at BLOCK_N=128, 8 at BLOCK_N=64
 constexpr int TC_A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;  // 16 KB
 
 struct TcParams {
@@ -50,47 +52,55 @@ template <int BLOCK_N>
 struct TcSmem {
   static constexpr int B_BYTES = BLOCK_N * TC_BLOCK_K * 2;
   static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
-  static constexpr int BAR_OFFSET = TC_STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + 128 + 1024;  // barriers + slack for 1024-B alignment
+  static constexpr int STAGES = TC_SMEM_BUDGET / STAGE_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + slack for 1024-B alignment
 };
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Persistent kernel: one CTA per SM walks tiles t = blockIdx.x, +gridDim.x, ...; the operand ring and
+// the two TMEM accumulator buffers let the TMA producer / MMA issuer run ahead into the next tile
+// while the epilogue warps drain the previous one.
 template <int BLOCK_N, bool OUT_F32>
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ TcParams p) {
   using S = TcSmem<BLOCK_N>;
+  constexpr int STAGES = S::STAGES;
+  constexpr uint32_t TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFFSET);
-  uint64_t* empty_bar = full_bar + TC_STAGES;
-  uint64_t* tmem_full_bar = empty_bar + TC_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  // tile coordinates (n fastest so neighbouring CTAs share the activation tile through L2)
   const int n_blocks = (p.cout + BLOCK_N - 1) / BLOCK_N;
-  const int n_blk = blockIdx.x % n_blocks;
-  int m_blk = blockIdx.x / n_blocks;
-  const int tile_w = m_blk % p.tiles_w; m_blk /= p.tiles_w;
-  const int tile_h = m_blk % p.tiles_h; m_blk /= p.tiles_h;
-  const int b0 = m_blk * p.nb, ay0 = tile_h * p.th, ax0 = tile_w * p.tw, n0 = n_blk * BLOCK_N;
+  const int total_tiles = p.n_tiles * n_blocks;
   const int k_chunks = (p.cin + TC_BLOCK_K - 1) / TC_BLOCK_K;
   const int num_kb = p.ntaps * k_chunks;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
-    for (int s = 0; s < TC_STAGES; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 4);  // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // TMEM allocation: whole warp, power-of-two columns >= 32
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(static_cast<uint32_t>(BLOCK_N < 32 ? 32 : BLOCK_N))
+                 "r"(TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -99,43 +109,64 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // tile -> coordinates (n fastest so CTAs running at the same time share activation tiles in L2)
+  auto tile_coords = [&](int tile, int& b0, int& ay0, int& ax0, int& n0) {
+    const int n_blk = tile % n_blocks;
+    int m_blk = tile / n_blocks;
+    const int tile_w = m_blk % p.tiles_w; m_blk /= p.tiles_w;
+    const int tile_h = m_blk % p.tiles_h; m_blk /= p.tiles_h;
+    b0 = m_blk * p.nb; ay0 = tile_h * p.th; ax0 = tile_w * p.tw; n0 = n_blk * BLOCK_N;
+  };
+
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % TC_STAGES;
-        const uint32_t ph = (kb / TC_STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        const int tap = kb / k_chunks, kc = kb - tap * k_chunks;
-        uint8_t* a_dst = smem + s * S::STAGE_BYTES;
-        uint8_t* b_dst = a_dst + TC_A_BYTES;
-        mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
-        tma_load_4d(a_dst, &map_x, &full_bar[s], kc * TC_BLOCK_K, ax0 * p.in_stride + p.tap_dx[tap],
-                    ay0 * p.in_stride + p.tap_dy[tap], b0);
-        const int wsl = p.w_slices_per_sample ? b0 * p.w_slices_per_sample + p.tap_w[tap] : p.tap_w[tap];
-        tma_load_3d(b_dst, &map_w, &full_bar[s], kc * TC_BLOCK_K, n0, wsl);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int b0, ay0, ax0, n0;
+        tile_coords(tile, b0, ay0, ax0, n0);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          const int tap = kb / k_chunks, kc = kb - tap * k_chunks;
+          uint8_t* a_dst = smem + s * S::STAGE_BYTES;
+          uint8_t* b_dst = a_dst + TC_A_BYTES;
+          mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
+          tma_load_4d(a_dst, &map_x, &full_bar[s], kc * TC_BLOCK_K, ax0 * p.in_stride + p.tap_dx[tap],
+                      ay0 * p.in_stride + p.tap_dy[tap], b0);
+          const int wsl = p.w_slices_per_sample ? b0 * p.w_slices_per_sample + p.tap_w[tap] : p.tap_w[tap];
+          tma_load_3d(b_dst, &map_w, &full_bar[s], kc * TC_BLOCK_K, n0, wsl);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
       constexpr uint32_t idesc = make_idesc_bf16(TC_BLOCK_M, BLOCK_N);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % TC_STAGES;
-        const uint32_t ph = (kb / TC_STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+        const uint32_t buf = ti & 1;
+        mbar_wait(&tmem_empty_bar[buf], ((ti >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         tcgen05_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
-        const uint64_t da = make_sw128_desc(a_addr);
-        const uint64_t db = make_sw128_desc(a_addr + TC_A_BYTES);
+        const uint32_t d_tmem = tmem_base + buf * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
+          const uint64_t da = make_sw128_desc(a_addr);
+          const uint64_t db = make_sw128_desc(a_addr + TC_A_BYTES);
 #pragma unroll
-        for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
-          // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in 16-byte units
-          umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in 16-byte units
+            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
         }
-        umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+        umma_commit(&tmem_full_bar[buf]);  // accumulator complete
       }
-      umma_commit(tmem_full_bar);    // accumulator complete
     }
   } else {
     // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
@@ -145,66 +176,75 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const int nbi = row / per_img;
     const int rem = row - nbi * per_img;
     const int thi = rem / p.tw, twi = rem - thi * p.tw;
-    const int b = b0 + nbi, ay = ay0 + thi, ax = ax0 + twi;
-    const bool valid = b < p.batch && ay < p.grid_h && ax < p.grid_w;
-    const int bs = valid ? b : 0;
-    const float* osc = p.out_scale ? p.out_scale + static_cast<int64_t>(bs) * p.cout : nullptr;
-    const int oy = ay * p.out_stride + p.out_off_y, ox = ax * p.out_stride + p.out_off_x;
-    const int64_t pix = (static_cast<int64_t>(bs) * p.hout + oy) * p.wout + ox;
+    uint32_t ti = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      int b0, ay0, ax0, n0;
+      tile_coords(tile, b0, ay0, ax0, n0);
+      const uint32_t buf = ti & 1;
+      const int b = b0 + nbi, ay = ay0 + thi, ax = ax0 + twi;
+      const bool valid = b < p.batch && ay < p.grid_h && ax < p.grid_w;
+      const int bs = valid ? b : 0;
+      const float* osc = p.out_scale ? p.out_scale + static_cast<int64_t>(bs) * p.cout : nullptr;
+      const int oy = ay * p.out_stride + p.out_off_y, ox = ax * p.out_stride + p.out_off_x;
+      const int64_t pix = (static_cast<int64_t>(bs) * p.hout + oy) * p.wout + ox;
 
-    mbar_wait(tmem_full_bar, 0);
-    tcgen05_fence_after();
+      mbar_wait(&tmem_full_bar[buf], (ti >> 1) & 1);
+      tcgen05_fence_after();
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-      if (n0 + c0 >= p.cout) break;  // warp-uniform
-      uint32_t v[32];
-      tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c0, v);
-      float f[32];
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        if (n0 + c0 >= p.cout) break;  // warp-uniform
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * BLOCK_N + c0, v);
+        float f[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int n = n0 + c0 + j;
-        float a = __uint_as_float(v[j]);
-        if (n < p.cout) {
-          if (osc) a *= __ldg(osc + n);
-          if (p.bias) a += __ldg(p.bias + n);
+        for (int j = 0; j < 32; ++j) {
+          const int n = n0 + c0 + j;
+          float a = __uint_as_float(v[j]);
+          if (n < p.cout) {
+            if (osc) a *= __ldg(osc + n);
+            if (p.bias) a += __ldg(p.bias + n);
+          }
+          if (p.act == 1) a = (a > 0.f ? a : 0.2f * a) * 1.4142135623730951f;
+          f[j] = a;
         }
-        if (p.act == 1) a = (a > 0.f ? a : 0.2f * a) * 1.4142135623730951f;
-        f[j] = a;
-      }
-      if (valid) {
-        if (OUT_F32) {
-          float* dst = static_cast<float*>(p.y) + pix * p.cout + n0 + c0;
+        if (valid) {
+          if (OUT_F32) {
+            float* dst = static_cast<float*>(p.y) + pix * p.cout + n0 + c0;
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (n0 + c0 + 4 * j < p.cout)
-              reinterpret_cast<float4*>(dst)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-        } else {
-          __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.y) + pix * p.cout + n0 + c0;
+            for (int j = 0; j < 8; ++j)
+              if (n0 + c0 + 4 * j < p.cout)
+                reinterpret_cast<float4*>(dst)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          } else {
+            __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.y) + pix * p.cout + n0 + c0;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (n0 + c0 + 8 * j >= p.cout) continue;
-            uint4 o;
-            __nv_bfloat162 t0 = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]);
-            __nv_bfloat162 t1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
-            __nv_bfloat162 t2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
-            __nv_bfloat162 t3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
-            o.x = *reinterpret_cast<uint32_t*>(&t0);
-            o.y = *reinterpret_cast<uint32_t*>(&t1);
-            o.z = *reinterpret_cast<uint32_t*>(&t2);
-            o.w = *reinterpret_cast<uint32_t*>(&t3);
-            reinterpret_cast<uint4*>(dst)[j] = o;
+            for (int j = 0; j < 4; ++j) {
+              if (n0 + c0 + 8 * j >= p.cout) continue;
+              uint4 o;
+              __nv_bfloat162 t0 = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]);
+              __nv_bfloat162 t1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
+              __nv_bfloat162 t2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
+              __nv_bfloat162 t3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+              o.x = *reinterpret_cast<uint32_t*>(&t0);
+              o.y = *reinterpret_cast<uint32_t*>(&t1);
+              o.z = *reinterpret_cast<uint32_t*>(&t2);
+              o.w = *reinterpret_cast<uint32_t*>(&t3);
+              reinterpret_cast<uint4*>(dst)[j] = o;
+            }
           }
         }
       }
+      // this warp is done reading the accumulator buffer: hand it back to the MMA issuer
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
     }
-    tcgen05_fence_before();
   }
+  tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
     __syncwarp();
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"(static_cast<uint32_t>(BLOCK_N < 32 ? 32 : BLOCK_N))
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
                  : "memory");
   }
 }
@@ -219,7 +259,8 @@ static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const TcParam
     TE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     configured = true;
   }
-  const int grid = p.n_tiles * ((p.cout + BLOCK_N - 1) / BLOCK_N);
+  const int total = p.n_tiles * ((p.cout + BLOCK_N - 1) / BLOCK_N);
+  const int grid = total < kNumSMs ? total : kNumSMs;  // persistent: one CTA per SM
   kern<<<grid, TC_THREADS, S::TOTAL, st>>>(mx, mw, p);
   TE_CHECK_LAUNCH();
   return TE_OK;

@@ -8,21 +8,25 @@
 
 namespace te {
 
+// grid.y = sample; a CTA's threads walk the sample's P*C/VEC vectors; the channel index is one
+// 32-bit modulo per vector and the per-sample scale row stays in L1.
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256)
-scale_bc_kernel(T* __restrict__ y, const T* __restrict__ x, const float* __restrict__ s, int64_t n_vec,
-                int64_t pc_vec /* P*C/VEC */, int c_vec /* C/VEC */) {
+scale_bc_kernel(T* __restrict__ y, const T* __restrict__ x, const float* __restrict__ s, uint32_t pc_vec,
+                uint32_t c_vec) {
   struct alignas(sizeof(T) * VEC) V { T v[VEC]; };
-  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
-  for (int64_t iv = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; iv < n_vec; iv += stride) {
-    const int64_t b = iv / pc_vec;
-    const int cv = int(iv % c_vec);
-    const float* sp = s + (b * c_vec + cv) * VEC;
-    V in = reinterpret_cast<const V*>(x)[iv];
+  const int64_t base = int64_t(blockIdx.y) * pc_vec;
+  const float* srow = s + int64_t(blockIdx.y) * c_vec * VEC;
+  const V* xin = reinterpret_cast<const V*>(x) + base;
+  V* yout = reinterpret_cast<V*>(y) + base;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t iv = blockIdx.x * blockDim.x + threadIdx.x; iv < pc_vec; iv += stride) {
+    const float* sp = srow + (iv % c_vec) * VEC;
+    V in = xin[iv];
     V o;
 #pragma unroll
     for (int j = 0; j < VEC; ++j) o.v[j] = from_acc<T, float>(float(to_acc(in.v[j])) * __ldg(sp + j));
-    reinterpret_cast<V*>(y)[iv] = o;
+    yout[iv] = o;
   }
 }
 
@@ -68,10 +72,15 @@ static int scale_bc_typed(void* y, const void* x, const float* s, int64_t batch,
                           cudaStream_t st) {
   constexpr int VEC = 16 / sizeof(T);
   TE_CHECK_ARG(c % VEC == 0, "scale_bc: channel count %d must be a multiple of %d", c, VEC);
-  const int64_t n_vec = batch * pixels * c / VEC;
-  if (n_vec == 0) return TE_OK;
-  scale_bc_kernel<T, VEC><<<grid_for(n_vec, 256, 16), 256, 0, st>>>(
-      static_cast<T*>(y), static_cast<const T*>(x), s, n_vec, pixels * c / VEC, c / VEC);
+  const int64_t pc_vec = pixels * c / VEC;
+  if (batch * pc_vec == 0) return TE_OK;
+  TE_CHECK_ARG(pc_vec < (int64_t(1) << 31) && batch <= 65535, "scale_bc: tensor too large");
+  int64_t want = (int64_t(kNumSMs) * 16 + batch - 1) / batch;       // CTAs per sample for ~16 waves
+  int64_t need = (pc_vec + 255) / 256;
+  const unsigned gx = unsigned(need < want ? need : want);
+  dim3 grid(gx > 0 ? gx : 1, unsigned(batch));
+  scale_bc_kernel<T, VEC><<<grid, 256, 0, st>>>(static_cast<T*>(y), static_cast<const T*>(x), s,
+                                                uint32_t(pc_vec), uint32_t(c / VEC));
   TE_CHECK_LAUNCH();
   return TE_OK;
 }

@@ -119,7 +119,30 @@ fused_bias_act_bwd_cols(T* __restrict__ gin, typename Acc<T>::type* __restrict__
 #pragma unroll
   for (int j = 0; j < VEC; ++j) acc[j] = A(0);
   if (col_ok) {
-    for (int64_t r = r_lo + ty; r < r_hi; r += tys) {
+    // 4 rows per trip: 8 independent 16-byte loads in flight per thread
+    int64_t r = r_lo + ty;
+    for (; r + 3 * int64_t(tys) < r_hi; r += 4 * int64_t(tys)) {
+      V gv[4], rv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t off = (r + u * int64_t(tys)) * cols + c0;
+        gv[u] = *reinterpret_cast<const V*>(g + off);
+        rv[u] = *reinterpret_cast<const V*>(ref + off);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        V o;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          A gg = to_acc(gv[u].v[j]);
+          A y = (to_acc(rv[u].v[j]) > A(0) ? gg : gg * alpha) * scale;
+          o.v[j] = from_acc<T, A>(y);
+          acc[j] += y;
+        }
+        *reinterpret_cast<V*>(gin + (r + u * int64_t(tys)) * cols + c0) = o;
+      }
+    }
+    for (; r < r_hi; r += tys) {
       const int64_t off = r * cols + c0;
       V gv = *reinterpret_cast<const V*>(g + off);
       V rv = *reinterpret_cast<const V*>(ref + off);
@@ -231,7 +254,7 @@ static int fused_bias_act_bwd_typed(void* gin_, void* gbias_, const void* g_, co
     // enough row chunks to fill the chip (~8 CTAs per SM), at least 8 rows per thread row
     int64_t want = (int64_t(kNumSMs) * 8 + gx - 1) / gx;
     int64_t rpb = (rows + want - 1) / want;
-    if (rpb < 8 * tys) rpb = 8 * tys;
+    if (rpb < 16 * tys) rpb = 16 * tys;
     const unsigned gy = unsigned((rows + rpb - 1) / rpb);
     dim3 grid(gx, gy);
     if (v)

@@ -20,8 +20,13 @@ __global__ void __launch_bounds__(256)
 adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                 float* __restrict__ v, float* __restrict__ ema, int64_t n4, int64_t n, float lr,
                 float b1, float b2, float eps, float bc1, float bc2_sqrt, float ema_decay,
-                float gscale) {
+                float gscale, const int* __restrict__ step_dev) {
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  if (step_dev) {  // CUDA-graph friendly: the step count lives on the device
+    const float t = float(*step_dev);
+    bc1 = 1.f - ((b1 == 0.f) ? 0.f : powf(b1, t));
+    bc2_sqrt = sqrtf(1.f - powf(b2, t));
+  }
   const float step_size = lr / bc1;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 pv = reinterpret_cast<float4*>(p)[i];
@@ -137,7 +142,23 @@ extern "C" int te_adam_ema(float* p, const float* g, float* m, float* v, float* 
   const double bc2 = 1.0 - pow(double(beta2), double(step));
   adam_ema_kernel<<<grid_for(n4 > 0 ? n4 : n, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       p, g, m, v, ema, n4, n, lr, beta1, beta2, eps, float(bc1), float(sqrt(bc2)), ema_decay,
-      grad_scale);
+      grad_scale, nullptr);
+  TE_CHECK_LAUNCH();
+  return TE_OK;
+}
+
+extern "C" int te_adam_ema_devstep(float* p, const float* g, float* m, float* v, float* ema, int64_t n,
+                                   float lr, float beta1, float beta2, float eps, const int* step_dev,
+                                   float ema_decay, float grad_scale, void* stream) {
+  using namespace te;
+  if (n == 0) return TE_OK;
+  TE_CHECK_ARG(p && g && m && v && step_dev, "adam_ema_devstep: null pointer");
+  const uintptr_t al = reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) |
+                       reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v) |
+                       reinterpret_cast<uintptr_t>(ema);
+  const int64_t n4 = (al & 15) == 0 ? n / 4 : 0;
+  adam_ema_kernel<<<grid_for(n4 > 0 ? n4 : n, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      p, g, m, v, ema, n4, n, lr, beta1, beta2, eps, 1.f, 1.f, ema_decay, grad_scale, step_dev);
   TE_CHECK_LAUNCH();
   return TE_OK;
 }

@@ -201,7 +201,7 @@ fir_planes_tiled(T* __restrict__ out, const T* __restrict__ in, const float* __r
 // up to 4 output rows.  When the FIR is an outer product (every FIR on this path is make_kernel([1,3,3,1]),
 // model_spatial_query.py:84-92) the row is first reduced horizontally (4 FMA) and then scattered
 // vertically (4 FMA) instead of 16 FMA per element.
-constexpr int FN_TY = 8;
+constexpr int FN_TY = 4;
 
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256)
@@ -254,20 +254,21 @@ fir_nhwc_kernel(T* __restrict__ out, const T* __restrict__ in, const float* __re
 #pragma unroll
     for (int ry = 0; ry < FN_TY + 3; ++ry) {
       const int iy = iy0 + ry;
-      if (iy < 0 || iy >= p.in_h) continue;
-      if (oy0 + ry - 3 >= p.out_h) break;  // no remaining output row needs this input row
+      // predicated (branch-free) loads so the compiler can keep several rows in flight
+      const bool row_ok = iy >= 0 && iy < p.in_h && (oy0 + ry - 3 < p.out_h);
       float xv[4][VEC];
 #pragma unroll
       for (int kx = 0; kx < 4; ++kx) {
         const int ix = ix0 + kx;
-        if (ix >= 0 && ix < p.in_w && kx < p.kw) {
-          V v = *reinterpret_cast<const V*>(src + (int64_t(iy) * p.in_w + ix) * p.minor);
-#pragma unroll
-          for (int j = 0; j < VEC; ++j) xv[kx][j] = float(to_acc(v.v[j]));
+        V v;
+        if (row_ok && ix >= 0 && ix < p.in_w) {
+          v = *reinterpret_cast<const V*>(src + (int64_t(iy) * p.in_w + ix) * p.minor);
         } else {
 #pragma unroll
-          for (int j = 0; j < VEC; ++j) xv[kx][j] = 0.f;
+          for (int j = 0; j < VEC; ++j) v.v[j] = from_acc<T, float>(0.f);
         }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) xv[kx][j] = float(to_acc(v.v[j]));
       }
       if (sep) {
         float h[VEC];

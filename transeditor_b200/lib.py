@@ -51,6 +51,7 @@ _SIGNATURES = {
     "te_conv2d_simt": ([_P, _P, _P, _P, _P, _P, _P, _P, ctypes.POINTER(ConvGeom), _I, _P], _I),
     "te_conv2d_wgrad_simt": ([_P, _P, _P, _P, _P, ctypes.POINTER(ConvGeom), _I, _P], _I),
     "te_adam_ema": ([_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _F, _P], _I),
+    "te_adam_ema_devstep": ([_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _P, _F, _F, _P], _I),
     "te_conv_tc": ([_P, _P, _P, _P, _P, ctypes.POINTER(TcConvDesc), _P], _I),
     "te_conv_wgrad_tc": ([_P, _P, _P, ctypes.POINTER(TcConvDesc), _P], _I),
     "te_scale_bc": ([_P, _P, _P, _L, _L, _I, _I, _P], _I),
@@ -155,6 +156,12 @@ def conv2d_wgrad_simt(gw, x, gy, in_scale, out_scale, geom):
 def adam_ema(p, g, m, v, ema, lr, beta1, beta2, eps, step, ema_decay, grad_scale):
     _check(load().te_adam_ema(ptr(p), ptr(g), ptr(m), ptr(v), ptr(ema), p.numel(), lr, beta1, beta2,
                               eps, step, ema_decay, grad_scale, stream()), "adam_ema")
+    _count()
+
+
+def adam_ema_devstep(p, g, m, v, ema, lr, beta1, beta2, eps, step_dev, ema_decay, grad_scale):
+    _check(load().te_adam_ema_devstep(ptr(p), ptr(g), ptr(m), ptr(v), ptr(ema), p.numel(), lr, beta1, beta2,
+                                      eps, ptr(step_dev), ema_decay, grad_scale, stream()), "adam_ema_devstep")
     _count()
 
 

@@ -104,8 +104,10 @@ class FlatAdam:
         self.lr, self.betas, self.eps = lr, betas, eps
         self.m = torch.zeros_like(flat.data)
         self.v = torch.zeros_like(flat.data)
-        # per-range step counters: Adam's bias correction counts the updates a parameter received
-        self.steps = [0] * len(flat.group_end)
+        # per-range step counters (Adam's bias correction counts the updates a parameter received);
+        # they live on the DEVICE so that the update can be replayed from a captured CUDA graph
+        self.steps = [torch.zeros(1, dtype=torch.int32, device=flat.data.device)
+                      for _ in flat.group_end]
 
     def step(self, n_groups, grad_scale=1.0):
         """Update parameter groups [0, n_groups) (the main group is group 0)."""
@@ -113,11 +115,11 @@ class FlatAdam:
         for gi in range(n_groups):
             hi = self.flat.group_end[gi]
             if hi > lo:
-                self.steps[gi] += 1
+                self.steps[gi].add_(1)
                 sl = slice(lo, hi)
-                lib.adam_ema(self.flat.data[sl], self.flat.grad[sl], self.m[sl], self.v[sl], None,
-                             self.lr, self.betas[0], self.betas[1], self.eps, self.steps[gi], 0.0,
-                             grad_scale)
+                lib.adam_ema_devstep(self.flat.data[sl], self.flat.grad[sl], self.m[sl], self.v[sl], None,
+                                     self.lr, self.betas[0], self.betas[1], self.eps, self.steps[gi], 0.0,
+                                     grad_scale)
             lo = hi
 
 
@@ -185,6 +187,40 @@ class Trainer:
         self.mean_path_length = torch.zeros((), device=self.device)
         self.iteration = 0
         self.losses = {}
+        self.use_graphs = False
+        self._graphs = {}
+        self._real = None  # static input buffer (graph replays read from it)
+
+    # ------------------------------------------------------------------ CUDA graphs
+    def enable_graphs(self, flag=True):
+        """Replay each phase (D step, R1, G step, path regulariser) from captured CUDA graphs: forward +
+        backward in one graph, the optimiser update in a second one, the NCCL gradient all-reduce issued
+        between them.  Call after at least one eager iteration (lazy initialisation must be done)."""
+        self.use_graphs = flag
+
+    def _phase(self, name, fwdbwd, flat, optim, n_groups):
+        if not self.use_graphs:
+            fwdbwd()
+            self._reduce_and_step(flat, optim, n_groups)
+            return
+        entry = self._graphs.get(name)
+        if entry is None:
+            torch.cuda.synchronize()
+            n0 = lib.launch_count
+            ga = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ga):
+                fwdbwd()
+            gb = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gb):
+                optim.step(n_groups, grad_scale=1.0 / self.world)
+            entry = (ga, gb, lib.launch_count - n0)
+            self._graphs[name] = entry
+        ga, gb, launches = entry
+        ga.replay()
+        if self.world > 1:
+            dist.all_reduce(flat.grad, op=dist.ReduceOp.SUM)
+        gb.replay()
+        lib.launch_count += launches
 
     # ------------------------------------------------------------------ pieces of one iteration
     def _latents(self, n):
@@ -198,30 +234,30 @@ class Trainer:
             dist.all_reduce(flat.grad, op=dist.ReduceOp.SUM)
         optim.step(n_groups, grad_scale=1.0 / self.world)
 
-    def d_step(self, real_img):
+    def _d_fwdbwd(self):
         _set_requires_grad(self.g_flat, False)
         _set_requires_grad(self.d_flat, True)
         z, p = self._latents(self.cfg.batch)
         fake_img, _, _ = self.generator(z, p)
         fake_pred = self.discriminator(fake_img)
-        real_pred = self.discriminator(real_img)
+        real_pred = self.discriminator(self._real)
         d_loss = d_logistic_loss(real_pred, fake_pred)
         self.d_flat.grad.zero_()
         d_loss.backward()
-        self._reduce_and_step(self.d_flat, self.d_optim, 1)
         self.losses.update(d=d_loss.detach(), real_score=real_pred.mean().detach(),
                            fake_score=fake_pred.mean().detach())
 
-    def d_regularize(self, real_img):
-        real_img = real_img.detach().requires_grad_(True)
+    def _dreg_fwdbwd(self):
+        _set_requires_grad(self.g_flat, False)
+        _set_requires_grad(self.d_flat, True)
+        real_img = self._real.detach().requires_grad_(True)
         real_pred = self.discriminator(real_img)
         r1_loss = d_r1_loss(real_pred, real_img)
         self.d_flat.grad.zero_()
         (self.cfg.r1 / 2 * r1_loss * self.cfg.d_reg_every + 0 * real_pred[0]).backward()
-        self._reduce_and_step(self.d_flat, self.d_optim, 1)
         self.losses["r1"] = r1_loss.detach()
 
-    def g_step(self):
+    def _g_fwdbwd(self):
         _set_requires_grad(self.g_flat, True)
         _set_requires_grad(self.d_flat, False)
         z, p = self._latents(self.cfg.batch)
@@ -229,25 +265,46 @@ class Trainer:
         g_loss = g_nonsaturating_loss(self.discriminator(fake_img))
         self.g_flat.grad.zero_()
         g_loss.backward()
-        # noise strengths receive no gradient when noise injection is off (reference: grad None)
-        self._reduce_and_step(self.g_flat, self.g_optim, 2)
         self.losses["g"] = g_loss.detach()
 
-    def g_regularize(self):
+    def _greg_fwdbwd(self):
         c = self.cfg
+        _set_requires_grad(self.g_flat, True)
+        _set_requires_grad(self.d_flat, False)
         n = max(1, c.batch // c.path_batch_shrink)
         z, p = self._latents(n)
         fake_img, latents, _ = self.generator(z, p, return_latents=True)
-        path_loss, self.mean_path_length, path_lengths = g_path_regularize(
-            fake_img, latents, self.mean_path_length)
+        path_loss, path_mean, path_lengths = g_path_regularize(fake_img, latents, self.mean_path_length)
         self.g_flat.grad.zero_()
         weighted = c.path_regularize * c.g_reg_every * path_loss
         if c.path_batch_shrink:
             weighted = weighted + 0 * fake_img[0, 0, 0, 0]
         weighted.backward()
-        # to_rgb biases get no gradient from the path penalty -> skipped like Adam skips grad=None
-        self._reduce_and_step(self.g_flat, self.g_optim, 1)
+        self.mean_path_length.copy_(path_mean)  # in place: a static buffer for graph replays
         self.losses.update(path=path_loss.detach(), path_length=path_lengths.mean().detach())
+
+    def _set_real(self, real_img):
+        if real_img is self._real:
+            return
+        if self._real is None or self._real.shape != real_img.shape:
+            self._real = torch.empty(real_img.shape, dtype=torch.float32, device=self.device)
+        self._real.copy_(real_img, non_blocking=True)
+
+    def d_step(self, real_img):
+        self._set_real(real_img)
+        self._phase("d", self._d_fwdbwd, self.d_flat, self.d_optim, 1)
+
+    def d_regularize(self, real_img):
+        self._set_real(real_img)
+        self._phase("dreg", self._dreg_fwdbwd, self.d_flat, self.d_optim, 1)
+
+    def g_step(self):
+        # noise strengths receive no gradient when noise injection is off (reference: grad None)
+        self._phase("g", self._g_fwdbwd, self.g_flat, self.g_optim, 2)
+
+    def g_regularize(self):
+        # to_rgb biases get no gradient from the path penalty -> skipped like Adam skips grad=None
+        self._phase("greg", self._greg_fwdbwd, self.g_flat, self.g_optim, 1)
 
     def ema_update(self):
         """accumulate(g_ema, g_module, 0.5 ** (32 / 10000)), train_spatial_query.py:56-61,294"""
@@ -269,8 +326,8 @@ class Trainer:
 
     def step_from_host(self, real_pinned):
         """End-to-end form: host (pinned) images in, host loss scalars out."""
-        real = real_pinned.to(self.device, non_blocking=True)
-        losses = self.step(real)
+        self._set_real(real_pinned)  # H2D straight into the static input buffer
+        losses = self.step(self._real)
         keys = sorted(losses)
         host = torch.stack([losses[k].float() for k in keys]).cpu()  # D2H + sync, like the .item()s at :298-306
         return dict(zip(keys, host.tolist()))
