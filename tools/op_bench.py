@@ -68,6 +68,23 @@ def main():
             res["upfirdn2d_blur_f32 [16,128,256,256]->257^2 (D)"] = {"ms": ms, "GB/s": byts / ms / 1e6,
                                                                      "frac_hbm": byts / ms / 1e6 / PEAKS["hbm_gbs"]}
             del x
+        if want("upfirdn2d_blur_bf16_nhwc"):
+            x = torch.randn(16, 128, 257, 257, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            ms = timeit(lambda: upfirdn2d(x, fir, pad=(1, 1)), a.iters)
+            byts = 2 * 16 * 128 * (257 * 257 + 256 * 256)
+            res["upfirdn2d_blur_bf16_nhwc [16,257,257,128]->256^2"] = {"ms": ms, "GB/s": byts / ms / 1e6,
+                                                                       "frac_hbm": byts / ms / 1e6 / PEAKS["hbm_gbs"]}
+            del x
+        if want("scale_bc"):
+            x = torch.randn(16, 128, 256, 256, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            sc = torch.rand(16, 128, device=dev) + 0.5
+            ms = timeit(lambda: op.scale_bc(x, sc), a.iters)
+            byts = 2 * 2 * x.numel()
+            res["scale_bc_bf16 [16,256,256,128]"] = {"ms": ms, "GB/s": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / PEAKS["hbm_gbs"]}
+            from transeditor_b200.op import DotBC
+            ms = timeit(lambda: DotBC.apply(x, x), a.iters)
+            res["dot_bc_bf16 [16,256,256,128]"] = {"ms": ms, "GB/s": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / PEAKS["hbm_gbs"]}
+            del x
         if want("fused_bias_act_f32"):
             x = torch.randn(16, 128, 256, 256, device=dev)
             b = torch.randn(128, device=dev)
@@ -101,6 +118,15 @@ def main():
             byts = 2.0 * (b * h * h * (cin + cout) + 9 * cin * cout)
             res[name] = {"ms": ms, "TFLOP/s": fl / ms / 1e9, "frac_tensor": fl / ms / 1e9 / PEAKS["tf"],
                          "GB/s_algorithmic": byts / ms / 1e6}
+            ms = timeit(lambda: op.conv2d_tc(x, wp, 3), a.iters)
+            res[name + " (plain epilogue)"] = {"ms": ms, "TFLOP/s": fl / ms / 1e9,
+                                               "frac_tensor": fl / ms / 1e9 / PEAKS["tf"]}
+            from transeditor_b200 import tc
+            gy = torch.randn(b, cout, h, h, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            ms = timeit(lambda: tc.wgrad_raw(gy, x, tc.Mode("s1", 3), (cout, cin, 3, 3)), a.iters)
+            res[name.replace("conv2d_tc", "wgrad_tc")] = {"ms": ms, "TFLOP/s": fl / ms / 1e9,
+                                                          "frac_tensor": fl / ms / 1e9 / PEAKS["tf"]}
+            del gy
             del x
     for k, v in res.items():
         print(k, {kk: round(vv, 4) for kk, vv in v.items()}, flush=True)

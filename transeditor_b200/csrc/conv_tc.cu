@@ -54,7 +54,8 @@ struct TcSmem {
   static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
   static constexpr int STAGES = TC_SMEM_BUDGET / STAGE_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + slack for 1024-B alignment
+  static constexpr int EPI_OFFSET = BAR_OFFSET + 256;     // per-epilogue-warp scale/bias staging
+  static constexpr int TOTAL = EPI_OFFSET + 4 * 2 * BLOCK_N * 4 + 1024;  // + slack for 1024-B alignment
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -176,11 +177,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const int nbi = row / per_img;
     const int rem = row - nbi * per_img;
     const int thi = rem / p.tw, twi = rem - thi * p.tw;
+    // per-warp staging of out_scale / bias for the tile (valid when the tile lies in one sample)
+    float* s_osc = reinterpret_cast<float*>(smem + S::EPI_OFFSET) + quarter * 2 * BLOCK_N;
+    float* s_bias = s_osc + BLOCK_N;
+    const bool staged = p.nb == 1;
     uint32_t ti = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
       int b0, ay0, ax0, n0;
       tile_coords(tile, b0, ay0, ax0, n0);
       const uint32_t buf = ti & 1;
+      if (staged) {
+        __syncwarp();
+        for (int c = lane; c < BLOCK_N; c += 32) {
+          const int n = n0 + c;
+          s_osc[c] = (p.out_scale && n < p.cout) ? __ldg(p.out_scale + static_cast<int64_t>(b0) * p.cout + n) : 1.f;
+          s_bias[c] = (p.bias && n < p.cout) ? __ldg(p.bias + n) : 0.f;
+        }
+        __syncwarp();
+      }
       const int b = b0 + nbi, ay = ay0 + thi, ax = ax0 + twi;
       const bool valid = b < p.batch && ay < p.grid_h && ax < p.grid_w;
       const int bs = valid ? b : 0;
@@ -196,16 +210,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         uint32_t v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * BLOCK_N + c0, v);
         float f[32];
+        if (staged) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = n0 + c0 + j;
-          float a = __uint_as_float(v[j]);
-          if (n < p.cout) {
-            if (osc) a *= __ldg(osc + n);
-            if (p.bias) a += __ldg(p.bias + n);
+          for (int j = 0; j < 32; j += 4) {
+            const float4 sc = *reinterpret_cast<const float4*>(s_osc + c0 + j);
+            const float4 bi = *reinterpret_cast<const float4*>(s_bias + c0 + j);
+            f[j] = __uint_as_float(v[j]) * sc.x + bi.x;
+            f[j + 1] = __uint_as_float(v[j + 1]) * sc.y + bi.y;
+            f[j + 2] = __uint_as_float(v[j + 2]) * sc.z + bi.z;
+            f[j + 3] = __uint_as_float(v[j + 3]) * sc.w + bi.w;
           }
-          if (p.act == 1) a = (a > 0.f ? a : 0.2f * a) * 1.4142135623730951f;
-          f[j] = a;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = n0 + c0 + j;
+            float a = __uint_as_float(v[j]);
+            if (n < p.cout) {
+              if (osc) a *= __ldg(osc + n);
+              if (p.bias) a += __ldg(p.bias + n);
+            }
+            f[j] = a;
+          }
+        }
+        if (p.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = (f[j] > 0.f ? f[j] : 0.2f * f[j]) * 1.4142135623730951f;
         }
         if (valid) {
           if (OUT_F32) {
