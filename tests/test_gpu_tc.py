@@ -146,3 +146,33 @@ def test_tc_flagship_wgrad_and_dgrad_shapes():
     ref = torch.nn.grad.conv2d_weight(x[:1].float(), (128, 128, 3, 3), gy[:1].float(), padding=1)
     got = tc.wgrad_raw(gy[:1], x[:1], mode, (128, 128, 3, 3))
     _close(got, ref, "flagship wgrad sample 0", rel=5e-3)
+
+
+@pytest.mark.parametrize("kind,h,k", [("s1", 16, 3), ("up", 16, 3), ("down", 17, 3), ("s1", 32, 1)])
+def test_tc_per_sample_weights(kind, h, k):
+    """Per-sample weights [B,O,I,K,K] (the reference's groups=batch formulation): forward, data gradient,
+    per-sample weight gradient and second order against a per-sample loop of torch convolutions."""
+    b, cin, cout = 3, 64, 64
+    x = _bf(_rand(b, cin, h, h, seed=21))
+    w = _rand(b, cout, cin, k, k, seed=22, scale=1.0 / math.sqrt(cin * k * k))
+
+    def ref_fn(xx, ww, _kind):
+        return torch.cat([_ref(xx[i:i + 1], ww[i], kind) for i in range(b)])
+
+    def run(fn, xin, win, cast):
+        xx = xin.clone().requires_grad_(True)
+        ww = win.clone().requires_grad_(True)
+        y = fn(xx, ww, kind)
+        gy = cast(_rand(*y.shape, seed=23)).requires_grad_(True)
+        gx, gw = torch.autograd.grad(y, (xx, ww), gy, create_graph=True)
+        u = cast(_rand(*gx.shape, seed=24))
+        v = _rand(*gw.shape, seed=25)
+        s = (gx.float() * u.float()).sum() + (gw * v).sum()
+        h_gy, h_x, h_w = torch.autograd.grad(s, (gy, xx, ww))
+        return [t.detach().float() for t in (y, gx, gw, h_gy, h_x, h_w)]
+
+    got = run(_ours, x, w, _bf)
+    ref = run(ref_fn, x.float(), w.to(torch.bfloat16).float(), lambda t: _bf(t).float())
+    for a, r, nm in zip(got, ref, ("y", "gx", "gw", "h_gy", "h_x", "h_w")):
+        assert a.shape == r.shape, nm
+        _close(a, r, "%s per-sample %s" % (nm, kind), rel=2e-2)

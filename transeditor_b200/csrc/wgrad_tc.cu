@@ -5,9 +5,11 @@
 // i.e. per tap a GEMM  D[cout, cin] = G^T . X  whose reduction dimension is the PIXELS.  Both operands are
 // read by TMA as [anchor rows x 64 channels] boxes straight from the channels-last tensors, which makes
 // them MN-major UMMA operands (the channel dimension is contiguous): no transpose pass exists anywhere.
-//   * CTA tile: 128 (cout) x 128 (cin), up to 4 taps resident (4 x 128 TMEM columns = all 512).
-//   * stage = 64 anchors of ONE tap: G tile 2 x [64 x 64ch] + X tile 2 x [64 x 64ch] = 32 KB, 5-stage ring.
-//   * 4 x tcgen05.mma (M128, N128, K16 anchors) per stage.
+//   * CTA tile: 128 (cout) x 128 (cin), up to 3 taps resident in TMEM (3 x 128 of the 512 columns).
+//   * stage = 64 anchors: ONE G tile (2 x [64 x 64ch]) shared by the taps + one shifted X tile per tap
+//     (2 x [64 x 64ch] each) = 16 + 3*16 = 64 KB, 3-stage ring: G is fetched once per anchor tile.
+//   * 4 x tcgen05.mma (M128, N128, K16 anchors) per tap per stage; taps are balanced over grid.y
+//     (9 taps -> 3 groups of 3, 4 -> 2 x 2).
 //   * split-K over anchor tiles (grid.z) so the chip is filled even when Cout*Cin is one tile;
 //     partial sums are combined with vectorised f32 reductions (red.global.add.v4.f32).
 //   * Out-of-range anchors / padding taps / channel tails are zero-filled by the TMA unit.
@@ -17,22 +19,26 @@ namespace te {
 
 constexpr int WG_M = 128, WG_N = 128;
 constexpr int WG_KA = 64;              // anchors per stage
-constexpr int WG_STAGES = 5;
-constexpr int WG_TAPS = 4;             // taps resident in TMEM
+constexpr int WG_STAGES = 3;
+constexpr int WG_TAPS = 3;             // taps resident in TMEM
 constexpr int WG_THREADS = 192;
 constexpr int WG_HALF_BYTES = WG_KA * 128;          // one [64 anchors x 64 ch] box = 8 KB
-constexpr int WG_STAGE_BYTES = 4 * WG_HALF_BYTES;   // G lo, G hi, X lo, X hi = 32 KB
+constexpr int WG_TILE_BYTES = 2 * WG_HALF_BYTES;    // [64 anchors x 128 ch] = 16 KB
+constexpr int WG_STAGE_BYTES = (1 + WG_TAPS) * WG_TILE_BYTES;   // G + 3 X tiles = 64 KB
 constexpr int WG_BAR_OFFSET = WG_STAGES * WG_STAGE_BYTES;
 constexpr int WG_SMEM_TOTAL = WG_BAR_OFFSET + 128 + 1024;
 
 struct WgParams {
   int batch, cin, cout;
-  int ntaps;
+  int ntaps, taps_per_group;
   int tap_dy[9], tap_dx[9], tap_w[9];
   int in_stride, out_stride, out_off_y, out_off_x;
   int tw, th, nb;                 // anchor tile patch; nb*th*tw == 64
   int tiles_w, tiles_h, tiles_b, n_tiles;
   int tiles_per_split;
+  int splits_per_sample;          // > 0: per-sample gradients (grid.z = batch * splits_per_sample)
+  int tiles_per_sample;
+  int64_t gw_bstride;             // elements between two samples' gradients (per-sample mode)
   int use_atomics;
   float* gw;                      // [w_slices, cout, cin]
 };
@@ -54,11 +60,20 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_blocks = (p.cin + WG_N - 1) / WG_N;
   const int m0 = (blockIdx.x / n_blocks) * WG_M, n0 = (blockIdx.x % n_blocks) * WG_N;
-  const int tap0 = blockIdx.y * WG_TAPS;
-  const int ntap = min(WG_TAPS, p.ntaps - tap0);
-  const int tile_lo = blockIdx.z * p.tiles_per_split;
-  const int tile_hi = min(p.n_tiles, tile_lo + p.tiles_per_split);
-  const int num_it = (tile_hi - tile_lo) * ntap;  // pipeline iterations: (tile, tap) pairs
+  const int tap0 = blockIdx.y * p.taps_per_group;
+  const int ntap = min(p.taps_per_group, p.ntaps - tap0);
+  int tile_lo, tile_hi;
+  float* gw_base = p.gw;
+  if (p.splits_per_sample > 0) {  // every sample owns its own gradient slice
+    const int smp = blockIdx.z / p.splits_per_sample, part = blockIdx.z % p.splits_per_sample;
+    tile_lo = smp * p.tiles_per_sample + part * p.tiles_per_split;
+    tile_hi = min((smp + 1) * p.tiles_per_sample, tile_lo + p.tiles_per_split);
+    gw_base += smp * p.gw_bstride;
+  } else {
+    tile_lo = blockIdx.z * p.tiles_per_split;
+    tile_hi = min(p.n_tiles, tile_lo + p.tiles_per_split);
+  }
+  const int num_it = max(0, tile_hi - tile_lo);  // pipeline iterations: anchor tiles
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_g)) : "memory");
@@ -88,20 +103,22 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
         const int s = it % WG_STAGES;
         const uint32_t ph = (it / WG_STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
-        const int tl = it / ntap, tp = it - tl * ntap;
-        int t = tile_lo + tl;
+        int t = tile_lo + it;
         const int tile_w = t % p.tiles_w; t /= p.tiles_w;
         const int tile_h = t % p.tiles_h; t /= p.tiles_h;
         const int b0 = t * p.nb, ay0 = tile_h * p.th, ax0 = tile_w * p.tw;
-        const int tap = tap0 + tp;
         uint8_t* dst = smem + s * WG_STAGE_BYTES;
-        mbar_expect_tx(&full_bar[s], WG_STAGE_BYTES);
+        mbar_expect_tx(&full_bar[s], (1 + ntap) * WG_TILE_BYTES);
         const int gx = ax0 * p.out_stride + p.out_off_x, gy = ay0 * p.out_stride + p.out_off_y;
         tma_load_4d(dst, &map_g, &full_bar[s], m0, gx, gy, b0);
         tma_load_4d(dst + WG_HALF_BYTES, &map_g, &full_bar[s], m0 + 64, gx, gy, b0);
-        const int xx = ax0 * p.in_stride + p.tap_dx[tap], xy = ay0 * p.in_stride + p.tap_dy[tap];
-        tma_load_4d(dst + 2 * WG_HALF_BYTES, &map_x, &full_bar[s], n0, xx, xy, b0);
-        tma_load_4d(dst + 3 * WG_HALF_BYTES, &map_x, &full_bar[s], n0 + 64, xx, xy, b0);
+        for (int tp = 0; tp < ntap; ++tp) {
+          const int tap = tap0 + tp;
+          uint8_t* xd = dst + (1 + tp) * WG_TILE_BYTES;
+          const int xx = ax0 * p.in_stride + p.tap_dx[tap], xy = ay0 * p.in_stride + p.tap_dy[tap];
+          tma_load_4d(xd, &map_x, &full_bar[s], n0, xx, xy, b0);
+          tma_load_4d(xd + WG_HALF_BYTES, &map_x, &full_bar[s], n0 + 64, xx, xy, b0);
+        }
       }
     }
   } else if (warp == 1) {
@@ -113,14 +130,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
         const uint32_t ph = (it / WG_STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
         tcgen05_fence_after();
-        const int tl = it / ntap, tp = it - tl * ntap;
         const uint32_t base = smem_u32(smem + s * WG_STAGE_BYTES);
+        for (int tp = 0; tp < ntap; ++tp) {
 #pragma unroll
-        for (int k = 0; k < WG_KA / 16; ++k) {
-          // 16 anchors = two 8-row groups = 2048 bytes further down the tile
-          const uint64_t da = make_sw128_mn_desc(base + k * 2048, WG_HALF_BYTES);
-          const uint64_t db = make_sw128_mn_desc(base + 2 * WG_HALF_BYTES + k * 2048, WG_HALF_BYTES);
-          umma_bf16(tmem_base + tp * WG_N, da, db, idesc, (tl | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < WG_KA / 16; ++k) {
+            // 16 anchors = two 8-row groups = 2048 bytes further down the tile
+            const uint64_t da = make_sw128_mn_desc(base + k * 2048, WG_HALF_BYTES);
+            const uint64_t db = make_sw128_mn_desc(base + (1 + tp) * WG_TILE_BYTES + k * 2048, WG_HALF_BYTES);
+            umma_bf16(tmem_base + tp * WG_N, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+          }
         }
         umma_commit(&empty_bar[s]);
       }
@@ -134,7 +152,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
     tcgen05_fence_after();
     if (num_it > 0) {
       for (int tp = 0; tp < ntap; ++tp) {
-        float* row = p.gw + (static_cast<int64_t>(p.tap_w[tap0 + tp]) * p.cout + m) * p.cin + n0;
+        float* row = gw_base + (static_cast<int64_t>(p.tap_w[tap0 + tp]) * p.cout + m) * p.cin + n0;
 #pragma unroll 1
         for (int c0 = 0; c0 < WG_N; c0 += 32) {
           if (n0 + c0 >= p.cin) break;
@@ -203,14 +221,34 @@ extern "C" int te_conv_wgrad_tc(float* gw, const void* g, const void* x, const t
   p.gw = gw;
   const int out_tiles = ((d.cout + WG_M - 1) / WG_M) * ((d.cin + WG_N - 1) / WG_N);
   const int tap_groups = (d.ntaps + WG_TAPS - 1) / WG_TAPS;
+  p.taps_per_group = (d.ntaps + tap_groups - 1) / tap_groups;  // balanced: 9 -> 3+3+3, 4 -> 2+2
   // split the anchor reduction so that about one wave of CTAs exists, at least 8 tiles per split
-  int splits = (kNumSMs + out_tiles * tap_groups - 1) / (out_tiles * tap_groups);
-  int max_splits = (p.n_tiles + 7) / 8;
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
-  p.tiles_per_split = (p.n_tiles + splits - 1) / splits;
-  splits = (p.n_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
-  p.use_atomics = splits > 1 ? 1 : 0;
+  int splits;
+  p.splits_per_sample = 0; p.tiles_per_sample = 0; p.gw_bstride = 0;
+  if (d.w_bstride != 0) {
+    TE_CHECK_ARG(p.nb == 1, "conv_wgrad_tc: per-sample gradients need >= 64 anchors per sample");
+    TE_CHECK_ARG(d.w_bstride == int64_t(d.w_slices) * d.cout * d.cin, "conv_wgrad_tc: per-sample gradients must be densely packed");
+    p.tiles_per_sample = p.tiles_w * p.tiles_h;
+    int sps = (kNumSMs + out_tiles * tap_groups * d.batch - 1) / (out_tiles * tap_groups * d.batch);
+    int max_sps = (p.tiles_per_sample + 7) / 8;
+    if (sps > max_sps) sps = max_sps;
+    if (sps < 1) sps = 1;
+    p.tiles_per_split = (p.tiles_per_sample + sps - 1) / sps;
+    sps = (p.tiles_per_sample + p.tiles_per_split - 1) / p.tiles_per_split;
+    p.splits_per_sample = sps;
+    p.gw_bstride = d.w_bstride;
+    splits = sps * d.batch;
+    p.use_atomics = sps > 1 ? 1 : 0;
+    TE_CHECK_ARG(splits <= 65535, "conv_wgrad_tc: grid.z too large");
+  } else {
+    splits = (kNumSMs + out_tiles * tap_groups - 1) / (out_tiles * tap_groups);
+    int max_splits = (p.n_tiles + 7) / 8;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    p.tiles_per_split = (p.n_tiles + splits - 1) / splits;
+    splits = (p.n_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+    p.use_atomics = splits > 1 ? 1 : 0;
+  }
 
   CUtensorMap mg, mx;
   {

@@ -275,6 +275,26 @@ def _modconv_forward_tc(self, x, s, d, wn, bias, noise, noise_weight, activate, 
         wn = F.pad(wn, (0, 0, 0, 0, 0, 0, 0, 8 - cout % 8))
         if d is not None:
             d = F.pad(d, (0, 8 - cout % 8), value=1.0)
+    hw = x.shape[2] * x.shape[3]
+    if hw >= 128 and hw >= 4 * wn.shape[0] * k * k:
+        # High resolution: per-sample weights W*s*d (the reference's own formulation, :299-304) are tiny
+        # next to the activations (1-15 % of their size), so fold modulation AND demodulation into them
+        # and skip every activation-sized scaling pass, forward and backward.
+        wb = wn.unsqueeze(0) * s[:, None, :, None, None]
+        if d is not None:
+            wb = wb * d[:, :, None, None, None]
+        if self.upsample:
+            v = self.blur(tc.conv_transpose2d(x, wb))
+        elif fused_ok and noise is None:
+            pb = None if bias is None else F.pad(bias.reshape(-1), (0, wn.shape[0] - cout))
+            v = tc.conv_raw(x, tc.pack_weight(wb, False), tc.Mode("s1", k), bias=pb, act=activate)
+            return v if wn.shape[0] == cout else v[:, :cout]
+        else:
+            v = tc.conv2d(x, wb)
+        if wn.shape[0] != cout:
+            v = v[:, :cout]
+        return _epilogue(v, bias, noise, noise_weight, activate)
+    # Low resolution: shared weights, modulation / demodulation applied to the (small) activations.
     u = op.scale_bc(x, s)
     if self.upsample:
         v = self.blur(tc.conv_transpose2d(u, wn))

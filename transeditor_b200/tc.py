@@ -79,7 +79,16 @@ class Mode:
 
 def pack_weight(w, transposed):
     """Master weight [O, I, K, K] (f32) -> bf16 slices [K*K, Cout, Cin] (Cin contiguous), channel counts
-    padded to multiples of 8 with zeros."""
+    padded to multiples of 8 with zeros.  A leading batch dimension ([B, O, I, K, K] -> [B, K*K, Cout, Cin])
+    gives per-sample weights."""
+    if w.dim() == 5:
+        b, o, i, k, _ = w.shape
+        if o % 8 or i % 8:
+            raise RuntimeError("per-sample tensor-core weights need channel counts that are multiples of 8")
+        if transposed:
+            w = w.transpose(1, 2)
+            o, i = i, o
+        return w.permute(0, 3, 4, 1, 2).reshape(b, k * k, o, i).to(torch.bfloat16).contiguous()
     o, i, k, _ = w.shape
     if transposed:
         w = w.transpose(0, 1)
@@ -93,7 +102,7 @@ def pack_weight(w, transposed):
     return wp.contiguous()
 
 
-def _desc(x, cout, hout, wout, launch, w_slices, act=0, out_f32=0):
+def _desc(x, cout, hout, wout, launch, w_slices, act=0, out_f32=0, per_sample=False):
     taps, ist, ost, oy, ox, gh, gw = launch
     b, cin, hin, win = x.shape
     d = lib.TcConvDesc()
@@ -105,7 +114,8 @@ def _desc(x, cout, hout, wout, launch, w_slices, act=0, out_f32=0):
     d.w_slices = w_slices
     d.in_stride, d.out_stride, d.out_off_y, d.out_off_x = ist, ost, oy, ox
     d.grid_h, d.grid_w = gh, gw
-    d.act, d.out_f32, d.w_bstride = act, out_f32, 0
+    d.act, d.out_f32 = act, out_f32
+    d.w_bstride = w_slices * cout * cin if per_sample else 0
     return d
 
 
@@ -122,9 +132,10 @@ def conv_raw(x, wp, mode, out_scale=None, bias=None, act=False):
     lib.require_cuda(x, wp, out_scale, bias)
     x = _cl_bf16(x)
     b, cin, hin, win = x.shape
-    cout = wp.shape[1]
-    if wp.shape[2] != cin:
-        raise RuntimeError("conv_tc: weight expects %d input channels, tensor has %d" % (wp.shape[2], cin))
+    per_sample = wp.dim() == 4
+    cout = wp.shape[-2]
+    if wp.shape[-1] != cin or (per_sample and wp.shape[0] != b):
+        raise RuntimeError("conv_tc: weight %s does not match activations %s" % (tuple(wp.shape), tuple(x.shape)))
     hout, wout = mode.output_hw(hin, win)
     y = torch.empty((b, cout, hout, wout), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
     if not mode.covers_output():
@@ -132,7 +143,8 @@ def conv_raw(x, wp, mode, out_scale=None, bias=None, act=False):
     f32 = lambda t: None if t is None else t.to(torch.float32).contiguous()  # noqa: E731
     osc, bi = f32(out_scale), f32(bias)
     for launch in mode.launches(hin, win, hout, wout):
-        lib.conv_tc(y, x, wp, osc, bi, _desc(x, cout, hout, wout, launch, wp.shape[0], 1 if act else 0))
+        lib.conv_tc(y, x, wp, osc, bi, _desc(x, cout, hout, wout, launch, wp.shape[-3], 1 if act else 0,
+                                             per_sample=per_sample))
     return y
 
 
@@ -143,10 +155,16 @@ def wgrad_raw(g, x, mode, w_shape):
     b, cin, hin, win = x.shape
     cout, hout, wout = g.shape[1], g.shape[2], g.shape[3]
     k = mode.k
-    gw = torch.zeros((k * k, cout, cin), dtype=torch.float32, device=x.device)
+    per_sample = len(w_shape) == 5
+    shape = (b, k * k, cout, cin) if per_sample else (k * k, cout, cin)
+    gw = torch.zeros(shape, dtype=torch.float32, device=x.device)
     for launch in mode.launches(hin, win, hout, wout):
-        lib.conv_wgrad_tc(gw, g, x, _desc(x, cout, hout, wout, launch, k * k))
-    o, i = w_shape[0], w_shape[1]
+        lib.conv_wgrad_tc(gw, g, x, _desc(x, cout, hout, wout, launch, k * k, per_sample=per_sample))
+    o, i = w_shape[-4], w_shape[-3]
+    if per_sample:
+        if mode.transposed:
+            return gw[:, :, :i, :o].permute(0, 3, 2, 1).reshape(b, o, i, k, k).contiguous()
+        return gw[:, :, :o, :i].permute(0, 2, 3, 1).reshape(b, o, i, k, k).contiguous()
     if mode.transposed:   # logical (cout, cin) = (I_store, O_store)
         return gw[:, :i, :o].permute(2, 1, 0).reshape(o, i, k, k).contiguous()
     return gw[:, :o, :i].permute(1, 2, 0).reshape(o, i, k, k).contiguous()
@@ -198,12 +216,13 @@ class TcWeightGrad(Function):
 
 
 def conv2d(x, w, stride=1):
-    """F.conv2d(x, w, stride, padding = k//2 if stride == 1 else 0) in bf16 on tensor cores."""
-    k = w.shape[2]
+    """F.conv2d(x, w, stride, padding = k//2 if stride == 1 else 0) in bf16 on tensor cores.
+    w [O, I, K, K], or [B, O, I, K, K] for per-sample weights (the reference's groups=batch form)."""
+    k = w.shape[-1]
     return TcConv.apply(x, w, Mode("s1" if stride == 1 else "down", k))
 
 
 def conv_transpose2d(x, w_oi, stride=2):
     """F.conv_transpose2d(x, w_oi.transpose(0, 1), stride=2, padding=0), weight kept [O, I, K, K]."""
     assert stride == 2
-    return TcConv.apply(x, w_oi, Mode("up", w_oi.shape[2]))
+    return TcConv.apply(x, w_oi, Mode("up", w_oi.shape[-1]))
