@@ -53,7 +53,7 @@ def main():
     def want(n):
         return a.only is None or a.only in n
 
-    with torch.no_grad():
+    if True:
         if want("upfirdn2d_blur_f32"):
             x = torch.randn(16, 128, 257, 257, device=dev)
             ms = timeit(lambda: upfirdn2d(x, fir, pad=(1, 1)), a.iters)
@@ -97,7 +97,15 @@ def main():
             byts = 2 * 2 * x.numel()
             res["fused_bias_act_bf16_nhwc [16,128,256,256]"] = {"ms": ms, "GB/s": byts / ms / 1e6,
                                                                 "frac_hbm": byts / ms / 1e6 / PEAKS["hbm_gbs"]}
-            del x, xb
+            gy = torch.randn_like(xb)
+            xr = xb.clone().requires_grad_(True)
+            br = b.to(torch.bfloat16).clone().requires_grad_(True)
+            yb = fused_leaky_relu(xr, br)
+            ms = timeit(lambda: torch.autograd.grad(yb, (xr, br), gy, retain_graph=True), a.iters)
+            byts = 3 * 2 * x.numel()
+            res["fused_bias_act_bwd_bf16_nhwc [16,128,256,256]"] = {"ms": ms, "GB/s": byts / ms / 1e6,
+                                                                    "frac_hbm": byts / ms / 1e6 / PEAKS["hbm_gbs"]}
+            del x, xb, gy, xr, yb
         if want("conv_simt"):
             x = torch.randn(16, 128, 256, 256, device=dev)
             w = torch.randn(128, 128, 3, 3, device=dev) / 34
