@@ -150,7 +150,13 @@ class KernelMeter:
                 _fn(*args)
                 e1.record()
                 flops, byts = self._work(_name, args)
-                self.records.append((_name, e0, e1, flops, byts))
+                tag = None
+                if _name in ("conv_tc", "conv_wgrad_tc"):
+                    d = args[-1]
+                    tag = "%s b%d cin%d cout%d grid%dx%d taps%d is%d os%d ps%d" % (
+                        _name, d.batch, d.cin, d.cout, d.grid_h, d.grid_w, d.ntaps, d.in_stride, d.out_stride,
+                        1 if d.w_bstride else 0)
+                self.records.append((_name, e0, e1, flops, byts, tag))
             setattr(lib, name, wrapped)
 
     def uninstall(self):
@@ -161,12 +167,20 @@ class KernelMeter:
     def summary(self):
         torch.cuda.synchronize()
         agg = {}
-        for name, e0, e1, flops, byts in self.records:
+        shapes = {}
+        for name, e0, e1, flops, byts, tag in self.records:
             a = agg.setdefault(name, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            ms = e0.elapsed_time(e1)
             a["launches"] += 1
-            a["ms"] += e0.elapsed_time(e1)
+            a["ms"] += ms
             a["flops"] += flops
             a["bytes"] += byts
+            if tag:
+                t = shapes.setdefault(tag, [0, 0.0, 0.0])
+                t[0] += 1
+                t[1] += ms
+                t[2] += flops
+        self.shapes = shapes
         return agg
 
 
@@ -329,6 +343,11 @@ def run_ours(args, rank, local_rank, world):
     trainer.step(real_dev)
     meter.uninstall()
     roof, table = roofline_from(meter.summary(), _peaks())
+    if args.shapes_out and rank == 0:
+        rows = sorted(meter.shapes.items(), key=lambda kv: -kv[1][1])
+        with open(args.shapes_out, "w") as f:
+            for tag, (n, ms, fl) in rows:
+                f.write("%-78s n=%3d  %8.3f ms  %7.1f TFLOP/s\n" % (tag, n, ms, fl / ms / 1e9 if ms > 0 else 0))
 
     images = args.steps * cfg.batch * world
     line = {"metric": METRIC, "value": round(images / (ms * 1e-3), 3), "unit": UNIT, "n_gpus": world,
@@ -369,6 +388,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
                     help="bf16: tcgen05 tensor-core path (BASELINE configs[1]); fp32: SIMT parity path")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--shapes-out", default=None, help="write per-shape conv timings of the instrumented step here")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ncu", action="store_true",
                     help="profiling aid: W warm-up + K steps only, prints no bench line (numbers under ncu are never bench values)")
