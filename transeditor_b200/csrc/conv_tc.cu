@@ -22,6 +22,8 @@
 //     (tmem_full / tmem_empty barriers) let the producer and the MMA issuer run into the next tile
 //     while the epilogue warps drain the previous one.
 //   * Epilogue: out = act(acc * out_scale[b,cout] + bias[cout]) -> bf16 (or f32), 16-byte stores.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace te {
@@ -43,6 +45,7 @@ struct TcParams {
   int tiles_w, tiles_h, tiles_b, n_tiles;
   int w_slices_per_sample; // 0: shared weights; else slices per sample (weights indexed b*slices + w_t)
   int act;
+  int debug;               // TE_TC_DEBUG bits (profiling aid): 1 no stores, 2 no epilogue work, 4 no MMAs
   const float* out_scale;  // [B, cout] or null
   const float* bias;       // [cout] or null
   void* y;
@@ -159,10 +162,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
           const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
           const uint64_t da = make_sw128_desc(a_addr);
           const uint64_t db = make_sw128_desc(a_addr + TC_A_BYTES);
+          if (!(p.debug & 4)) {
 #pragma unroll
-          for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in 16-byte units
-            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
+              // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in 16-byte units
+              umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
         }
@@ -206,7 +211,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
       tcgen05_fence_after();
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        if (n0 + c0 >= p.cout) break;  // warp-uniform
+        if (n0 + c0 >= p.cout || (p.debug & 2)) break;  // warp-uniform
         uint32_t v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * BLOCK_N + c0, v);
         float f[32];
@@ -236,7 +241,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = (f[j] > 0.f ? f[j] : 0.2f * f[j]) * 1.4142135623730951f;
         }
-        if (valid) {
+        if (valid && !(p.debug & 1)) {
           if (OUT_F32) {
             float* dst = static_cast<float*>(p.y) + pix * p.cout + n0 + c0;
 #pragma unroll
@@ -329,6 +334,11 @@ static int conv_tc_dispatch(void* y, const void* x, const void* w, const float* 
   p.tiles_b = (d.batch + p.nb - 1) / p.nb;
   p.n_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
   p.act = d.act; p.out_scale = out_scale; p.bias = bias; p.y = y;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("TE_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+    p.debug = dbg;
+  }
   p.w_slices_per_sample = 0;
   if (d.w_bstride != 0) {
     TE_CHECK_ARG(d.w_bstride == int64_t(d.w_slices) * d.cout * d.cin, "conv_tc: per-sample weights must be densely packed");
