@@ -345,7 +345,11 @@ static int conv_tc_dispatch(void* y, const void* x, const void* w, const float* 
     TE_CHECK_ARG(p.nb == 1, "conv_tc: per-sample weights need >= 128 anchors per sample");
     p.w_slices_per_sample = d.w_slices;
   }
-  const int block_n = (d.cout % 128 == 0) ? 128 : 64;
+  // N tile: 256 halves the A-operand shared-memory reads per FLOP (one-CTA UMMA at M128 x N128 is bound by
+  // the 128 B/cycle shared-memory port: every K16 step reads 4 KB of A + 4 KB of B in 64 cycles); used when
+  // the layer still yields >= 2 tiles per SM.
+  int block_n = (d.cout % 128 == 0) ? 128 : 64;
+  if (d.cout % 256 == 0 && int64_t(p.n_tiles) * (d.cout / 256) >= 2 * kNumSMs) block_n = 256;
 
   CUtensorMap mx, mw;
   {
@@ -366,6 +370,8 @@ static int conv_tc_dispatch(void* y, const void* x, const void* w, const float* 
     int rc = encode_map_bf16(&mw, w, 3, dims, strides, box, nullptr);
     if (rc) return rc;
   }
+  if (block_n == 256)
+    return d.out_f32 ? launch_tc<256, true>(mx, mw, p, st) : launch_tc<256, false>(mx, mw, p, st);
   if (block_n == 128)
     return d.out_f32 ? launch_tc<128, true>(mx, mw, p, st) : launch_tc<128, false>(mx, mw, p, st);
   return d.out_f32 ? launch_tc<64, true>(mx, mw, p, st) : launch_tc<64, false>(mx, mw, p, st);

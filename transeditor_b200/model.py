@@ -697,7 +697,10 @@ class Discriminator(nn.Module):
     def forward(self, input):
         bf16 = _PRECISION == "bf16"
         # bf16: the whole conv stack incl. final_conv on tensor cores; statistics and linears in f32
-        out = self.convs(_to_bf16_cl(input) if bf16 else input)
+        # RGB is zero-padded to 64 channels: a TMA box whose rows are mostly out of bounds (8 of 64 channels)
+        # takes the unit's slow path (measured 4 us per tile); a dense 128-byte row costs 134 MB of extra
+        # input but runs at full speed
+        out = self.convs(_to_bf16_cl(input, pad_to=64) if bf16 else input)
         batch, channel, height, width = out.shape
         group = min(batch, self.stddev_group)
         # minibatch standard deviation, one scalar per sub-batch (:844-852)
