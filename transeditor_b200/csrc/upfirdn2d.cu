@@ -69,7 +69,7 @@ upfirdn2d_generic(T* __restrict__ out, const T* __restrict__ in, const float* __
 // 256 threads arranged threads_x x threads_y (chosen per launch so that odd widths such as 257 split
 // into equal tiles: 257 -> 3 tiles of 88 columns, 22 x 11 threads), each thread a 4x4 output block.
 constexpr int FT_THREADS = 256;
-constexpr int FT_MAX_SMEM_ELEMS = 6144;  // (tile_h + 3) * pitch upper bound for every layout below
+constexpr int FT_MAX_SMEM_ELEMS = 5632;  // (tile_h + 3) * pitch upper bound for every layout below
 
 struct FirTiling {
   int threads_x, threads_y, tile_w, tile_h, pitch, tiles_x, tiles_y;
@@ -252,6 +252,166 @@ fir_planes_tiled(T* __restrict__ out, const T* __restrict__ in, const float* __r
           if (ox + b < p.out_w) q[b] = from_acc<T, A>(acc[a][b]);
       }
     }
+  }
+}
+
+// ---- f32 planes, separable FIR: cp.async double-buffered version of fir_planes_tiled -------------
+// The synchronous kernel alternates "load tile -> barrier -> compute -> store" and relies on other CTAs to
+// hide the global-load latency (ncu: long-scoreboard stalls, 0.51 of HBM peak).  Here every CTA prefetches
+// tile i+1 into the second shared buffer with cp.async (4-byte copies: plane rows such as 257 floats are not
+// 16-byte aligned; src-size 0 zero-fills the padding halo) while it computes tile i.
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc, bool valid) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  const int n = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+
+__global__ void __launch_bounds__(FT_THREADS)
+fir_planes_async(float* __restrict__ out, const float* __restrict__ in, const float* __restrict__ fir,
+                 UpfirdnParams p, FirTiling tl, int64_t n_tiles, int buf_elems) {
+  extern __shared__ __align__(16) unsigned char fir_smem[];
+  float* sbuf = reinterpret_cast<float*>(fir_smem);
+  __shared__ float sk[4][4];
+  __shared__ float s_row[4], s_col[4];
+  __shared__ int s_sep;
+  if (threadIdx.x < 16) {
+    int ky = threadIdx.x >> 2, kx = threadIdx.x & 3;
+    sk[ky][kx] = (ky < p.kh && kx < p.kw) ? fir[(p.kh - 1 - ky) * p.kw + (p.kw - 1 - kx)] : 0.f;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {  // rank-1 test + factorisation, pivot at the largest |tap|
+    int py = 0, px = 0;
+    float best = 0.f;
+    for (int y = 0; y < 4; ++y)
+      for (int x = 0; x < 4; ++x)
+        if (fabsf(sk[y][x]) > best) { best = fabsf(sk[y][x]); py = y; px = x; }
+    int sepf = best > 0.f;
+    for (int y = 0; y < 4 && sepf; ++y)
+      for (int x = 0; x < 4; ++x)
+        if (fabsf(sk[y][x] - sk[y][px] * (sk[py][x] / sk[py][px])) > 1e-6f * best) { sepf = 0; break; }
+    for (int i = 0; i < 4; ++i) {
+      s_col[i] = sk[i][px];
+      s_row[i] = best > 0.f ? sk[py][i] / sk[py][px] : 0.f;
+    }
+    s_sep = sepf;
+  }
+  __syncthreads();
+  const bool sep = s_sep != 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tx = threadIdx.x % tl.threads_x, ty = threadIdx.x / tl.threads_x;
+  const bool worker = ty < tl.threads_y;
+  const int rows_in = tl.tile_h + 3, cols_in = tl.tile_w + 3;
+  const bool vec_store = (p.out_w % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+
+  auto prefetch = [&](int64_t tile, float* sx) {
+    int64_t r = tile;
+    const int tcol = int(r % tl.tiles_x); r /= tl.tiles_x;
+    const int trow = int(r % tl.tiles_y); r /= tl.tiles_y;
+    const int ix0 = tcol * tl.tile_w - p.pad_x0, iy0 = trow * tl.tile_h - p.pad_y0;
+    const float* src = in + r * int64_t(p.in_h) * p.in_w;
+    for (int ry = warp; ry < rows_in; ry += FT_THREADS / 32) {
+      const int iy = iy0 + ry;
+      const bool row_ok = iy >= 0 && iy < p.in_h;
+      const float* srow = src + int64_t(row_ok ? iy : 0) * p.in_w;
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const int c = lane + 32 * j;
+        if (c < cols_in) {
+          const int ix = ix0 + c;
+          const bool ok = row_ok && ix >= 0 && ix < p.in_w;
+          cp_async4(sx + ry * tl.pitch + c, srow + (ok ? ix : 0), ok);
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  int64_t tile = blockIdx.x;
+  if (tile < n_tiles) prefetch(tile, sbuf);
+  int it = 0;
+  for (; tile < n_tiles; tile += gridDim.x, ++it) {
+    float* sx = sbuf + (it & 1) * buf_elems;
+    const int64_t next = tile + gridDim.x;
+    if (next < n_tiles) {
+      prefetch(next, sbuf + ((it + 1) & 1) * buf_elems);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    int64_t r = tile;
+    const int tcol = int(r % tl.tiles_x); r /= tl.tiles_x;
+    const int trow = int(r % tl.tiles_y); r /= tl.tiles_y;
+    const int64_t plane = r;
+    const int ox0 = tcol * tl.tile_w, oy0 = trow * tl.tile_h;
+    if (worker) {
+      float2 acc2[4][2];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) acc2[a][0] = acc2[a][1] = make_float2(0.f, 0.f);
+      const float2 r0 = make_float2(s_row[0], s_row[0]), r1 = make_float2(s_row[1], s_row[1]);
+      const float2 r2 = make_float2(s_row[2], s_row[2]), r3 = make_float2(s_row[3], s_row[3]);
+      if (!sep) {  // general 4x4 FIR: 16 taps per output from the same shared tile
+#pragma unroll
+        for (int ry = 0; ry < 7; ++ry) {
+          const float* rp = sx + (ty * 4 + ry) * tl.pitch + tx * 4;
+          float rowv[8];
+#pragma unroll
+          for (int j = 0; j < 7; ++j) rowv[j] = rp[j];
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            const int ky = ry - a;
+            if (ky >= 0 && ky < 4) {
+#pragma unroll
+              for (int kx = 0; kx < 4; ++kx) {
+                const float t = sk[ky][kx];
+                acc2[a][0].x += rowv[kx] * t;     acc2[a][0].y += rowv[1 + kx] * t;
+                acc2[a][1].x += rowv[2 + kx] * t; acc2[a][1].y += rowv[3 + kx] * t;
+              }
+            }
+          }
+        }
+      } else
+#pragma unroll
+      for (int ry = 0; ry < 7; ++ry) {
+        const float* rp = sx + (ty * 4 + ry) * tl.pitch + tx * 4;
+        const float4 q0 = *reinterpret_cast<const float4*>(rp);
+        const float4 q1 = *reinterpret_cast<const float4*>(rp + 4);
+        float2 h01 = __fmul2_rn(make_float2(q0.x, q0.y), r0);
+        h01 = __ffma2_rn(make_float2(q0.y, q0.z), r1, h01);
+        h01 = __ffma2_rn(make_float2(q0.z, q0.w), r2, h01);
+        h01 = __ffma2_rn(make_float2(q0.w, q1.x), r3, h01);
+        float2 h23 = __fmul2_rn(make_float2(q0.z, q0.w), r0);
+        h23 = __ffma2_rn(make_float2(q0.w, q1.x), r1, h23);
+        h23 = __ffma2_rn(make_float2(q1.x, q1.y), r2, h23);
+        h23 = __ffma2_rn(make_float2(q1.y, q1.z), r3, h23);
+#pragma unroll
+        for (int ky = 0; ky < 4; ++ky) {
+          const int a = ry - ky;
+          if (a >= 0 && a < 4) {
+            const float2 ck = make_float2(s_col[ky], s_col[ky]);
+            acc2[a][0] = __ffma2_rn(h01, ck, acc2[a][0]);
+            acc2[a][1] = __ffma2_rn(h23, ck, acc2[a][1]);
+          }
+        }
+      }
+      float* dst = out + plane * int64_t(p.out_h) * p.out_w;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int oy = oy0 + ty * 4 + a;
+        const int ox = ox0 + tx * 4;
+        if (oy >= p.out_h || ox >= p.out_w) continue;
+        float* q = dst + int64_t(oy) * p.out_w + ox;
+        if (vec_store && ox + 3 < p.out_w) {
+          *reinterpret_cast<float4*>(q) = make_float4(acc2[a][0].x, acc2[a][0].y, acc2[a][1].x, acc2[a][1].y);
+        } else {
+          const float v[4] = {acc2[a][0].x, acc2[a][0].y, acc2[a][1].x, acc2[a][1].y};
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+            if (ox + b < p.out_w) q[b] = v[b];
+        }
+      }
+    }
+    __syncthreads();  // buffer (it & 1) may be refilled by the prefetch issued in the next iteration
   }
 }
 
@@ -577,8 +737,16 @@ static int upfirdn2d_typed(void* out_, const void* in_, const float* fir, const 
     const FirTiling tl = fir_tiling(p.out_w, p.out_h);
     const int64_t n_tiles = p.major * tl.tiles_x * tl.tiles_y;
     const size_t smem = size_t(tl.tile_h + 3) * tl.pitch * sizeof(typename Acc<T>::type);
-    int64_t blocks = n_tiles < int64_t(kNumSMs) * 8 ? n_tiles : int64_t(kNumSMs) * 8;
-    fir_planes_tiled<T><<<unsigned(blocks), FT_THREADS, smem, st>>>(out, in, fir, p, tl, n_tiles);
+    if constexpr (sizeof(T) == 4) {
+      // f32: cp.async double-buffered kernel; ~4 resident CTAs per SM, a few tiles each
+      const int buf_elems = (tl.tile_h + 3) * tl.pitch;
+      int64_t blocks = n_tiles < int64_t(kNumSMs) * 4 ? n_tiles : int64_t(kNumSMs) * 4;
+      fir_planes_async<<<unsigned(blocks), FT_THREADS, 2 * smem, st>>>(
+          reinterpret_cast<float*>(out), reinterpret_cast<const float*>(in), fir, p, tl, n_tiles, buf_elems);
+    } else {
+      int64_t blocks = n_tiles < int64_t(kNumSMs) * 8 ? n_tiles : int64_t(kNumSMs) * 8;
+      fir_planes_tiled<T><<<unsigned(blocks), FT_THREADS, smem, st>>>(out, in, fir, p, tl, n_tiles);
+    }
   } else {
     upfirdn2d_generic<T><<<grid_for(total, 256, 32), 256, 0, st>>>(out, in, fir, p, total);
   }
