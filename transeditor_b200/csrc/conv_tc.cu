@@ -25,6 +25,7 @@
 #include <stdlib.h>
 
 #include "tc_common.cuh"
+#include "conv_tc2.cuh"
 
 namespace te {
 
@@ -283,6 +284,247 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   }
 }
 
+// ---- 2-CTA (cta_group::2) kernel: see conv_tc2.cuh for the protocol --------------------------------
+template <int BLOCK_N>
+struct Tc2Smem {
+  static constexpr int B_BYTES = (BLOCK_N / 2) * TC_BLOCK_K * 2;   // this CTA's half of the weight tile
+  static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+  static constexpr int STAGES = TC_SMEM_BUDGET / STAGE_BYTES;      // 8 at N=128, 6 at N=256
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int EPI_OFFSET = BAR_OFFSET + 256;
+  static constexpr int TOTAL = EPI_OFFSET + 4 * 2 * BLOCK_N * 4 + 1024;
+};
+
+template <int BLOCK_N, bool OUT_F32>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                const __grid_constant__ TcParams p) {
+  using S = Tc2Smem<BLOCK_N>;
+  constexpr int STAGES = S::STAGES;
+  constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFFSET);   // used in the leader only
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2], used in the leader only
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int n_blocks = (p.cout + BLOCK_N - 1) / BLOCK_N;
+  const int m_pairs = (p.n_tiles + 1) / 2;
+  const int total_work = m_pairs * n_blocks;
+  const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int k_chunks = (p.cin + TC_BLOCK_K - 1) / TC_BLOCK_K;
+  const int num_kb = p.ntaps * k_chunks;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 8);  // 4 epilogue warps x 2 CTAs
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto work_coords = [&](int w, int& b0, int& ay0, int& ax0, int& n0) {
+    const int n_blk = w % n_blocks;
+    int m_blk = (w / n_blocks) * 2 + int(rank);   // this CTA's M tile of the pair
+    const int tile_w = m_blk % p.tiles_w; m_blk /= p.tiles_w;
+    const int tile_h = m_blk % p.tiles_h; m_blk /= p.tiles_h;
+    b0 = m_blk * p.nb; ay0 = tile_h * p.th; ax0 = tile_w * p.tw; n0 = n_blk * BLOCK_N;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer (both CTAs): own A tile + own half of the B tile, signalling the leader's barrier =====
+      uint32_t it = 0;
+      for (int w = pair_id; w < total_work; w += num_pairs) {
+        int b0, ay0, ax0, n0;
+        work_coords(w, b0, ay0, ax0, n0);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          const int tap = kb / k_chunks, kc = kb - tap * k_chunks;
+          uint8_t* a_dst = smem + s * S::STAGE_BYTES;
+          uint8_t* b_dst = a_dst + TC_A_BYTES;
+          if (leader) mbar_expect_tx(&full_bar[s], 2 * S::STAGE_BYTES);
+          tma2_load_4d(a_dst, &map_x, &full_bar[s], kc * TC_BLOCK_K, ax0 * p.in_stride + p.tap_dx[tap],
+                       ay0 * p.in_stride + p.tap_dy[tap], b0);
+          const int wsl = p.w_slices_per_sample ? b0 * p.w_slices_per_sample + p.tap_w[tap] : p.tap_w[tap];
+          tma2_load_3d(b_dst, &map_w, &full_bar[s], kc * TC_BLOCK_K, n0 + int(rank) * (BLOCK_N / 2), wsl);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      // ===== MMA issuer (leader only): M256 x BLOCK_N x K16 across the pair =====
+      constexpr uint32_t idesc = make_idesc_bf16(2 * TC_BLOCK_M, BLOCK_N);
+      uint32_t it = 0, ti = 0;
+      for (int w = pair_id; w < total_work; w += num_pairs, ++ti) {
+        const uint32_t buf = ti & 1;
+        mbar_wait(&tmem_empty_bar[buf], ((ti >> 1) & 1) ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
+          const uint64_t da = make_sw128_desc(a_addr);
+          const uint64_t db = make_sw128_desc(a_addr + TC_A_BYTES);
+          if (!(p.debug & 4)) {
+#pragma unroll
+            for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k)
+              umma2_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma2_commit_both(&empty_bar[s]);
+        }
+        umma2_commit_both(&tmem_full_bar[buf]);
+      }
+    }
+  } else {
+    // ===== epilogue (both CTAs): own 128 TMEM lanes =====
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int per_img = p.th * p.tw;
+    const int nbi = row / per_img;
+    const int rem = row - nbi * per_img;
+    const int thi = rem / p.tw, twi = rem - thi * p.tw;
+    float* s_osc = reinterpret_cast<float*>(smem + S::EPI_OFFSET) + quarter * 2 * BLOCK_N;
+    float* s_bias = s_osc + BLOCK_N;
+    const bool staged = p.nb == 1;
+    uint32_t ti = 0;
+    for (int w = pair_id; w < total_work; w += num_pairs, ++ti) {
+      int b0, ay0, ax0, n0;
+      work_coords(w, b0, ay0, ax0, n0);
+      const uint32_t buf = ti & 1;
+      const int b = b0 + nbi, ay = ay0 + thi, ax = ax0 + twi;
+      const bool valid = b < p.batch && ay < p.grid_h && ax < p.grid_w;
+      const int bs = valid ? b : 0;
+      if (staged) {
+        __syncwarp();
+        const int bq = b0 < p.batch ? b0 : 0;
+        for (int c = lane; c < BLOCK_N; c += 32) {
+          const int n = n0 + c;
+          s_osc[c] = (p.out_scale && n < p.cout) ? __ldg(p.out_scale + static_cast<int64_t>(bq) * p.cout + n) : 1.f;
+          s_bias[c] = (p.bias && n < p.cout) ? __ldg(p.bias + n) : 0.f;
+        }
+        __syncwarp();
+      }
+      const float* osc = p.out_scale ? p.out_scale + static_cast<int64_t>(bs) * p.cout : nullptr;
+      const int oy = ay * p.out_stride + p.out_off_y, ox = ax * p.out_stride + p.out_off_x;
+      const int64_t pix = (static_cast<int64_t>(bs) * p.hout + oy) * p.wout + ox;
+
+      mbar_wait(&tmem_full_bar[buf], (ti >> 1) & 1);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        if (n0 + c0 >= p.cout || (p.debug & 2)) break;  // warp-uniform
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * BLOCK_N + c0, v);
+        float f[32];
+        if (staged) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 sc = *reinterpret_cast<const float4*>(s_osc + c0 + j);
+            const float4 bi = *reinterpret_cast<const float4*>(s_bias + c0 + j);
+            f[j] = __uint_as_float(v[j]) * sc.x + bi.x;
+            f[j + 1] = __uint_as_float(v[j + 1]) * sc.y + bi.y;
+            f[j + 2] = __uint_as_float(v[j + 2]) * sc.z + bi.z;
+            f[j + 3] = __uint_as_float(v[j + 3]) * sc.w + bi.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = n0 + c0 + j;
+            float a = __uint_as_float(v[j]);
+            if (n < p.cout) {
+              if (osc) a *= __ldg(osc + n);
+              if (p.bias) a += __ldg(p.bias + n);
+            }
+            f[j] = a;
+          }
+        }
+        if (p.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = (f[j] > 0.f ? f[j] : 0.2f * f[j]) * 1.4142135623730951f;
+        }
+        if (valid && !(p.debug & 1)) {
+          if (OUT_F32) {
+            float* dst = static_cast<float*>(p.y) + pix * p.cout + n0 + c0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (n0 + c0 + 4 * j < p.cout)
+                reinterpret_cast<float4*>(dst)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          } else {
+            __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.y) + pix * p.cout + n0 + c0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (n0 + c0 + 8 * j >= p.cout) continue;
+              uint4 o;
+              __nv_bfloat162 t0 = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]);
+              __nv_bfloat162 t1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
+              __nv_bfloat162 t2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
+              __nv_bfloat162 t3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+              o.x = *reinterpret_cast<uint32_t*>(&t0);
+              o.y = *reinterpret_cast<uint32_t*>(&t1);
+              o.z = *reinterpret_cast<uint32_t*>(&t2);
+              o.w = *reinterpret_cast<uint32_t*>(&t3);
+              reinterpret_cast<uint4*>(dst)[j] = o;
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[buf]);
+    }
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();   // the peer's shared memory / TMEM stay alive until the leader's last MMA has retired
+  if (warp == 1) {
+    __syncwarp();
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+template <int BLOCK_N, bool OUT_F32>
+static int launch_tc2(const CUtensorMap& mx, const CUtensorMap& mw, const TcParams& p, cudaStream_t st) {
+  using S = Tc2Smem<BLOCK_N>;
+  auto kern = conv_tc2_kernel<BLOCK_N, OUT_F32>;
+  static bool configured = false;
+  if (!configured) {
+    TE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    configured = true;
+  }
+  const int total_work = ((p.n_tiles + 1) / 2) * ((p.cout + BLOCK_N - 1) / BLOCK_N);
+  const int pairs = total_work < kNumSMs / 2 ? total_work : kNumSMs / 2;
+  kern<<<2 * pairs, TC_THREADS, S::TOTAL, st>>>(mx, mw, p);
+  TE_CHECK_LAUNCH();
+  return TE_OK;
+}
+
 // ---- host side ---------------------------------------------------------------------------------
 template <int BLOCK_N, bool OUT_F32>
 static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const TcParams& p, cudaStream_t st) {
@@ -351,6 +593,13 @@ static int conv_tc_dispatch(void* y, const void* x, const void* w, const float* 
   int block_n = (d.cout % 128 == 0) ? 128 : 64;
   if (d.cout % 256 == 0 && int64_t(p.n_tiles) * (d.cout / 256) >= 2 * kNumSMs) block_n = 256;
 
+  // 2-CTA pairs (cta_group::2) when the layer has enough tiles and, for per-sample weights, both tiles of
+  // a pair always belong to one sample.  TE_TC_2CTA=0 forces the single-CTA kernel.
+  static int use2 = -1;
+  if (use2 < 0) { const char* e = getenv("TE_TC_2CTA"); use2 = e ? atoi(e) : 1; }
+  bool two_cta = use2 != 0 && block_n >= 128 && int64_t((p.n_tiles + 1) / 2) * ((d.cout + block_n - 1) / block_n) >= kNumSMs / 2;
+  if (two_cta && p.w_slices_per_sample && ((p.tiles_w * p.tiles_h) % 2) != 0) two_cta = false;
+
   CUtensorMap mx, mw;
   {
     const uint32_t is = uint32_t(d.in_stride);
@@ -366,9 +615,14 @@ static int conv_tc_dispatch(void* y, const void* x, const void* w, const float* 
     const uint64_t nw = uint64_t(d.w_slices) * (d.w_bstride ? d.batch : 1);
     uint64_t dims[3] = {uint64_t(d.cin), uint64_t(d.cout), nw};
     uint64_t strides[2] = {uint64_t(d.cin) * 2, uint64_t(d.cout) * d.cin * 2};
-    uint32_t box[3] = {TC_BLOCK_K, uint32_t(block_n), 1};
+    uint32_t box[3] = {TC_BLOCK_K, uint32_t(two_cta ? block_n / 2 : block_n), 1};
     int rc = encode_map_bf16(&mw, w, 3, dims, strides, box, nullptr);
     if (rc) return rc;
+  }
+  if (two_cta) {
+    if (block_n == 256)
+      return d.out_f32 ? launch_tc2<256, true>(mx, mw, p, st) : launch_tc2<256, false>(mx, mw, p, st);
+    return d.out_f32 ? launch_tc2<128, true>(mx, mw, p, st) : launch_tc2<128, false>(mx, mw, p, st);
   }
   if (block_n == 256)
     return d.out_f32 ? launch_tc<256, true>(mx, mw, p, st) : launch_tc<256, false>(mx, mw, p, st);
