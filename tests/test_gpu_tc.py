@@ -176,3 +176,38 @@ def test_tc_per_sample_weights(kind, h, k):
     for a, r, nm in zip(got, ref, ("y", "gx", "gw", "h_gy", "h_x", "h_w")):
         assert a.shape == r.shape, nm
         _close(a, r, "%s per-sample %s" % (nm, kind), rel=2e-2)
+
+
+@pytest.mark.parametrize("case", [
+    # large enough (>= 74 tile pairs) to take the 2-CTA (cta_group::2) kernel
+    (16, 128, 128, 64, 64, 3, "s1"), (16, 256, 256, 64, 64, 3, "s1"), (11, 128, 128, 40, 40, 3, "s1"),
+    (16, 128, 256, 65, 65, 3, "down"), (16, 256, 128, 32, 32, 3, "up"), (16, 64, 128, 64, 64, 1, "s1"),
+])
+def test_tc_two_cta_kernel(case):
+    b, cin, cout, h, w_, k, kind = case
+    x = _bf(_rand(b, cin, h, w_, seed=31))
+    w = _rand(cout, cin, k, k, seed=32, scale=1.0 / math.sqrt(cin * k * k))
+    xr = x.clone().requires_grad_(True)
+    y = _ours(xr, w, kind)
+    ref_in = x.float().requires_grad_(True)
+    ref = _ref(ref_in, w.to(torch.bfloat16).float(), kind)
+    assert y.shape == ref.shape
+    _close(y, ref, "2cta fwd %s" % (case,))
+    gy = _bf(_rand(*y.shape, seed=33))
+    (gx,) = torch.autograd.grad(y, xr, gy)
+    (gxr,) = torch.autograd.grad(ref, ref_in, gy.float())
+    _close(gx, gxr, "2cta dgrad %s" % (case,))
+
+
+def test_tc_two_cta_per_sample_and_epilogue():
+    from transeditor_b200 import tc
+    b, c, h, k = 16, 128, 64, 3
+    x = _bf(_rand(b, c, h, h, seed=41))
+    w = _rand(b, c, c, k, k, seed=42, scale=1.0 / math.sqrt(c * k * k))
+    bias = _rand(c, seed=43)
+    osc = _rand(b, c, seed=44).abs() + 0.5
+    y = tc.conv_raw(x, tc.pack_weight(w, False), tc.Mode("s1", k), out_scale=osc, bias=bias, act=True)
+    wb = w.to(torch.bfloat16).float()
+    ref = torch.cat([F.conv2d(x[i:i + 1].float(), wb[i], padding=1) for i in range(b)])
+    ref = F.leaky_relu(ref * osc[:, :, None, None] + bias.view(1, -1, 1, 1), 0.2) * math.sqrt(2)
+    _close(y, ref, "2cta per-sample + epilogue")
