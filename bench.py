@@ -278,7 +278,9 @@ def run_ours(args, rank, local_rank, world):
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
-    torch.backends.cuda.matmul.allow_tf32 = False
+    # fp32 parity mode keeps every GEMM in full fp32; the bf16 mode lets the small f32 front-end GEMMs
+    # (mapping, attention, modulation linears: cuBLAS library calls) use TF32 tensor cores
+    torch.backends.cuda.matmul.allow_tf32 = args.precision == "bf16"
     torch.backends.cudnn.allow_tf32 = False
     from transeditor_b200 import model as te_model
     te_model.set_precision(args.precision)

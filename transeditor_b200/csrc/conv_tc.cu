@@ -130,6 +130,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int b0, ay0, ax0, n0;
         tile_coords(tile, b0, ay0, ax0, n0);
+        if (tile + int(gridDim.x) < total_tiles) {
+          // pull the NEXT tile's activation patch into L2 now: its first touch comes from HBM, and an HBM
+          // miss in the middle of the ring stalls every stage behind it (measured: feed-bound at 128 channels)
+          int pb, py, px, pn;
+          tile_coords(tile + int(gridDim.x), pb, py, px, pn);
+          for (int kc = 0; kc < k_chunks; ++kc)
+            tma_prefetch_4d(&map_x, kc * TC_BLOCK_K, px * p.in_stride, py * p.in_stride, pb);
+        }
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
@@ -359,6 +367,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       for (int w = pair_id; w < total_work; w += num_pairs) {
         int b0, ay0, ax0, n0;
         work_coords(w, b0, ay0, ax0, n0);
+        if (w + num_pairs < total_work) {  // L2 prefetch of the next work item's activation patch
+          int pb, py, px, pn;
+          work_coords(w + num_pairs, pb, py, px, pn);
+          for (int kc = 0; kc < k_chunks; ++kc)
+            tma_prefetch_4d(&map_x, kc * TC_BLOCK_K, px * p.in_stride, py * p.in_stride, pb);
+        }
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
