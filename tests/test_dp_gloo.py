@@ -41,10 +41,11 @@ def _worker(rank, world, port, out):
     opt = FlatAdam(flat, 0.01, (0.0, 0.99))
     assert flat.group_end[0] % 4 == 0 and flat.group_end[1] == flat.numel
     for step in range(3):
-        flat.grad.zero_()
+        flat.clear_grads()
         g = torch.Generator().manual_seed(100 * step + rank)
         for _, p in flat.params:
-            p.grad.add_(torch.randn(p.shape, generator=g))   # in place, like AccumulateGrad
+            p.grad = torch.randn(p.shape, generator=g)       # what AccumulateGrad leaves behind
+        flat.gather_grads()
         dist.all_reduce(flat.grad, op=dist.ReduceOp.SUM)
         opt.step(1 if step == 1 else 2, grad_scale=1.0 / world)  # step 1 skips the tail group
     out[rank] = flat.data.clone()

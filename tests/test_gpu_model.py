@@ -172,10 +172,9 @@ def test_train_step_matches_cpu_oracle_update():
     for k in ("conv1.conv.weight", "to_rgb1.bias", "adjust_style.weight", "convs.1.activate.bias",
               "interact.3.mlp.0.weight", "style_mapping_network.5.weight"):
         close(gp[k].detach().cpu(), ref.g[k].detach(), k)
-    # gradients stayed bound to the flat buffers
-    for name, p_ in tr.g_flat.params:
-        o = tr.g_flat.offsets[name]
-        assert p_.grad.data_ptr() == tr.g_flat.grad[o:o + 1].data_ptr(), name
+    # gradients were gathered into the flat buffers (and the per-parameter tensors released)
+    assert all(p_.grad is None for _, p_ in tr.g_flat.params)
+    assert tr.g_flat.grad.abs().sum().item() > 0 and tr.d_flat.grad.abs().sum().item() > 0
     tr.ema_update()
     assert torch.isfinite(tr.ema_flat.data).all()
     # lazy regularisers run

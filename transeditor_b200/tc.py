@@ -88,18 +88,18 @@ def pack_weight(w, transposed):
         if transposed:
             w = w.transpose(1, 2)
             o, i = i, o
-        return w.permute(0, 3, 4, 1, 2).reshape(b, k * k, o, i).to(torch.bfloat16).contiguous()
+        out = torch.empty((b, k * k, o, i), dtype=torch.bfloat16, device=w.device)
+        out.view(b, k, k, o, i).copy_(w.permute(0, 3, 4, 1, 2))  # permute + f32->bf16 in ONE copy kernel
+        return out
     o, i, k, _ = w.shape
     if transposed:
         w = w.transpose(0, 1)
         o, i = i, o
-    wp = w.permute(2, 3, 0, 1).reshape(k * k, o, i).to(torch.bfloat16)
     po, pi = _pad8(o), _pad8(i)
-    if po != o or pi != i:
-        full = torch.zeros((k * k, po, pi), dtype=torch.bfloat16, device=w.device)
-        full[:, :o, :i] = wp
-        return full
-    return wp.contiguous()
+    alloc = torch.empty if (po == o and pi == i) else torch.zeros
+    out = alloc((k * k, po, pi), dtype=torch.bfloat16, device=w.device)
+    out.view(k, k, po, pi)[:, :, :o, :i].copy_(w.permute(2, 3, 0, 1))
+    return out
 
 
 def _desc(x, cout, hout, wout, launch, w_slices, act=0, out_f32=0, per_sample=False):
