@@ -23,6 +23,9 @@ extern "C" {
 #endif
 
 typedef enum { TE_F32 = 0, TE_BF16 = 1, TE_F16 = 2, TE_F64 = 3 } te_dtype;
+/* OR-ed into te_fused_bias_act's dtype: x/out are bf16 or f16 while `bias` points to FLOAT32 values
+ * (the f32 master parameter is used directly, no per-call down-cast kernel). */
+#define TE_BIAS_F32 0x100
 
 typedef enum {
   TE_OK = 0,

@@ -20,9 +20,9 @@ __device__ __forceinline__ A bias_act_apply(A x, A ref, int code, A alpha, A sca
 
 // BIAS_MODE 0: none, 1: one bias per vector (step_b % VEC == 0), 2: consecutive biases
 // (step_b == 1 && size_b % VEC == 0).  IDX is uint32_t when n < 2^31 (cheap division).
-template <typename T, int VEC, int BIAS_MODE, typename IDX>
+template <typename T, int VEC, int BIAS_MODE, typename IDX, typename BT>
 __global__ void __launch_bounds__(256)
-fused_bias_act_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __restrict__ bias,
+fused_bias_act_kernel(T* __restrict__ out, const T* __restrict__ x, const BT* __restrict__ bias,
                       const T* __restrict__ ref, int code, float alpha_f, float scale_f, IDX n_vec,
                       IDX step_b, IDX size_b) {
   using A = typename Acc<T>::type;
@@ -35,13 +35,13 @@ fused_bias_act_kernel(T* __restrict__ out, const T* __restrict__ x, const T* __r
     if (code == 31 && ref != nullptr) rin = reinterpret_cast<const V*>(ref)[iv];
     A b[VEC];
     if (BIAS_MODE == 1) {
-      A bb = to_acc(bias[(iv * VEC / step_b) % size_b]);
+      A bb = A(to_acc(bias[(iv * VEC / step_b) % size_b]));
 #pragma unroll
       for (int j = 0; j < VEC; ++j) b[j] = bb;
     } else if (BIAS_MODE == 2) {
       IDX c0 = (iv * VEC) % size_b;
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) b[j] = to_acc(bias[c0 + j]);
+      for (int j = 0; j < VEC; ++j) b[j] = A(to_acc(bias[c0 + j]));
     } else {
 #pragma unroll
       for (int j = 0; j < VEC; ++j) b[j] = A(0);
@@ -172,33 +172,33 @@ fused_bias_act_bwd_cols(T* __restrict__ gin, typename Acc<T>::type* __restrict__
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-template <typename T, int VEC, typename IDX>
-static int launch_fwd_mode(T* out, const T* x, const T* bias, const T* ref, int code, float alpha,
+template <typename T, int VEC, typename IDX, typename BT>
+static int launch_fwd_mode(T* out, const T* x, const BT* bias, const T* ref, int code, float alpha,
                            float scale, int64_t n, int64_t step_b, int64_t size_b, int mode,
                            cudaStream_t st) {
   const int64_t n_vec = n / VEC;
   const int threads = 256;
   const int blocks = grid_for(n_vec, threads, 16);
   if (mode == 0)
-    fused_bias_act_kernel<T, VEC, 0, IDX><<<blocks, threads, 0, st>>>(
+    fused_bias_act_kernel<T, VEC, 0, IDX, BT><<<blocks, threads, 0, st>>>(
         out, x, bias, ref, code, alpha, scale, IDX(n_vec), IDX(1), IDX(1));
   else if (mode == 1)
-    fused_bias_act_kernel<T, VEC, 1, IDX><<<blocks, threads, 0, st>>>(
+    fused_bias_act_kernel<T, VEC, 1, IDX, BT><<<blocks, threads, 0, st>>>(
         out, x, bias, ref, code, alpha, scale, IDX(n_vec), IDX(step_b), IDX(size_b));
   else
-    fused_bias_act_kernel<T, VEC, 2, IDX><<<blocks, threads, 0, st>>>(
+    fused_bias_act_kernel<T, VEC, 2, IDX, BT><<<blocks, threads, 0, st>>>(
         out, x, bias, ref, code, alpha, scale, IDX(n_vec), IDX(step_b), IDX(size_b));
   TE_CHECK_LAUNCH();
   return TE_OK;
 }
 
-template <typename T>
+template <typename T, typename BT>
 static int fused_bias_act_typed(void* out_, const void* x_, const void* bias_, const void* ref_,
                                 int code, float alpha, float scale, int64_t n, int64_t step_b,
                                 int64_t size_b, cudaStream_t st) {
   T* out = static_cast<T*>(out_);
   const T* x = static_cast<const T*>(x_);
-  const T* bias = static_cast<const T*>(bias_);
+  const BT* bias = static_cast<const BT*>(bias_);
   const T* ref = static_cast<const T*>(ref_);
   constexpr int VEC = 16 / sizeof(T);
   const bool vec_ok = (n % VEC == 0) && aligned16(out) && aligned16(x) && (!ref || aligned16(ref));
@@ -218,15 +218,15 @@ static int fused_bias_act_typed(void* out_, const void* x_, const void* bias_, c
   }
   const bool small = n < (int64_t(1) << 31);
   if (vec == VEC) {
-    return small ? launch_fwd_mode<T, VEC, uint32_t>(out, x, bias, ref, code, alpha, scale, n,
-                                                     step_b, size_b, mode, st)
-                 : launch_fwd_mode<T, VEC, uint64_t>(out, x, bias, ref, code, alpha, scale, n,
-                                                     step_b, size_b, mode, st);
+    return small ? launch_fwd_mode<T, VEC, uint32_t, BT>(out, x, bias, ref, code, alpha, scale, n,
+                                                         step_b, size_b, mode, st)
+                 : launch_fwd_mode<T, VEC, uint64_t, BT>(out, x, bias, ref, code, alpha, scale, n,
+                                                         step_b, size_b, mode, st);
   }
-  return small ? launch_fwd_mode<T, 1, uint32_t>(out, x, bias, ref, code, alpha, scale, n, step_b,
-                                                 size_b, mode, st)
-               : launch_fwd_mode<T, 1, uint64_t>(out, x, bias, ref, code, alpha, scale, n, step_b,
-                                                 size_b, mode, st);
+  return small ? launch_fwd_mode<T, 1, uint32_t, BT>(out, x, bias, ref, code, alpha, scale, n, step_b,
+                                                     size_b, mode, st)
+               : launch_fwd_mode<T, 1, uint64_t, BT>(out, x, bias, ref, code, alpha, scale, n, step_b,
+                                                     size_b, mode, st);
 }
 
 template <typename T>
@@ -297,11 +297,17 @@ extern "C" int te_fused_bias_act(void* out, const void* x, const void* bias, con
   TE_CHECK_ARG(!bias || (step_b >= 1 && size_b >= 1), "fused_bias_act: bad bias geometry");
   const int code = act * 10 + grad;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool bias_f32 = (dtype & TE_BIAS_F32) != 0;  // 16-bit activations with an f32 bias (master parameter)
+  dtype &= 0xff;
+  if (bias_f32 && dtype == TE_BF16)
+    return fused_bias_act_typed<__nv_bfloat16, float>(out, x, bias, ref, code, alpha, scale, n, step_b, size_b, st);
+  if (bias_f32 && dtype == TE_F16)
+    return fused_bias_act_typed<__half, float>(out, x, bias, ref, code, alpha, scale, n, step_b, size_b, st);
   switch (dtype) {
-    case TE_F32: return fused_bias_act_typed<float>(out, x, bias, ref, code, alpha, scale, n, step_b, size_b, st);
-    case TE_BF16: return fused_bias_act_typed<__nv_bfloat16>(out, x, bias, ref, code, alpha, scale, n, step_b, size_b, st);
-    case TE_F16: return fused_bias_act_typed<__half>(out, x, bias, ref, code, alpha, scale, n, step_b, size_b, st);
-    case TE_F64: return fused_bias_act_typed<double>(out, x, bias, ref, code, alpha, scale, n, step_b, size_b, st);
+    case TE_F32: return fused_bias_act_typed<float, float>(out, x, bias, ref, code, alpha, scale, n, step_b, size_b, st);
+    case TE_BF16: return fused_bias_act_typed<__nv_bfloat16, __nv_bfloat16>(out, x, bias, ref, code, alpha, scale, n, step_b, size_b, st);
+    case TE_F16: return fused_bias_act_typed<__half, __half>(out, x, bias, ref, code, alpha, scale, n, step_b, size_b, st);
+    case TE_F64: return fused_bias_act_typed<double, double>(out, x, bias, ref, code, alpha, scale, n, step_b, size_b, st);
   }
   set_error("fused_bias_act: unknown dtype %d", dtype);
   return TE_ERR_INVALID;

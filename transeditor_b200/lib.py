@@ -117,9 +117,15 @@ def _count(n=1):
 
 
 # ----------------------------------------------------------------------------- thin wrappers
+TE_BIAS_F32 = 0x100
+
+
 def fused_bias_act(out, x, bias, ref, act, grad, alpha, scale, step_b, size_b):
+    code = dtype_code(x)
+    if bias is not None and bias.dtype == torch.float32 and x.dtype in (torch.bfloat16, torch.float16):
+        code |= TE_BIAS_F32
     _check(load().te_fused_bias_act(ptr(out), ptr(x), ptr(bias), ptr(ref), act, grad, alpha, scale,
-                                    x.numel(), step_b, size_b, dtype_code(x), stream()),
+                                    x.numel(), step_b, size_b, code, stream()),
            "fused_bias_act")
     _count()
 

@@ -164,10 +164,18 @@ class EqualLinear(nn.Module):
         self.lr_mul = lr_mul
 
     def forward(self, input):
-        w = self.weight * self.scale
+        # x (W*scale)^T + b*lr_mul as ONE addmm with alpha=scale: the reference's separate `weight * scale`
+        # elementwise kernel (:215,218) and its backward disappear (beta=0 ignores the placeholder input)
+        x2 = input.reshape(-1, input.shape[-1])
+        if self.activation or self.bias is None:
+            out = torch.addmm(x2.new_empty(1), x2, self.weight.t(), beta=0, alpha=self.scale)
+        else:
+            b = self.bias if self.lr_mul == 1 else self.bias * self.lr_mul
+            out = torch.addmm(b, x2, self.weight.t(), alpha=self.scale)
+        out = out.reshape(*input.shape[:-1], out.shape[-1])
         if self.activation:
-            return fused_leaky_relu(F.linear(input, w), self.bias * self.lr_mul)
-        return F.linear(input, w, bias=None if self.bias is None else self.bias * self.lr_mul)
+            return fused_leaky_relu(out, self.bias * self.lr_mul)
+        return out
 
     def __repr__(self):
         return f"{self.__class__.__name__}({self.weight.shape[1]}, {self.weight.shape[0]})"
@@ -545,10 +553,11 @@ class Generator(nn.Module):
         EqualLinear(+fused lrelu).  Returns [B,D,C]."""
         code = network[0](code)
         layers = [network[i + 1] for i in range(count)]
-        w = torch.stack([l.weight for l in layers]) * layers[0].scale          # [C, out, in]
+        w = torch.stack([l.weight for l in layers])                            # [C, out, in]
         bias = torch.stack([l.bias for l in layers]) * layers[0].lr_mul        # [C, out]
         cols = code.permute(2, 0, 1)[:count]                                   # [C, B, in]
-        y = torch.bmm(cols, w.transpose(1, 2))                                 # [C, B, out]
+        # scale folded into the batched GEMM (alpha) instead of a pass over the 4.2 M stacked weights
+        y = torch.baddbmm(cols.new_empty(1), cols, w.transpose(1, 2), beta=0, alpha=layers[0].scale)
         y = fused_leaky_relu(y.permute(1, 0, 2).reshape(code.shape[0], -1), bias.reshape(-1))
         y = y.reshape(code.shape[0], count, -1).permute(0, 2, 1)               # [B, out, C]
         if count == code.shape[2]:

@@ -52,7 +52,10 @@ def _bias_act(x, bias, ref, act, grad, alpha, scale):
     if ref is not None:
         ref = ref.contiguous(memory_format=torch.channels_last) if cl else ref.contiguous()
     if bias is not None:
-        bias = bias.to(x.dtype).contiguous()
+        # 16-bit activations take the f32 master bias directly (TE_BIAS_F32): no down-cast kernel per call
+        if not (bias.dtype == torch.float32 and x.dtype in (torch.bfloat16, torch.float16)):
+            bias = bias.to(x.dtype)
+        bias = bias.contiguous()
     out = torch.empty_like(x)
     step_b, size_b = _bias_geometry(x, cl)
     lib.fused_bias_act(out, x, bias, ref, act, grad, float(alpha), float(scale), step_b, size_b)
