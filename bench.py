@@ -190,11 +190,16 @@ def roofline_from(agg, peaks):
     total = sum(a["ms"] for a in agg.values())
     top = max(agg, key=lambda k: agg[k]["ms"])
     a = agg[top]
-    traffic = None
+    traffic, traffic_note = None, None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(top)
+            entry = json.load(f).get(top)
+        if isinstance(entry, dict):
+            traffic = entry.get("bytes_per_launch")
+            traffic_note = "%s; algorithmic %s B; %s" % (entry.get("shape"), entry.get("algorithmic_bytes"), entry.get("source"))
+        else:
+            traffic, traffic_note = entry, None
     if a["flops"] > 0:
         achieved = a["flops"] / (a["ms"] * 1e-3) / 1e12
         peak = peaks["tf_sustained"]
@@ -202,7 +207,7 @@ def roofline_from(agg, peaks):
                 "unit": "TFLOP/s", "frac": round(achieved / peak, 4), "traffic": traffic,
                 "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a step)",
                 "launches": a["launches"], "avg_launch_ms": round(a["ms"] / a["launches"], 4),
-                "share_of_kernel_time": round(a["ms"] / total, 3)}
+                "share_of_kernel_time": round(a["ms"] / total, 3), "traffic_note": traffic_note}
     else:
         achieved = a["bytes"] / (a["ms"] * 1e-3) / 1e9
         peak = peaks["hbm_gbs"]
