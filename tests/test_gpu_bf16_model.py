@@ -135,3 +135,17 @@ def test_train_step_cuda_graph_replay():
     assert torch.isfinite(tr.g_flat.data).all() and torch.isfinite(tr.d_flat.data).all()
     assert all(torch.isfinite(v).all() for v in losses.values())
     assert set(tr._graphs) == {"d", "dreg", "g", "greg"}
+
+
+def test_bf16_generator_1024_batch8_inference():
+    """BASELINE configs[3]: generator inference at 1024^2, batch 8 (editing path: z+/p+ given), bf16 mode."""
+    import model_spatial_query as M
+    torch.manual_seed(0)
+    g = M.Generator(1024, 512, 512, 18, channel_multiplier=2, n_trans=8, pixel_norm_op_dim=1).to(DEV).eval()
+    z, p = torch.randn(8, 512, 16, device=DEV), torch.randn(8, 512, 16, device=DEV)
+    with torch.no_grad():
+        zp, pp = g(z, p, return_mapped_codes=True)
+        img, _, _ = g(zp, pp, use_spatial_mapping=False, use_style_mapping=False)
+        full, _, _ = g(z, p)
+    assert img.shape == (8, 3, 1024, 1024) and torch.isfinite(img).all()
+    assert (img - full).abs().max().item() < 1e-3 * max(1.0, full.abs().max().item())

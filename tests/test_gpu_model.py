@@ -184,3 +184,22 @@ def test_train_step_matches_cpu_oracle_update():
     assert torch.isfinite(tr.g_flat.data).all() and torch.isfinite(tr.d_flat.data).all()
     out = tr.step_from_host((torch.rand(4, 3, 32, 32) * 2 - 1).pin_memory())
     assert all(np.isfinite(v) for v in out.values())
+
+
+def test_generator_1024_matches_oracle_fp32():
+    """BASELINE configs[3] shape (1024^2 generator, 32/64-channel tail layers) in fp32 parity mode against
+    the CPU oracle with the same deterministic weights (batch 1 keeps the CPU side to a few seconds)."""
+    import model_spatial_query as M
+    size, cm = 1024, 2
+    sdg = O.synthetic_state(O.generator_shapes(size, cm))
+    g = M.Generator(size, 512, 512, 18, channel_multiplier=cm, n_trans=8, pixel_norm_op_dim=1)
+    g.load_state_dict(sdg, strict=True)
+    g = g.to(DEV)
+    gen = torch.Generator().manual_seed(5)
+    z, p = torch.randn(1, 512, 16, generator=gen), torch.randn(1, 512, 16, generator=gen)
+    with torch.no_grad():
+        img, lat, _ = g(z.to(DEV), p.to(DEV), return_latents=True)
+        ref, lat_ref = O.generator_forward(sdg, z, p, size)
+    assert img.shape == (1, 3, 1024, 1024) and lat.shape == (1, 18, 512)
+    assert (lat.cpu() - lat_ref).abs().max().item() < 1e-3
+    assert (img.cpu() - ref).abs().max().item() < 1e-3
