@@ -251,8 +251,9 @@ static int fused_bias_act_bwd_typed(void* gin_, void* gbias_, const void* g_, co
     while (ctpb < 256 && ctpb < col_threads) ctpb <<= 1;  // power of two <= 256 covering the columns
     const unsigned gx = unsigned((col_threads + ctpb - 1) / ctpb);
     const int tys = threads / ctpb;
-    // enough row chunks to fill the chip (~8 CTAs per SM), at least 8 rows per thread row
-    int64_t want = (int64_t(kNumSMs) * 8 + gx - 1) / gx;
+    // one full wave: 4 CTAs per SM (5 fit by registers; 1184 CTAs used to leave a 0.6-wave tail)
+    int64_t want = (int64_t(kNumSMs) * 4) / gx;
+    if (want < 1) want = 1;
     int64_t rpb = (rows + want - 1) / want;
     if (rpb < 16 * tys) rpb = 16 * tys;
     const unsigned gy = unsigned((rows + rpb - 1) / rpb);

@@ -229,7 +229,9 @@ extern "C" int te_conv_wgrad_tc(float* gw, const void* g, const void* x, const t
     TE_CHECK_ARG(p.nb == 1, "conv_wgrad_tc: per-sample gradients need >= 64 anchors per sample");
     TE_CHECK_ARG(d.w_bstride == int64_t(d.w_slices) * d.cout * d.cin, "conv_wgrad_tc: per-sample gradients must be densely packed");
     p.tiles_per_sample = p.tiles_w * p.tiles_h;
-    int sps = (kNumSMs + out_tiles * tap_groups * d.batch - 1) / (out_tiles * tap_groups * d.batch);
+    // one CTA per SM (196 KB of shared memory): keep the grid within ONE wave — 150 CTAs on 148 SMs would
+    // run two waves and double the kernel time — so round the split count DOWN
+    int sps = kNumSMs / (out_tiles * tap_groups * d.batch);
     int max_sps = (p.tiles_per_sample + 7) / 8;
     if (sps > max_sps) sps = max_sps;
     if (sps < 1) sps = 1;
@@ -241,7 +243,7 @@ extern "C" int te_conv_wgrad_tc(float* gw, const void* g, const void* x, const t
     p.use_atomics = sps > 1 ? 1 : 0;
     TE_CHECK_ARG(splits <= 65535, "conv_wgrad_tc: grid.z too large");
   } else {
-    splits = (kNumSMs + out_tiles * tap_groups - 1) / (out_tiles * tap_groups);
+    splits = kNumSMs / (out_tiles * tap_groups);  // rounded down: a single wave of CTAs
     int max_splits = (p.n_tiles + 7) / 8;
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
