@@ -603,9 +603,9 @@ static int conv_tc_dispatch(void* y, const void* x, const void* w, const float* 
   }
   // N tile: 256 halves the A-operand shared-memory reads per FLOP (one-CTA UMMA at M128 x N128 is bound by
   // the 128 B/cycle shared-memory port: every K16 step reads 4 KB of A + 4 KB of B in 64 cycles); used when
-  // the layer still yields >= 2 tiles per SM.
+  // the layer still yields >= 1 tile per SM.
   int block_n = (d.cout % 128 == 0) ? 128 : 64;
-  if (d.cout % 256 == 0 && int64_t(p.n_tiles) * (d.cout / 256) >= 2 * kNumSMs) block_n = 256;
+  if (d.cout % 256 == 0 && int64_t(p.n_tiles) * (d.cout / 256) >= kNumSMs) block_n = 256;
 
   // 2-CTA pairs (cta_group::2) when the layer has enough tiles and, for per-sample weights, both tiles of
   // a pair always belong to one sample.  TE_TC_2CTA=0 forces the single-CTA kernel.
