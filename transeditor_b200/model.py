@@ -297,6 +297,8 @@ def _modconv_forward_tc(self, x, s, d, wn, bias, noise, noise_weight, activate, 
             pb = None if bias is None else F.pad(bias.reshape(-1), (0, wn.shape[0] - cout))
             v = tc.conv_raw(x, tc.pack_weight(wb, False), tc.Mode("s1", k), bias=pb, act=activate)
             return v if wn.shape[0] == cout else v[:, :cout]
+        elif activate and noise is None and bias is not None and wn.shape[0] == cout:
+            return tc.conv2d_bias_act(x, wb, bias.reshape(-1))  # bias + lrelu in the conv epilogue
         else:
             v = tc.conv2d(x, wb)
         if wn.shape[0] != cout:
@@ -663,6 +665,30 @@ class ConvLayer(nn.Sequential):
         if activate:
             layers.append(FusedLeakyReLU(out_channel) if bias else ScaledLeakyReLU(0.2))
         super().__init__(*layers)
+
+    def forward(self, input):
+        if input.dtype != torch.bfloat16:
+            return super().forward(input)
+        # bf16 tensor-core route: [Blur] -> EqualConv2d + FusedLeakyReLU as ONE kernel (bias and activation
+        # in the convolution epilogue) when the pair is present; anything else runs module by module
+        mods = list(self)
+        x = input
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            nxt = mods[i + 1] if i + 1 < len(mods) else None
+            if (isinstance(m, EqualConv2d) and isinstance(nxt, FusedLeakyReLU) and nxt.bias is not None
+                    and m.bias is None and m.weight.shape[0] % 8 == 0 and nxt.negative_slope == 0.2
+                    and abs(nxt.scale - _SQRT2) < 1e-12):
+                w = m.weight * m.scale
+                if x.shape[1] != w.shape[1]:
+                    w = F.pad(w, (0, 0, 0, 0, 0, x.shape[1] - w.shape[1]))
+                x = tc.conv2d_bias_act(x, w, nxt.bias, stride=m.stride)
+                i += 2
+            else:
+                x = m(x)
+                i += 1
+        return x
 
 
 class ResBlock(nn.Module):

@@ -215,6 +215,45 @@ class TcWeightGrad(Function):
         return g_x, g_gy, None, None
 
 
+class TcConvBiasAct(Function):
+    """out = leaky_relu(conv(x, W; mode) + bias, 0.2) * sqrt(2) with bias and activation applied in the
+    convolution kernel's epilogue (no separate bias-act pass over the activation).  Backward is the
+    composition of the differentiable pieces: the masked gradient comes from FusedLeakyReLUFunctionBackward
+    (sign taken from the saved OUTPUT, like the reference op, utils/op/fused_act.py:27-29), then the usual
+    data / weight gradient kernels — so second order works exactly as for the unfused ops."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, mode):
+        out = conv_raw(x, pack_weight(w, mode.transposed), mode, bias=bias, act=True)
+        ctx.save_for_backward(x, w, out)
+        ctx.mode = mode
+        ctx.bias_dtype = bias.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        from .op import FusedLeakyReLUFunctionBackward
+        x, w, out = ctx.saved_tensors
+        mode = ctx.mode
+        g_y, g_b = FusedLeakyReLUFunctionBackward.apply(g_out, out, True, 0.2, 2 ** 0.5, ctx.bias_dtype)
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            gx = TcConv.apply(g_y, w, mode.adjoint((x.shape[2], x.shape[3])))
+            if gx.shape[1] != x.shape[1]:
+                gx = gx[:, :x.shape[1]]
+        if ctx.needs_input_grad[1]:
+            gw = TcWeightGrad.apply(x, g_y, mode, tuple(w.shape))
+        return gx, gw, (g_b if ctx.needs_input_grad[2] else None), None
+
+
+def conv2d_bias_act(x, w, bias, stride=1):
+    """conv2d + bias + leaky_relu(0.2)*sqrt(2) in one kernel (EqualConv2d + FusedLeakyReLU, StyledConv tail)."""
+    k = w.shape[-1]
+    if w.shape[-4] % 8:
+        raise RuntimeError("conv2d_bias_act needs an output channel count that is a multiple of 8")
+    return TcConvBiasAct.apply(x, w, bias, Mode("s1" if stride == 1 else "down", k))
+
+
 def conv2d(x, w, stride=1):
     """F.conv2d(x, w, stride, padding = k//2 if stride == 1 else 0) in bf16 on tensor cores.
     w [O, I, K, K], or [B, O, I, K, K] for per-sample weights (the reference's groups=batch form)."""
