@@ -156,6 +156,31 @@ def test_upfirdn2d_matches_oracle(dtype, case, cl):
     assert (y.double().cpu() - ref).abs().max().item() <= tol * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("case", [
+    # (n, c, h, w, pad, fir) — large 16-bit channels-last inputs take the TMA-staged kernel (>= 2^20 outputs, c % 64 == 0)
+    (2, 128, 65, 67, (1, 1), "sep"), (1, 64, 129, 129, (2, 2), "sep"), (1, 192, 80, 96, (2, 1), "sep"),
+    (2, 64, 97, 100, (-1, 2), "sep"), (1, 128, 257, 36, (1, 1), "sep"), (3, 64, 90, 70, (2, 2), "full"),
+    (1, 128, 100, 90, (1, 1), "k3"), (1, 64, 300, 60, (0, 0), "sep"), (1, 64, 20, 900, (2, 2), "sep"),
+])
+def test_upfirdn2d_tma_staged_channels_last(dtype, case):
+    from utils.op import upfirdn2d
+    n, c, h, w, pad, kind = case
+    x = _rand(n, c, h, w, dtype=dtype, seed=31)
+    if kind == "sep":
+        fir = torch.outer(torch.tensor([1., 3., 3., 1.]), torch.tensor([1., 3., 3., 1.])) / 64
+    elif kind == "full":
+        fir = _rand(4, 4, seed=32).abs() / 8
+    else:
+        fir = _rand(3, 3, seed=33).abs() / 4
+    y = upfirdn2d(x.to(DEV).contiguous(memory_format=torch.channels_last), fir.to(DEV), pad=pad)
+    assert y.is_contiguous(memory_format=torch.channels_last)
+    ref = ops_cpu.upfirdn2d(x.double(), fir.double(), 1, 1, pad)
+    assert y.shape == ref.shape and y.numel() >= 1 << 20
+    tol = {torch.float16: 2e-3, torch.bfloat16: 1.6e-2}[dtype]
+    assert (y.double().cpu() - ref).abs().max().item() <= tol * max(1.0, ref.abs().max().item())
+
+
 def test_upfirdn2d_channels_last_nonseparable_fir():
     """The vectorised channels-last kernel takes a separable fast path; a random (rank-4) FIR must go
     through its general path and still match."""

@@ -75,6 +75,18 @@ def main():
             res["upfirdn2d_blur_bf16_nhwc [16,257,257,128]->256^2"] = {"ms": ms, "GB/s": byts / ms / 1e6,
                                                                        "frac_hbm": byts / ms / 1e6 / PEAKS["hbm_gbs"]}
             del x
+        if want("upfirdn2d_blur_bf16_nhwc"):
+            x = torch.randn(16, 128, 256, 256, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            ms = timeit(lambda: upfirdn2d(x, fir, pad=(2, 2)), a.iters)
+            byts = 2 * 16 * 128 * (257 * 257 + 256 * 256)
+            res["upfirdn2d_blur_bf16_nhwc [16,256,256,128]->257^2 (D)"] = {"ms": ms, "GB/s": byts / ms / 1e6,
+                                                                           "frac_hbm": byts / ms / 1e6 / PEAKS["hbm_gbs"]}
+            x = torch.randn(16, 512, 65, 65, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            ms = timeit(lambda: upfirdn2d(x, fir, pad=(1, 1)), a.iters)
+            byts = 2 * 16 * 512 * (65 * 65 + 64 * 64)
+            res["upfirdn2d_blur_bf16_nhwc [16,65,65,512]->64^2"] = {"ms": ms, "GB/s": byts / ms / 1e6,
+                                                                    "frac_hbm": byts / ms / 1e6 / PEAKS["hbm_gbs"]}
+            del x
         if want("scale_bc"):
             x = torch.randn(16, 128, 256, 256, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
             sc = torch.rand(16, 128, device=dev) + 0.5

@@ -154,6 +154,25 @@ inline int encode_map_bf16(CUtensorMap* map, const void* base, int rank, const u
   return TE_OK;
 }
 
+// 16-bit elements moved as raw words, NO swizzle (rows of the box land back to back in shared memory), zero fill
+inline int encode_map_u16_linear(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                                 const uint64_t* strides_bytes, const uint32_t* box) {
+  auto fn = get_encode_fn();
+  if (!fn) {
+    set_error("TMA path: cuTensorMapEncodeTiled entry point unavailable");
+    return TE_ERR_CUDA;
+  }
+  uint32_t ones[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, rank, const_cast<void*>(base), dims, strides_bytes, box, ones,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("TMA path: cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+    return TE_ERR_CUDA;
+  }
+  return TE_OK;
+}
+
 inline int next_pow2(int v) {
   int p = 1;
   while (p < v) p <<= 1;

@@ -11,7 +11,10 @@
 //     produces a 4x4 register block from a 7x7 patch (3 shared-memory words per output),
 //     16-byte stores.  TMA tiled loads are not usable here: row pitches such as 257*4 B are not
 //     16-byte multiples (cuTensorMapEncodeTiled requirement), so staging uses coalesced LDG.
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace te {
 
@@ -714,6 +717,224 @@ static int launch_fir_nhwc16(T* out, const T* in, const float* fir, const Upfird
   }
 }
 
+
+// ---- channels-last, 16-bit, TMA-staged ---------------------------------------------------------------------
+// The register kernel above tops out near half of HBM bandwidth: 128 registers per thread leave 16 warps per SM and
+// every warp alternates between its loads and ~700 instructions of FIR arithmetic, so too few bytes are in flight.
+// Here one elected thread streams haloed [rows+3][cols+3][64 channels] boxes into a two-stage shared-memory ring
+// with cp.async.bulk.tensor (out-of-bounds = the operator's zero padding, negative start coordinates included) while
+// all threads filter the previous box out of shared memory; two such CTAs per SM keep ~200 KB of loads in flight.
+struct FirTmaTiling {
+  int tw, th;          // output tile (columns even, rows multiple of F2_TY)
+  int xpairs, strips;  // per tile: tw / 2, th / F2_TY
+  int box_w, box_h;    // tw + 3, th + 3
+  int tiles_x, tiles_y, chunks;
+  int64_t jobs;
+};
+constexpr int FIR_TMA_STAGES = 2;
+constexpr int FIR_TMA_MAX_THREADS = 256;  // x 2 CTAs per SM -> 128 registers per thread, no spills
+
+template <typename T>
+__global__ void __launch_bounds__(FIR_TMA_MAX_THREADS, 2)
+fir_nhwc_tma_kernel(T* __restrict__ out, const __grid_constant__ CUtensorMap in_map, const float* __restrict__ fir,
+                    UpfirdnParams p, FirTmaTiling t) {
+  extern __shared__ __align__(128) uint8_t fir_smem_raw[];
+  __shared__ __align__(8) uint64_t full[FIR_TMA_STAGES];
+  __shared__ float sk[4][4];
+  __shared__ float s_row[4], s_col[4];
+  __shared__ int s_sep;
+  uint8_t* stage0 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fir_smem_raw) + 127) & ~uintptr_t(127));
+  const uint32_t stage_bytes = uint32_t(t.box_h) * t.box_w * 128u;
+  const int tid = threadIdx.x;
+  if (tid < 16) {
+    int ky = tid >> 2, kx = tid & 3;
+    sk[ky][kx] = (ky < p.kh && kx < p.kw) ? fir[(p.kh - 1 - ky) * p.kw + (p.kw - 1 - kx)] : 0.f;
+  }
+  if (tid == 32) {
+    for (int s = 0; s < FIR_TMA_STAGES; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int64_t job, int s) {
+    const int chunk = int(job % t.chunks);
+    int64_t r = job / t.chunks;
+    const int tx = int(r % t.tiles_x); r /= t.tiles_x;
+    const int ty = int(r % t.tiles_y); r /= t.tiles_y;
+    mbar_expect_tx(&full[s], stage_bytes);
+    tma_load_4d(stage0 + size_t(s) * stage_bytes, &in_map, &full[s], chunk * 64, tx * t.tw - p.pad_x0,
+                ty * t.th - p.pad_y0, int(r));
+  };
+  if (tid == 32) {
+    int64_t job = blockIdx.x;
+    for (int s = 0; s < FIR_TMA_STAGES && job < t.jobs; ++s, job += gridDim.x) issue(job, s);
+  }
+  if (tid == 0) {
+    int py = 0, px = 0;
+    float best = 0.f;
+    for (int y = 0; y < 4; ++y)
+      for (int x = 0; x < 4; ++x)
+        if (fabsf(sk[y][x]) > best) { best = fabsf(sk[y][x]); py = y; px = x; }
+    int sep = best > 0.f;
+    for (int y = 0; y < 4 && sep; ++y)
+      for (int x = 0; x < 4; ++x)
+        if (fabsf(sk[y][x] - sk[y][px] * (sk[py][x] / sk[py][px])) > 1e-6f * best) { sep = 0; break; }
+    for (int i = 0; i < 4; ++i) {
+      s_col[i] = sk[i][px];
+      s_row[i] = best > 0.f ? sk[py][i] / sk[py][px] : 0.f;
+    }
+    s_sep = sep;
+  }
+  __syncthreads();
+  const bool sep = s_sep != 0;
+  const int q8 = tid & 7;                 // 8-channel group inside the 64-channel chunk
+  const int xp = (tid >> 3) % t.xpairs;
+  const int strip = (tid >> 3) / t.xpairs;
+  const bool active = strip < t.strips;
+  const float2 r0 = make_float2(s_row[0], s_row[0]), r1 = make_float2(s_row[1], s_row[1]);
+  const float2 r2 = make_float2(s_row[2], s_row[2]), r3 = make_float2(s_row[3], s_row[3]);
+  const float c0 = s_col[0], c1 = s_col[1], c2 = s_col[2], c3 = s_col[3];
+
+  int it = 0;
+  for (int64_t job = blockIdx.x; job < t.jobs; job += gridDim.x, ++it) {
+    const int s = it % FIR_TMA_STAGES;
+    mbar_wait(&full[s], (it / FIR_TMA_STAGES) & 1);
+    if (active) {
+      const int chunk = int(job % t.chunks);
+      int64_t r = job / t.chunks;
+      const int tx = int(r % t.tiles_x); r /= t.tiles_x;
+      const int ty = int(r % t.tiles_y); r /= t.tiles_y;
+      const int ox0 = tx * t.tw + xp * F2_XW, oy0 = ty * t.th + strip * F2_TY;
+      const uint8_t* src = stage0 + size_t(s) * stage_bytes +
+                           (size_t(strip * F2_TY) * t.box_w + xp * F2_XW) * 128 + q8 * 16;
+      T* dst = out + ((r * p.out_h + oy0) * int64_t(p.out_w) + ox0) * p.minor + chunk * 64 + q8 * 8;
+      if (ox0 < p.out_w && oy0 < p.out_h) {
+        float2 acc[F2_TY][F2_XW][4];
+#pragma unroll
+        for (int a = 0; a < F2_TY; ++a)
+#pragma unroll
+          for (int w = 0; w < F2_XW; ++w)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[a][w][q] = make_float2(0.f, 0.f);
+        if (sep) {
+#pragma unroll
+          for (int ry = 0; ry < F2_TY + 3; ++ry) {
+            uint4 raw[5];
+#pragma unroll
+            for (int kx = 0; kx < 5; ++kx)
+              raw[kx] = *reinterpret_cast<const uint4*>(src + (size_t(ry) * t.box_w + kx) * 128);
+            float2 h[F2_XW][4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float2 v[5];
+#pragma unroll
+              for (int kx = 0; kx < 5; ++kx) v[kx] = Unpack2<T>::get((&raw[kx].x)[q]);
+#pragma unroll
+              for (int w = 0; w < F2_XW; ++w) {
+                float2 u = __fmul2_rn(v[w], r0);
+                u = __ffma2_rn(v[w + 1], r1, u);
+                u = __ffma2_rn(v[w + 2], r2, u);
+                h[w][q] = __ffma2_rn(v[w + 3], r3, u);
+              }
+            }
+#pragma unroll
+            for (int ky = 0; ky < 4; ++ky) {
+              const int a = ry - ky;
+              if (a >= 0 && a < F2_TY) {
+                const float cs = ky == 0 ? c0 : ky == 1 ? c1 : ky == 2 ? c2 : c3;
+                const float2 ck = make_float2(cs, cs);
+#pragma unroll
+                for (int w = 0; w < F2_XW; ++w)
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) acc[a][w][q] = __ffma2_rn(h[w][q], ck, acc[a][w][q]);
+              }
+            }
+          }
+        } else {
+          // general (non rank-1) FIR: rare, every FIR on the path is separable
+          for (int ry = 0; ry < F2_TY + 3; ++ry)
+            for (int kx = 0; kx < 5; ++kx) {
+              const uint4 raw = *reinterpret_cast<const uint4*>(src + (size_t(ry) * t.box_w + kx) * 128);
+#pragma unroll
+              for (int a = 0; a < F2_TY; ++a)
+#pragma unroll
+                for (int w = 0; w < F2_XW; ++w) {
+                  const int ky = ry - a, kk = kx - w;
+                  if (ky >= 0 && ky < 4 && kk >= 0 && kk < 4) {
+                    const float2 tp = make_float2(sk[ky][kk], sk[ky][kk]);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                      acc[a][w][q] = __ffma2_rn(Unpack2<T>::get((&raw.x)[q]), tp, acc[a][w][q]);
+                  }
+                }
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < F2_TY; ++a) {
+          if (oy0 + a >= p.out_h) break;
+#pragma unroll
+          for (int w = 0; w < F2_XW; ++w) {
+            if (ox0 + w >= p.out_w) continue;
+            uint4 o;
+            o.x = Unpack2<T>::put(acc[a][w][0]);
+            o.y = Unpack2<T>::put(acc[a][w][1]);
+            o.z = Unpack2<T>::put(acc[a][w][2]);
+            o.w = Unpack2<T>::put(acc[a][w][3]);
+            *reinterpret_cast<uint4*>(dst + (int64_t(a) * p.out_w + w) * p.minor) = o;
+          }
+        }
+      }
+    }
+    __syncthreads();  // every thread is done reading stage s
+    const int64_t next = job + int64_t(FIR_TMA_STAGES) * gridDim.x;
+    if (tid == 32 && next < t.jobs) issue(next, s);
+  }
+}
+
+template <typename T>
+static int launch_fir_nhwc_tma(T* out, const T* in, const float* fir, const UpfirdnParams& p, cudaStream_t st,
+                               int* status) {
+  *status = TE_OK;
+  if constexpr (Is16<T>::value) {
+    FirTmaTiling t;
+    const int nx = (p.out_w + 31) / 32;
+    t.tw = (((p.out_w + nx - 1) / nx) + 1) & ~1;
+    t.xpairs = t.tw / 2;
+    int strips = FIR_TMA_MAX_THREADS / (t.xpairs * 8);
+    const int need = (p.out_h + F2_TY - 1) / F2_TY;
+    strips = strips < 1 ? 1 : strips > 4 ? 4 : strips;
+    if (strips > need) strips = need;
+    t.strips = strips;
+    t.th = strips * F2_TY;
+    t.box_w = t.tw + 3;
+    t.box_h = t.th + 3;
+    t.tiles_x = (p.out_w + t.tw - 1) / t.tw;
+    t.tiles_y = (p.out_h + t.th - 1) / t.th;
+    t.chunks = p.minor / 64;
+    t.jobs = int64_t(p.major) * t.tiles_y * t.tiles_x * t.chunks;
+    const int threads = ((t.strips * t.xpairs * 8) + 31) / 32 * 32;
+    const size_t smem = size_t(FIR_TMA_STAGES) * t.box_h * t.box_w * 128 + 128;
+    if (threads < 64 || threads > FIR_TMA_MAX_THREADS || smem > 110 * 1024) return 0;
+    CUtensorMap map;
+    const uint64_t dims[4] = {uint64_t(p.minor), uint64_t(p.in_w), uint64_t(p.in_h), uint64_t(p.major)};
+    const uint64_t strides[3] = {uint64_t(p.minor) * 2, uint64_t(p.in_w) * p.minor * 2,
+                                 uint64_t(p.in_h) * p.in_w * p.minor * 2};
+    const uint32_t box[4] = {64, uint32_t(t.box_w), uint32_t(t.box_h), 1};
+    *status = encode_map_u16_linear(&map, in, 4, dims, strides, box);
+    if (*status != TE_OK) return 1;
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(fir_nhwc_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+      attr_done = true;
+    }
+    const int64_t cap = int64_t(kNumSMs) * 2;
+    const int grid = int(t.jobs < cap ? t.jobs : cap);
+    fir_nhwc_tma_kernel<T><<<grid, threads, smem, st>>>(out, map, fir, p, t);
+    return 1;
+  } else {
+    return 0;
+  }
+}
+
 template <typename T>
 static int upfirdn2d_typed(void* out_, const void* in_, const float* fir, const UpfirdnParams& p,
                            cudaStream_t st) {
@@ -727,8 +948,14 @@ static int upfirdn2d_typed(void* out_, const void* in_, const float* fir, const 
   const bool hot_cl = p.up_x == 1 && p.up_y == 1 && p.down_x == 1 && p.down_y == 1 && p.minor > 1 &&
                       p.minor % NVEC == 0 && p.kh <= 4 && p.kw <= 4 && sizeof(T) <= 4 &&
                       (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
-  if (hot_cl && launch_fir_nhwc16<T>(out, in, fir, p, st)) {
-    // 16-bit channels-last: packed-f32 kernel launched
+  static const bool use_tma = getenv("TE_FIR_TMA") == nullptr || atoi(getenv("TE_FIR_TMA")) != 0;
+  int tma_status = TE_OK;
+  if (hot_cl && use_tma && p.minor % 64 == 0 && total >= (int64_t(1) << 20) &&
+      launch_fir_nhwc_tma<T>(out, in, fir, p, st, &tma_status)) {
+    // 16-bit channels-last, large: TMA-staged kernel launched (or the tensor map could not be encoded)
+    if (tma_status != TE_OK) return tma_status;
+  } else if (hot_cl && launch_fir_nhwc16<T>(out, in, fir, p, st)) {
+    // 16-bit channels-last: packed-f32 register kernel launched
   } else if (hot_cl) {
     const int strips = (p.out_h + FN_TY - 1) / FN_TY;
     const int64_t work = p.major * strips * int64_t(p.out_w) * (p.minor / NVEC);
