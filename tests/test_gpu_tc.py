@@ -211,3 +211,78 @@ def test_tc_two_cta_per_sample_and_epilogue():
     ref = torch.cat([F.conv2d(x[i:i + 1].float(), wb[i], padding=1) for i in range(b)])
     ref = F.leaky_relu(ref * osc[:, :, None, None] + bias.view(1, -1, 1, 1), 0.2) * math.sqrt(2)
     _close(y, ref, "2cta per-sample + epilogue")
+
+
+@pytest.mark.parametrize("case", [(2, 64, 64, 16, 16, 3, "s1"), (16, 128, 256, 64, 64, 3, "s1"),
+                                  (2, 64, 128, 33, 33, 3, "down"), (16, 256, 256, 63, 63, 1, "down"),
+                                  (2, 64, 64, 8, 8, 3, "up")])
+def test_tc_weight_scale_folded_into_repack(case):
+    """conv(x, W * wscale) with the scale applied while the weight is repacked, and wscale * wgrad from the
+    weight-gradient kernel (alpha): values and both gradients against torch."""
+    from transeditor_b200 import tc
+    b, cin, cout, h, w_, k, kind = case
+    wscale = 1.0 / math.sqrt(cin * k * k)
+    x = _bf(_rand(b, cin, h, w_, seed=51)).requires_grad_(True)
+    w = _rand(cout, cin, k, k, seed=52).requires_grad_(True)
+    if kind == "up":
+        y = tc.conv_transpose2d(x, w, wscale=wscale)
+    else:
+        y = tc.conv2d(x, w, stride=1 if kind == "s1" else 2, wscale=wscale)
+    xr = x.detach().float().requires_grad_(True)
+    wr = w.detach().clone().requires_grad_(True)
+    ref = _ref(xr, (wr * wscale).to(torch.bfloat16).float(), kind)
+    _close(y, ref, "wscale fwd %s" % (case,))
+    gy = _bf(_rand(*y.shape, seed=53))
+    gx, gw = torch.autograd.grad(y, (x, w), gy)
+    gxr, gwr = torch.autograd.grad(ref, (xr, wr), gy.float())
+    _close(gx, gxr, "wscale dgrad %s" % (case,))
+    _close(gw, gwr, "wscale wgrad %s" % (case,), rel=2e-2)
+
+
+@pytest.mark.parametrize("case", [(2, 64, 64, 16, 16, 3, 1), (16, 128, 256, 64, 64, 1, 1), (4, 64, 128, 33, 33, 3, 2),
+                                  (16, 256, 512, 63, 63, 1, 2), (3, 64, 72, 9, 9, 3, 1)])
+def test_tc_conv_residual_epilogue(case):
+    """y = conv(x, W * wscale) + residual with the sum in the epilogue (1-CTA and 2-CTA kernels); the residual's
+    gradient is the incoming gradient itself."""
+    from transeditor_b200 import tc
+    b, cin, cout, h, w_, k, stride = case
+    wscale = 0.7 / math.sqrt(cin * k * k)
+    x = _bf(_rand(b, cin, h, w_, seed=61)).requires_grad_(True)
+    w = _rand(cout, cin, k, k, seed=62).requires_grad_(True)
+    ho = h if stride == 1 else (h - k) // 2 + 1
+    wo = w_ if stride == 1 else (w_ - k) // 2 + 1
+    res = _bf(_rand(b, cout, ho, wo, seed=63)).requires_grad_(True)
+    y = tc.conv2d_residual(x, w, res, stride=stride, wscale=wscale)
+    xr = x.detach().float().requires_grad_(True)
+    wr = w.detach().clone().requires_grad_(True)
+    wq = (wr * wscale).to(torch.bfloat16).float()
+    ref = (F.conv2d(xr, wq, padding=k // 2) if stride == 1 else F.conv2d(xr, wq, stride=2)) + res.detach().float()
+    _close(y, ref, "residual fwd %s" % (case,))
+    gy = _bf(_rand(*y.shape, seed=64))
+    gx, gw, gr = torch.autograd.grad(y, (x, w, res), gy)
+    gxr, gwr = torch.autograd.grad(ref, (xr, wr), gy.float())
+    _close(gx, gxr, "residual dgrad %s" % (case,))
+    _close(gw, gwr, "residual wgrad %s" % (case,), rel=2e-2)
+    assert torch.equal(gr, gy)
+
+
+@pytest.mark.parametrize("gain", [1.0, 2 ** -0.5 * 2 ** 0.5, 0.5])
+def test_tc_bias_act_gain(gain):
+    from transeditor_b200 import tc
+    b, cin, cout, h, k = 4, 64, 128, 32, 3
+    wscale = 1.0 / math.sqrt(cin * k * k)
+    x = _bf(_rand(b, cin, h, h, seed=71)).requires_grad_(True)
+    w = _rand(cout, cin, k, k, seed=72).requires_grad_(True)
+    bias = _rand(cout, seed=73).requires_grad_(True)
+    y = tc.conv2d_bias_act(x, w, bias, wscale=wscale, gain=gain)
+    xr = x.detach().float().requires_grad_(True)
+    wr = w.detach().clone().requires_grad_(True)
+    br = bias.detach().clone().requires_grad_(True)
+    ref = F.leaky_relu(F.conv2d(xr, (wr * wscale).to(torch.bfloat16).float(), padding=1) + br.view(1, -1, 1, 1), 0.2) * gain
+    _close(y, ref, "gain fwd")
+    gy = _bf(_rand(*y.shape, seed=74))
+    gx, gw, gb = torch.autograd.grad(y, (x, w, bias), gy)
+    gxr, gwr, gbr = torch.autograd.grad(ref, (xr, wr, br), gy.float())
+    _close(gx, gxr, "gain dgrad")
+    _close(gw, gwr, "gain wgrad", rel=2e-2)
+    _close(gb, gbr, "gain bias grad", rel=2e-2)

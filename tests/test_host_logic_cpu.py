@@ -41,6 +41,10 @@ def test_forward_and_routes_match_reference_golden():
         assert np.abs(img2.numpy() - gold["img_from_plus"]).max() < 1e-3
         assert np.abs(d(img).numpy() - gold["d_fake"]).max() < 1e-3
         assert np.abs(d(torch.from_numpy(gold["real"])).numpy() - gold["d_real"]).max() < 1e-3
+        # one stacked pass over [fake; real] = the two separate calls (per-sub-batch minibatch stddev)
+        both = d.forward_stacked(torch.cat([img, torch.from_numpy(gold["real"])]), 2)
+        assert np.abs(both[:4].numpy() - gold["d_fake"]).max() < 1e-3
+        assert np.abs(both[4:].numpy() - gold["d_real"]).max() < 1e-3
         only_lat = g(z, p, return_only_style_latent=True)
         assert torch.allclose(only_lat, lat)
         im3, l3 = g(z, p, return_style=True)

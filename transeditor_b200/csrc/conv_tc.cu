@@ -46,6 +46,8 @@ struct TcParams {
   int tiles_w, tiles_h, tiles_b, n_tiles;
   int w_slices_per_sample; // 0: shared weights; else slices per sample (weights indexed b*slices + w_t)
   int act;
+  float act_gain;
+  const __nv_bfloat16* residual;  // [B, hout, wout, cout] added after the activation, or null
   int debug;               // TE_TC_DEBUG bits (profiling aid): 1 no stores, 2 no epilogue work, 4 no MMAs
   const float* out_scale;  // [B, cout] or null
   const float* bias;       // [cout] or null
@@ -247,8 +249,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
           }
         }
         if (p.act == 1) {
+          const float gain = p.act_gain;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = (f[j] > 0.f ? f[j] : 0.2f * f[j]) * 1.4142135623730951f;
+          for (int j = 0; j < 32; ++j) f[j] = (f[j] > 0.f ? f[j] : 0.2f * f[j]) * gain;
+        }
+        if (p.residual != nullptr && valid) {
+          const uint4* rsrc = reinterpret_cast<const uint4*>(p.residual + pix * p.cout + n0 + c0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (n0 + c0 + 8 * j >= p.cout) continue;
+            const uint4 r = __ldg(rsrc + j);
+            const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              f[8 * j + 2 * q] += __uint_as_float(rw[q] << 16);
+              f[8 * j + 2 * q + 1] += __uint_as_float(rw[q] & 0xffff0000u);
+            }
+          }
         }
         if (valid && !(p.debug & 1)) {
           if (OUT_F32) {
@@ -480,8 +497,23 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           }
         }
         if (p.act == 1) {
+          const float gain = p.act_gain;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = (f[j] > 0.f ? f[j] : 0.2f * f[j]) * 1.4142135623730951f;
+          for (int j = 0; j < 32; ++j) f[j] = (f[j] > 0.f ? f[j] : 0.2f * f[j]) * gain;
+        }
+        if (p.residual != nullptr && valid) {
+          const uint4* rsrc = reinterpret_cast<const uint4*>(p.residual + pix * p.cout + n0 + c0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (n0 + c0 + 8 * j >= p.cout) continue;
+            const uint4 r = __ldg(rsrc + j);
+            const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              f[8 * j + 2 * q] += __uint_as_float(rw[q] << 16);
+              f[8 * j + 2 * q + 1] += __uint_as_float(rw[q] & 0xffff0000u);
+            }
+          }
         }
         if (valid && !(p.debug & 1)) {
           if (OUT_F32) {
@@ -590,6 +622,10 @@ static int conv_tc_dispatch(void* y, const void* x, const void* w, const float* 
   p.tiles_b = (d.batch + p.nb - 1) / p.nb;
   p.n_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
   p.act = d.act; p.out_scale = out_scale; p.bias = bias; p.y = y;
+  p.act_gain = d.act_gain != 0.f ? d.act_gain : 1.4142135623730951f;
+  p.residual = static_cast<const __nv_bfloat16*>(d.residual);
+  TE_CHECK_ARG(!(d.residual && d.out_f32), "conv_tc: a residual input needs bf16 output");
+  TE_CHECK_ARG((reinterpret_cast<uintptr_t>(d.residual) & 15) == 0, "conv_tc: residual must be 16-byte aligned");
   {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("TE_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
@@ -658,6 +694,7 @@ static void same_conv_desc(te_tc_conv_desc& d, int batch, int h, int wd, int cin
   d.w_slices = kh * kw;
   d.in_stride = 1; d.out_stride = 1; d.out_off_y = 0; d.out_off_x = 0;
   d.grid_h = h; d.grid_w = wd; d.act = act; d.out_f32 = out_f32; d.w_bstride = w_bstride;
+  d.act_gain = 0.f; d.wgrad_alpha = 0.f; d.residual = nullptr;
 }
 
 }  // namespace te

@@ -40,6 +40,7 @@ struct WgParams {
   int tiles_per_sample;
   int64_t gw_bstride;             // elements between two samples' gradients (per-sample mode)
   int use_atomics;
+  float alpha;                    // gw += alpha * partial
   float* gw;                      // [w_slices, cout, cin]
 };
 
@@ -162,8 +163,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               if (n0 + c0 + 4 * j >= p.cin) continue;
-              float a0 = __uint_as_float(v[4 * j]), a1 = __uint_as_float(v[4 * j + 1]);
-              float a2 = __uint_as_float(v[4 * j + 2]), a3 = __uint_as_float(v[4 * j + 3]);
+              float a0 = __uint_as_float(v[4 * j]) * p.alpha, a1 = __uint_as_float(v[4 * j + 1]) * p.alpha;
+              float a2 = __uint_as_float(v[4 * j + 2]) * p.alpha, a3 = __uint_as_float(v[4 * j + 3]) * p.alpha;
               if (p.use_atomics)
                 red_add_v4(row + c0 + 4 * j, a0, a1, a2, a3);
               else {
@@ -202,6 +203,7 @@ extern "C" int te_conv_wgrad_tc(float* gw, const void* g, const void* x, const t
                    (reinterpret_cast<uintptr_t>(gw) & 15) == 0 && d.cin % 4 == 0,
                "conv_wgrad_tc: pointers must be 16-byte aligned");
   WgParams p;
+  p.alpha = d.wgrad_alpha != 0.f ? d.wgrad_alpha : 1.f;
   p.batch = d.batch; p.cin = d.cin; p.cout = d.cout; p.ntaps = d.ntaps;
   for (int t = 0; t < 9; ++t) {
     p.tap_dy[t] = t < d.ntaps ? d.tap_dy[t] : 0;

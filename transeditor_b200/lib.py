@@ -38,7 +38,8 @@ class TcConvDesc(ctypes.Structure):
                 ("in_stride", ctypes.c_int), ("out_stride", ctypes.c_int),
                 ("out_off_y", ctypes.c_int), ("out_off_x", ctypes.c_int),
                 ("grid_h", ctypes.c_int), ("grid_w", ctypes.c_int),
-                ("act", ctypes.c_int), ("out_f32", ctypes.c_int), ("w_bstride", ctypes.c_int64)]
+                ("act", ctypes.c_int), ("out_f32", ctypes.c_int), ("w_bstride", ctypes.c_int64),
+                ("act_gain", ctypes.c_float), ("wgrad_alpha", ctypes.c_float), ("residual", ctypes.c_void_p)]
 
 
 _P, _I, _L, _F = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float

@@ -45,11 +45,15 @@ def get_precision():
 
 
 def _to_bf16_cl(x, pad_to=8):
-    """f32/bf16 NCHW -> bf16 channels-last with the channel count padded to a multiple of 8."""
-    c = x.shape[1]
-    if c % pad_to:
-        x = F.pad(x, (0, 0, 0, 0, 0, pad_to - c % pad_to))
-    return x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    """f32/bf16 NCHW -> bf16 channels-last with the channel count padded to a multiple of `pad_to`."""
+    b, c, h, w = x.shape
+    if c % pad_to == 0:
+        return x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    # one memset of the padded bf16 buffer + one strided convert-copy of the real channels (instead of pad in
+    # f32, dtype conversion and a layout change: three passes over the PADDED tensor)
+    buf = torch.zeros((b, h, w, c + pad_to - c % pad_to), dtype=torch.bfloat16, device=x.device)
+    buf[..., :c] = x.permute(0, 2, 3, 1)
+    return buf.permute(0, 3, 1, 2)
 
 
 def _grad_needed(*tensors):
@@ -130,18 +134,23 @@ class EqualConv2d(nn.Module):
         self.padding = padding
         self.bias = nn.Parameter(torch.zeros(out_channel)) if bias else None
 
+    def _tc_weight(self, input):
+        """Master weight for the tensor-core route; the equalised-lr scale is applied while it is repacked."""
+        k = self.weight.shape[2]
+        if self.padding != (k // 2 if self.stride == 1 else 0) or self.stride not in (1, 2):
+            raise RuntimeError("tensor-core EqualConv2d supports stride 1 (pad k//2) and stride 2 (pad 0)")
+        w = self.weight
+        if input.shape[1] != w.shape[1]:  # input channels were zero-padded
+            w = F.pad(w, (0, 0, 0, 0, 0, input.shape[1] - w.shape[1]))
+        return w
+
     def forward(self, input):
-        w = self.weight * self.scale
         if input.dtype == torch.bfloat16:
-            k = w.shape[2]
-            if self.padding != (k // 2 if self.stride == 1 else 0) or self.stride not in (1, 2):
-                raise RuntimeError("tensor-core EqualConv2d supports stride 1 (pad k//2) and stride 2 (pad 0)")
-            if input.shape[1] != w.shape[1]:  # input channels were zero-padded to a multiple of 8
-                w = F.pad(w, (0, 0, 0, 0, 0, input.shape[1] - w.shape[1]))
-            out = tc.conv2d(input, w, stride=self.stride)
+            out = tc.conv2d(input, self._tc_weight(input), stride=self.stride, wscale=self.scale)
             if self.bias is not None:
                 out = out + self.bias.view(1, -1, 1, 1).to(out.dtype)
             return out
+        w = self.weight * self.scale
         out = op.conv2d(input, w, stride=self.stride, padding=self.padding)
         if self.bias is not None:
             out = out + self.bias.view(1, -1, 1, 1)
@@ -192,6 +201,24 @@ class ScaledLeakyReLU(nn.Module):
         return fused_leaky_relu(input, None, self.negative_slope, _SQRT2)
 
 
+class WeightEnergy(torch.autograd.Function):
+    """energy[o, i] = sum_k (W[o, i, k] * scale)^2, the weight-only factor of the demodulation coefficient
+    (model_spatial_query.py:301-303 with the style factored out).  One node instead of autograd's
+    mul / square / sum chain; the backward is written with differentiable ops."""
+
+    @staticmethod
+    def forward(ctx, w, scale):
+        ctx.save_for_backward(w)
+        ctx.scale = scale
+        wn = w * scale
+        return (wn * wn).sum(dim=(2, 3))
+
+    @staticmethod
+    def backward(ctx, g):
+        (w,) = ctx.saved_tensors
+        return w * (g * (2.0 * ctx.scale * ctx.scale))[:, :, None, None], None
+
+
 class ModulatedConv2d(nn.Module):
     """:241-337.  Shared-weight formulation: with Wn = W/sqrt(Cin k^2), s = modulation(style),
     d[b,o] = rsqrt(sum_i s[b,i]^2 * sum_k Wn[o,i,k]^2 + 1e-8):
@@ -230,23 +257,26 @@ class ModulatedConv2d(nn.Module):
         return (f"{self.__class__.__name__}({self.in_channel}, {self.out_channel}, {self.kernel_size}, "
                 f"upsample={self.upsample}, downsample={self.downsample})")
 
-    def scales(self, style):
-        """(s [B,Cin], d [B,Cout] or None, Wn [Cout,Cin,k,k])"""
+    def scales(self, style, fold_scale=False):
+        """(s [B,Cin], d [B,Cout] or None, Wn [Cout,Cin,k,k]); with fold_scale the raw master weight is returned
+        instead of Wn = W * scale (the tensor-core route applies `scale` while repacking the weight)."""
         s = self.modulation(style)
-        wn = self.weight[0] * self.scale
+        w = self.weight[0]
         d = None
         if self.demodulate:
-            energy = wn.square().sum(dim=(2, 3))  # [Cout, Cin]
+            energy = WeightEnergy.apply(w, self.scale)  # [Cout, Cin] = sum_k (W * scale)^2
             d = torch.rsqrt(s.square() @ energy.t() + self.eps)
-        return s, d, wn
+        return s, d, (w if fold_scale else w * self.scale)
 
     def forward(self, input, style, bias=None, noise=None, noise_weight=None, activate=False):
         """`bias`/`noise`/`activate` let StyledConv hand its epilogue to the conv kernel on the
         inference path; reference callers pass only (input, style)."""
+        if input.dtype == torch.bfloat16:
+            s, d, w = self.scales(style, fold_scale=True)
+            fused_ok = not _grad_needed(input, s, w, bias, noise_weight)
+            return self._forward_tc(input, s, d, w, self.scale, bias, noise, noise_weight, activate, fused_ok)
         s, d, wn = self.scales(style)
         fused_ok = not _grad_needed(input, s, wn, bias, noise_weight)
-        if input.dtype == torch.bfloat16:
-            return self._forward_tc(input, s, d, wn, bias, noise, noise_weight, activate, fused_ok)
         if self.upsample:
             if fused_ok:
                 out = op.conv2d_fused(input, wn, in_scale=s, out_scale=d, transpose_stride=2)
@@ -271,10 +301,11 @@ class ModulatedConv2d(nn.Module):
         return _epilogue(out, bias, noise, noise_weight, activate)
 
 
-def _modconv_forward_tc(self, x, s, d, wn, bias, noise, noise_weight, activate, fused_ok):
-    """bf16 channels-last route on the tcgen05 kernels: y = d * conv(x * s, Wn) as
+def _modconv_forward_tc(self, x, s, d, wn, wscale, bias, noise, noise_weight, activate, fused_ok):
+    """bf16 channels-last route on the tcgen05 kernels: y = d * conv(x * s, W * wscale) as
     scale_bc -> conv (-> blur) -> scale_bc, every piece a twice-differentiable custom op.  Without
-    autograd the demodulation, bias and activation ride in the conv kernel's epilogue."""
+    autograd the demodulation, bias and activation ride in the conv kernel's epilogue.  `wn` is the RAW
+    master weight; `wscale` is applied when the weight is repacked to bf16."""
     if self.downsample:
         raise RuntimeError("tensor-core ModulatedConv2d: downsample is not used by the generator")
     k = self.kernel_size
@@ -292,28 +323,29 @@ def _modconv_forward_tc(self, x, s, d, wn, bias, noise, noise_weight, activate, 
         if d is not None:
             wb = wb * d[:, :, None, None, None]
         if self.upsample:
-            v = self.blur(tc.conv_transpose2d(x, wb))
+            v = self.blur(tc.conv_transpose2d(x, wb, wscale=wscale))
         elif fused_ok and noise is None:
             pb = None if bias is None else F.pad(bias.reshape(-1), (0, wn.shape[0] - cout))
-            v = tc.conv_raw(x, tc.pack_weight(wb, False), tc.Mode("s1", k), bias=pb, act=activate)
+            v = tc.conv_raw(x, tc.pack_weight(wb, False, wscale), tc.Mode("s1", k), bias=pb, act=activate)
             return v if wn.shape[0] == cout else v[:, :cout]
         elif activate and noise is None and bias is not None and wn.shape[0] == cout:
-            return tc.conv2d_bias_act(x, wb, bias.reshape(-1))  # bias + lrelu in the conv epilogue
+            return tc.conv2d_bias_act(x, wb, bias.reshape(-1), wscale=wscale)  # bias + lrelu in the epilogue
         else:
-            v = tc.conv2d(x, wb)
+            v = tc.conv2d(x, wb, wscale=wscale)
         if wn.shape[0] != cout:
             v = v[:, :cout]
         return _epilogue(v, bias, noise, noise_weight, activate)
     # Low resolution: shared weights, modulation / demodulation applied to the (small) activations.
     u = op.scale_bc(x, s)
     if self.upsample:
-        v = self.blur(tc.conv_transpose2d(u, wn))
+        v = self.blur(tc.conv_transpose2d(u, wn, wscale=wscale))
     elif fused_ok and noise is None:
         pb = None if bias is None else F.pad(bias.reshape(-1), (0, wn.shape[0] - cout))
-        v = tc.conv_raw(u, tc.pack_weight(wn, False), tc.Mode("s1", k), out_scale=d, bias=pb, act=activate)
+        v = tc.conv_raw(u, tc.pack_weight(wn, False, wscale), tc.Mode("s1", k), out_scale=d, bias=pb,
+                        act=activate)
         return v if wn.shape[0] == cout else v[:, :cout]
     else:
-        v = tc.conv2d(u, wn)
+        v = tc.conv2d(u, wn, wscale=wscale)
     if d is not None:
         v = op.scale_bc(v, d)
     if wn.shape[0] != cout:
@@ -669,25 +701,44 @@ class ConvLayer(nn.Sequential):
     def forward(self, input):
         if input.dtype != torch.bfloat16:
             return super().forward(input)
-        # bf16 tensor-core route: [Blur] -> EqualConv2d + FusedLeakyReLU as ONE kernel (bias and activation
-        # in the convolution epilogue) when the pair is present; anything else runs module by module
+        return self.forward_tc(input)
+
+    def forward_tc(self, input, out_mul=1.0, residual=None):
+        """bf16 tensor-core route, returns layer(input) * out_mul + residual.  [Blur] -> EqualConv2d +
+        FusedLeakyReLU run as ONE kernel (bias and activation in the convolution epilogue); the equalised-lr
+        scale, `out_mul` (folded into the activation gain or the weight scale) and the residual sum cost no
+        pass of their own."""
         mods = list(self)
         x = input
         i = 0
         while i < len(mods):
             m = mods[i]
             nxt = mods[i + 1] if i + 1 < len(mods) else None
+            last = i + (2 if isinstance(nxt, FusedLeakyReLU) else 1) >= len(mods)
             if (isinstance(m, EqualConv2d) and isinstance(nxt, FusedLeakyReLU) and nxt.bias is not None
                     and m.bias is None and m.weight.shape[0] % 8 == 0 and nxt.negative_slope == 0.2
-                    and abs(nxt.scale - _SQRT2) < 1e-12):
-                w = m.weight * m.scale
-                if x.shape[1] != w.shape[1]:
-                    w = F.pad(w, (0, 0, 0, 0, 0, x.shape[1] - w.shape[1]))
-                x = tc.conv2d_bias_act(x, w, nxt.bias, stride=m.stride)
+                    and (residual is None or not last)):
+                gain = nxt.scale * (out_mul if last else 1.0)
+                x = tc.conv2d_bias_act(x, m._tc_weight(x), nxt.bias, stride=m.stride, wscale=m.scale, gain=gain)
+                if last:
+                    out_mul = 1.0
                 i += 2
+            elif isinstance(m, EqualConv2d) and m.bias is None and nxt is None and m.weight.shape[0] % 8 == 0:
+                wscale = m.scale * out_mul
+                if residual is not None:
+                    x = tc.conv2d_residual(x, m._tc_weight(x), residual, stride=m.stride, wscale=wscale)
+                    residual = None
+                else:
+                    x = tc.conv2d(x, m._tc_weight(x), stride=m.stride, wscale=wscale)
+                out_mul = 1.0
+                i += 1
             else:
                 x = m(x)
                 i += 1
+        if out_mul != 1.0:
+            x = x * out_mul
+        if residual is not None:
+            x = x + residual
         return x
 
 
@@ -702,6 +753,11 @@ class ResBlock(nn.Module):
                               bias=False, activate=False)
 
     def forward(self, input):
+        if input.dtype == torch.bfloat16:
+            # (conv2(conv1(x)) + skip(x)) / sqrt(2) with the 1/sqrt(2) folded into conv2's activation gain and the
+            # skip convolution's weight scale, and the sum taken in the skip convolution's epilogue
+            out = self.conv2.forward_tc(self.conv1(input), out_mul=1 / _SQRT2)
+            return self.skip.forward_tc(input, out_mul=1 / _SQRT2, residual=out)
         out = self.conv2(self.conv1(input))
         return (out + self.skip(input)) / _SQRT2
 
@@ -730,6 +786,12 @@ class Discriminator(nn.Module):
             EqualLinear(channels[4], 1))
 
     def forward(self, input):
+        return self.forward_stacked(input, 1)
+
+    def forward_stacked(self, input, sub_batches):
+        """Not in the reference: treats `input` as `sub_batches` independent batches stacked along dim 0 —
+        e.g. cat([fake, real]) — so ONE pass gives exactly the logits of separate calls: every layer is
+        per-sample except the minibatch standard deviation, which is taken per sub-batch."""
         bf16 = _PRECISION == "bf16"
         # bf16: the whole conv stack incl. final_conv on tensor cores; statistics and linears in f32
         # RGB is zero-padded to 64 channels: a TMA box whose rows are mostly out of bounds (8 of 64 channels)
@@ -737,13 +799,17 @@ class Discriminator(nn.Module):
         # input but runs at full speed
         out = self.convs(_to_bf16_cl(input, pad_to=64) if bf16 else input)
         batch, channel, height, width = out.shape
-        group = min(batch, self.stddev_group)
-        # minibatch standard deviation, one scalar per sub-batch (:844-852)
+        if batch % sub_batches:
+            raise ValueError("batch %d is not divisible into %d sub-batches" % (batch, sub_batches))
+        sub = batch // sub_batches
+        group = min(sub, self.stddev_group)
+        # minibatch standard deviation, one scalar per group column of each sub-batch (:844-852)
         stat_in = out.float().contiguous() if bf16 else out
-        grouped = stat_in.view(group, -1, self.stddev_feat, channel // self.stddev_feat, height, width)
-        stddev = torch.sqrt(grouped.var(0, unbiased=False) + 1e-8)
-        stddev = stddev.mean([2, 3, 4], keepdim=True).squeeze(2)
-        stddev = stddev.repeat(group, 1, height, width)
+        grouped = stat_in.view(sub_batches, group, -1, self.stddev_feat, channel // self.stddev_feat, height, width)
+        stddev = torch.sqrt(grouped.var(1, unbiased=False) + 1e-8)          # [S, M, feat, C/feat, H, W]
+        stddev = stddev.mean([3, 4, 5], keepdim=True).squeeze(3)            # [S, M, feat, 1, 1]
+        stddev = stddev.unsqueeze(1).expand(sub_batches, group, -1, self.stddev_feat, height, width)
+        stddev = stddev.reshape(batch, self.stddev_feat, height, width)
         if bf16:
             out = _to_bf16_cl(torch.cat([out, stddev.to(out.dtype)], 1))  # 513 -> 520 channels
             out = self.final_conv(out).float().contiguous()

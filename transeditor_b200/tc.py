@@ -77,10 +77,18 @@ class Mode:
         return not (self.kind == "up" and self.k == 1)
 
 
-def pack_weight(w, transposed):
-    """Master weight [O, I, K, K] (f32) -> bf16 slices [K*K, Cout, Cin] (Cin contiguous), channel counts
-    padded to multiples of 8 with zeros.  A leading batch dimension ([B, O, I, K, K] -> [B, K*K, Cout, Cin])
-    gives per-sample weights."""
+def _scaled_copy(dst, src, scale):
+    """dst (bf16 view) = src (f32, any strides) * scale: permute + scale + f32->bf16 in ONE kernel."""
+    if scale == 1.0:
+        dst.copy_(src)
+    else:
+        torch.mul(src, scale, out=dst)
+
+
+def pack_weight(w, transposed, scale=1.0):
+    """Master weight [O, I, K, K] (f32) times `scale` -> bf16 slices [K*K, Cout, Cin] (Cin contiguous), channel
+    counts padded to multiples of 8 with zeros.  A leading batch dimension ([B, O, I, K, K] ->
+    [B, K*K, Cout, Cin]) gives per-sample weights."""
     if w.dim() == 5:
         b, o, i, k, _ = w.shape
         if o % 8 or i % 8:
@@ -89,7 +97,7 @@ def pack_weight(w, transposed):
             w = w.transpose(1, 2)
             o, i = i, o
         out = torch.empty((b, k * k, o, i), dtype=torch.bfloat16, device=w.device)
-        out.view(b, k, k, o, i).copy_(w.permute(0, 3, 4, 1, 2))  # permute + f32->bf16 in ONE copy kernel
+        _scaled_copy(out.view(b, k, k, o, i), w.permute(0, 3, 4, 1, 2), scale)
         return out
     o, i, k, _ = w.shape
     if transposed:
@@ -98,11 +106,12 @@ def pack_weight(w, transposed):
     po, pi = _pad8(o), _pad8(i)
     alloc = torch.empty if (po == o and pi == i) else torch.zeros
     out = alloc((k * k, po, pi), dtype=torch.bfloat16, device=w.device)
-    out.view(k, k, po, pi)[:, :, :o, :i].copy_(w.permute(2, 3, 0, 1))
+    _scaled_copy(out.view(k, k, po, pi)[:, :, :o, :i], w.permute(2, 3, 0, 1), scale)
     return out
 
 
-def _desc(x, cout, hout, wout, launch, w_slices, act=0, out_f32=0, per_sample=False):
+def _desc(x, cout, hout, wout, launch, w_slices, act=0, out_f32=0, per_sample=False, act_gain=0.0,
+          wgrad_alpha=0.0, residual=None):
     taps, ist, ost, oy, ox, gh, gw = launch
     b, cin, hin, win = x.shape
     d = lib.TcConvDesc()
@@ -116,6 +125,8 @@ def _desc(x, cout, hout, wout, launch, w_slices, act=0, out_f32=0, per_sample=Fa
     d.grid_h, d.grid_w = gh, gw
     d.act, d.out_f32 = act, out_f32
     d.w_bstride = w_slices * cout * cin if per_sample else 0
+    d.act_gain, d.wgrad_alpha = act_gain, wgrad_alpha
+    d.residual = residual.data_ptr() if residual is not None else None
     return d
 
 
@@ -127,9 +138,10 @@ def _cl_bf16(x):
     return x.contiguous(memory_format=torch.channels_last)
 
 
-def conv_raw(x, wp, mode, out_scale=None, bias=None, act=False):
-    """x [B, Cin, H, W] bf16 channels-last, wp = pack_weight(...).  Returns bf16 channels-last."""
-    lib.require_cuda(x, wp, out_scale, bias)
+def conv_raw(x, wp, mode, out_scale=None, bias=None, act=False, act_gain=0.0, residual=None):
+    """x [B, Cin, H, W] bf16 channels-last, wp = pack_weight(...).  Returns bf16 channels-last:
+    act(conv * out_scale + bias) * act_gain + residual."""
+    lib.require_cuda(x, wp, out_scale, bias, residual)
     x = _cl_bf16(x)
     b, cin, hin, win = x.shape
     per_sample = wp.dim() == 4
@@ -138,18 +150,22 @@ def conv_raw(x, wp, mode, out_scale=None, bias=None, act=False):
         raise RuntimeError("conv_tc: weight %s does not match activations %s" % (tuple(wp.shape), tuple(x.shape)))
     hout, wout = mode.output_hw(hin, win)
     y = torch.empty((b, cout, hout, wout), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+    if residual is not None:
+        if residual.shape != y.shape or residual.dtype != torch.bfloat16 or not mode.covers_output():
+            raise RuntimeError("conv_tc: residual must be bf16 of the output's shape %s" % (tuple(y.shape),))
+        residual = residual.contiguous(memory_format=torch.channels_last)
     if not mode.covers_output():
         y.zero_()
     f32 = lambda t: None if t is None else t.to(torch.float32).contiguous()  # noqa: E731
     osc, bi = f32(out_scale), f32(bias)
     for launch in mode.launches(hin, win, hout, wout):
         lib.conv_tc(y, x, wp, osc, bi, _desc(x, cout, hout, wout, launch, wp.shape[-3], 1 if act else 0,
-                                             per_sample=per_sample))
+                                             per_sample=per_sample, act_gain=act_gain, residual=residual))
     return y
 
 
-def wgrad_raw(g, x, mode, w_shape):
-    """Gradient w.r.t. the master weight [O, I, K, K] (f32) of y = conv(x, W; mode) given g = dL/dy."""
+def wgrad_raw(g, x, mode, w_shape, scale=1.0):
+    """Gradient w.r.t. the master weight [O, I, K, K] (f32) of y = conv(x, W * scale; mode) given g = dL/dy."""
     lib.require_cuda(g, x)
     g, x = _cl_bf16(g), _cl_bf16(x)
     b, cin, hin, win = x.shape
@@ -159,7 +175,8 @@ def wgrad_raw(g, x, mode, w_shape):
     shape = (b, k * k, cout, cin) if per_sample else (k * k, cout, cin)
     gw = torch.zeros(shape, dtype=torch.float32, device=x.device)
     for launch in mode.launches(hin, win, hout, wout):
-        lib.conv_wgrad_tc(gw, g, x, _desc(x, cout, hout, wout, launch, k * k, per_sample=per_sample))
+        lib.conv_wgrad_tc(gw, g, x, _desc(x, cout, hout, wout, launch, k * k, per_sample=per_sample,
+                                          wgrad_alpha=scale))
     o, i = w_shape[-4], w_shape[-3]
     if per_sample:
         if mode.transposed:
@@ -171,62 +188,65 @@ def wgrad_raw(g, x, mode, w_shape):
 
 
 class TcConv(Function):
-    """y = conv(x, W; mode) on tensor cores; W is the f32 master weight [O, I, K, K]."""
+    """y = conv(x, W * wscale; mode) on tensor cores; W is the f32 master weight [O, I, K, K] and `wscale` a
+    python float (the equalised-lr factor) applied while the weight is repacked to bf16."""
 
     @staticmethod
-    def forward(ctx, x, w, mode):
+    def forward(ctx, x, w, mode, wscale=1.0):
         ctx.save_for_backward(x, w)
-        ctx.mode = mode
-        return conv_raw(x, pack_weight(w, mode.transposed), mode)
+        ctx.mode, ctx.wscale = mode, wscale
+        return conv_raw(x, pack_weight(w, mode.transposed, wscale), mode)
 
     @staticmethod
     def backward(ctx, gy):
         x, w = ctx.saved_tensors
-        mode = ctx.mode
+        mode, wscale = ctx.mode, ctx.wscale
         gx = gw = None
         if ctx.needs_input_grad[0]:
-            gx = TcConv.apply(gy, w, mode.adjoint((x.shape[2], x.shape[3])))
+            gx = TcConv.apply(gy, w, mode.adjoint((x.shape[2], x.shape[3])), wscale)
             if gx.shape[1] != x.shape[1]:
                 gx = gx[:, :x.shape[1]]
         if ctx.needs_input_grad[1]:
-            gw = TcWeightGrad.apply(x, gy, mode, tuple(w.shape))
-        return gx, gw, None
+            gw = TcWeightGrad.apply(x, gy, mode, tuple(w.shape), wscale)
+        return gx, gw, None, None
 
 
 class TcWeightGrad(Function):
-    """gW = wgrad(x, gy; mode): bilinear, so its backward is two TcConv calls."""
+    """gW = wscale * wgrad(x, gy; mode): bilinear, so its backward is two TcConv calls."""
 
     @staticmethod
-    def forward(ctx, x, gy, mode, w_shape):
+    def forward(ctx, x, gy, mode, w_shape, wscale=1.0):
         ctx.save_for_backward(x, gy)
-        ctx.mode = mode
-        return wgrad_raw(gy, x, mode, w_shape)
+        ctx.mode, ctx.wscale = mode, wscale
+        return wgrad_raw(gy, x, mode, w_shape, wscale)
 
     @staticmethod
     def backward(ctx, ggw):
         x, gy = ctx.saved_tensors
-        mode = ctx.mode
+        mode, wscale = ctx.mode, ctx.wscale
         g_x = g_gy = None
         if ctx.needs_input_grad[0]:
-            g_x = TcConv.apply(gy, ggw, mode.adjoint((x.shape[2], x.shape[3])))
+            g_x = TcConv.apply(gy, ggw, mode.adjoint((x.shape[2], x.shape[3])), wscale)
         if ctx.needs_input_grad[1]:
             g_gy = TcConv.apply(x, ggw, Mode(mode.kind, mode.k, mode.transposed, mode.flip,
-                                             (gy.shape[2], gy.shape[3])))
-        return g_x, g_gy, None, None
+                                             (gy.shape[2], gy.shape[3])), wscale)
+        return g_x, g_gy, None, None, None
 
 
 class TcConvBiasAct(Function):
-    """out = leaky_relu(conv(x, W; mode) + bias, 0.2) * sqrt(2) with bias and activation applied in the
+    """out = leaky_relu(conv(x, W * wscale; mode) + bias, 0.2) * gain with bias and activation applied in the
     convolution kernel's epilogue (no separate bias-act pass over the activation).  Backward is the
     composition of the differentiable pieces: the masked gradient comes from FusedLeakyReLUFunctionBackward
     (sign taken from the saved OUTPUT, like the reference op, utils/op/fused_act.py:27-29), then the usual
     data / weight gradient kernels — so second order works exactly as for the unfused ops."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, mode):
-        out = conv_raw(x, pack_weight(w, mode.transposed), mode, bias=bias, act=True)
+    def forward(ctx, x, w, bias, mode, wscale=1.0, gain=2 ** 0.5):
+        if not gain > 0:
+            raise ValueError("TcConvBiasAct: the gain must be positive (the backward mask is the output's sign)")
+        out = conv_raw(x, pack_weight(w, mode.transposed, wscale), mode, bias=bias, act=True, act_gain=gain)
         ctx.save_for_backward(x, w, out)
-        ctx.mode = mode
+        ctx.mode, ctx.wscale, ctx.gain = mode, wscale, gain
         ctx.bias_dtype = bias.dtype
         return out
 
@@ -234,34 +254,65 @@ class TcConvBiasAct(Function):
     def backward(ctx, g_out):
         from .op import FusedLeakyReLUFunctionBackward
         x, w, out = ctx.saved_tensors
-        mode = ctx.mode
-        g_y, g_b = FusedLeakyReLUFunctionBackward.apply(g_out, out, True, 0.2, 2 ** 0.5, ctx.bias_dtype)
+        mode, wscale = ctx.mode, ctx.wscale
+        g_y, g_b = FusedLeakyReLUFunctionBackward.apply(g_out, out, True, 0.2, ctx.gain, ctx.bias_dtype)
         gx = gw = None
         if ctx.needs_input_grad[0]:
-            gx = TcConv.apply(g_y, w, mode.adjoint((x.shape[2], x.shape[3])))
+            gx = TcConv.apply(g_y, w, mode.adjoint((x.shape[2], x.shape[3])), wscale)
             if gx.shape[1] != x.shape[1]:
                 gx = gx[:, :x.shape[1]]
         if ctx.needs_input_grad[1]:
-            gw = TcWeightGrad.apply(x, g_y, mode, tuple(w.shape))
-        return gx, gw, (g_b if ctx.needs_input_grad[2] else None), None
+            gw = TcWeightGrad.apply(x, g_y, mode, tuple(w.shape), wscale)
+        return gx, gw, (g_b if ctx.needs_input_grad[2] else None), None, None, None
 
 
-def conv2d_bias_act(x, w, bias, stride=1):
-    """conv2d + bias + leaky_relu(0.2)*sqrt(2) in one kernel (EqualConv2d + FusedLeakyReLU, StyledConv tail)."""
-    k = w.shape[-1]
+class TcConvResidual(Function):
+    """y = conv(x, W * wscale; mode) + residual with the sum taken in the convolution epilogue (the ResBlock
+    skip connection, model_spatial_query.py:795-797): no separate pass over the two activations."""
+
+    @staticmethod
+    def forward(ctx, x, w, residual, mode, wscale=1.0):
+        ctx.save_for_backward(x, w)
+        ctx.mode, ctx.wscale = mode, wscale
+        return conv_raw(x, pack_weight(w, mode.transposed, wscale), mode, residual=residual)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        mode, wscale = ctx.mode, ctx.wscale
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            gx = TcConv.apply(gy, w, mode.adjoint((x.shape[2], x.shape[3])), wscale)
+            if gx.shape[1] != x.shape[1]:
+                gx = gx[:, :x.shape[1]]
+        if ctx.needs_input_grad[1]:
+            gw = TcWeightGrad.apply(x, gy, mode, tuple(w.shape), wscale)
+        return gx, gw, (gy if ctx.needs_input_grad[2] else None), None, None
+
+
+def _fwd_mode(w, stride):
+    return Mode("s1" if stride == 1 else "down", w.shape[-1])
+
+
+def conv2d_bias_act(x, w, bias, stride=1, wscale=1.0, gain=2 ** 0.5):
+    """conv2d + bias + leaky_relu(0.2)*gain in one kernel (EqualConv2d + FusedLeakyReLU, StyledConv tail)."""
     if w.shape[-4] % 8:
         raise RuntimeError("conv2d_bias_act needs an output channel count that is a multiple of 8")
-    return TcConvBiasAct.apply(x, w, bias, Mode("s1" if stride == 1 else "down", k))
+    return TcConvBiasAct.apply(x, w, bias, _fwd_mode(w, stride), wscale, gain)
 
 
-def conv2d(x, w, stride=1):
-    """F.conv2d(x, w, stride, padding = k//2 if stride == 1 else 0) in bf16 on tensor cores.
+def conv2d_residual(x, w, residual, stride=1, wscale=1.0):
+    """conv2d(x, w * wscale) + residual in one kernel."""
+    return TcConvResidual.apply(x, w, residual, _fwd_mode(w, stride), wscale)
+
+
+def conv2d(x, w, stride=1, wscale=1.0):
+    """F.conv2d(x, w * wscale, stride, padding = k//2 if stride == 1 else 0) in bf16 on tensor cores.
     w [O, I, K, K], or [B, O, I, K, K] for per-sample weights (the reference's groups=batch form)."""
-    k = w.shape[-1]
-    return TcConv.apply(x, w, Mode("s1" if stride == 1 else "down", k))
+    return TcConv.apply(x, w, _fwd_mode(w, stride), wscale)
 
 
-def conv_transpose2d(x, w_oi, stride=2):
-    """F.conv_transpose2d(x, w_oi.transpose(0, 1), stride=2, padding=0), weight kept [O, I, K, K]."""
+def conv_transpose2d(x, w_oi, stride=2, wscale=1.0):
+    """F.conv_transpose2d(x, (w_oi * wscale).transpose(0, 1), stride=2, padding=0), weight kept [O, I, K, K]."""
     assert stride == 2
-    return TcConv.apply(x, w_oi, Mode("up", w_oi.shape[-1]))
+    return TcConv.apply(x, w_oi, Mode("up", w_oi.shape[-1]), wscale)

@@ -260,8 +260,9 @@ class Trainer:
         _set_requires_grad(self.d_flat, True)
         z, p = self._latents(self.cfg.batch)
         fake_img, _, _ = self.generator(z, p)
-        fake_pred = self.discriminator(fake_img)
-        real_pred = self.discriminator(self._real)
+        # one discriminator pass over [fake; real] (two sub-batches): same logits as two calls
+        # (train_spatial_query.py:199-201), half the launches and weight repacks
+        fake_pred, real_pred = self.discriminator.forward_stacked(torch.cat([fake_img, self._real]), 2).chunk(2)
         d_loss = d_logistic_loss(real_pred, fake_pred)
         self.d_flat.clear_grads()
         d_loss.backward()
