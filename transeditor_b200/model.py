@@ -16,6 +16,7 @@ work unmodified.  What differs is everything underneath:
 Citations `:N` are into the reference's model_spatial_query.py.
 """
 import math
+import os
 
 import torch
 from torch import nn
@@ -54,6 +55,16 @@ def _to_bf16_cl(x, pad_to=8):
     buf = torch.zeros((b, h, w, c + pad_to - c % pad_to), dtype=torch.bfloat16, device=x.device)
     buf[..., :c] = x.permute(0, 2, 3, 1)
     return buf.permute(0, 3, 1, 2)
+
+
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    key = torch.device(device).index
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device)
+    return _SIDE_STREAMS[key]
 
 
 def _grad_needed(*tensors):
@@ -178,9 +189,8 @@ class EqualLinear(nn.Module):
         x2 = input.reshape(-1, input.shape[-1])
         if self.activation or self.bias is None:
             out = torch.addmm(x2.new_empty(1), x2, self.weight.t(), beta=0, alpha=self.scale)
-        else:
-            b = self.bias if self.lr_mul == 1 else self.bias * self.lr_mul
-            out = torch.addmm(b, x2, self.weight.t(), alpha=self.scale)
+        else:  # beta folds the bias's lr_mul too: no `bias * lr_mul` kernel, forward or backward
+            out = torch.addmm(self.bias, x2, self.weight.t(), beta=self.lr_mul, alpha=self.scale)
         out = out.reshape(*input.shape[:-1], out.shape[-1])
         if self.activation:
             return fused_leaky_relu(out, self.bias * self.lr_mul)
@@ -210,8 +220,8 @@ class WeightEnergy(torch.autograd.Function):
     def forward(ctx, w, scale):
         ctx.save_for_backward(w)
         ctx.scale = scale
-        wn = w * scale
-        return (wn * wn).sum(dim=(2, 3))
+        # ||W[o,i,:]||^2 * scale^2 with ONE pass over the weight (the literal mul / square / sum chain is three)
+        return torch.linalg.vector_norm(w, dim=(2, 3)).square_().mul_(scale * scale)
 
     @staticmethod
     def backward(ctx, g):
@@ -272,9 +282,11 @@ class ModulatedConv2d(nn.Module):
         """`bias`/`noise`/`activate` let StyledConv hand its epilogue to the conv kernel on the
         inference path; reference callers pass only (input, style)."""
         if input.dtype == torch.bfloat16:
-            s, d, w = self.scales(style, fold_scale=True)
-            fused_ok = not _grad_needed(input, s, w, bias, noise_weight)
-            return self._forward_tc(input, s, d, w, self.scale, bias, noise, noise_weight, activate, fused_ok)
+            ops = self._take_prepared(input)
+            if ops is None:
+                ops = self.tc_operands(style, input.shape[2] * input.shape[3])
+            fused_ok = not _grad_needed(input, ops["s"], ops["w"], bias, noise_weight)
+            return self._forward_tc(input, ops, bias, noise, noise_weight, activate, fused_ok)
         s, d, wn = self.scales(style)
         fused_ok = not _grad_needed(input, s, wn, bias, noise_weight)
         if self.upsample:
@@ -301,20 +313,20 @@ class ModulatedConv2d(nn.Module):
         return _epilogue(out, bias, noise, noise_weight, activate)
 
 
-def _modconv_forward_tc(self, x, s, d, wn, wscale, bias, noise, noise_weight, activate, fused_ok):
-    """bf16 channels-last route on the tcgen05 kernels: y = d * conv(x * s, W * wscale) as
-    scale_bc -> conv (-> blur) -> scale_bc, every piece a twice-differentiable custom op.  Without
-    autograd the demodulation, bias and activation ride in the conv kernel's epilogue.  `wn` is the RAW
-    master weight; `wscale` is applied when the weight is repacked to bf16."""
+def _modconv_tc_operands(self, style, hw):
+    """Everything of the bf16 route that depends only on (style, weights): s, d and — at high resolution —
+    the per-sample weights.  No activation is touched, so Generator.forward computes these for ALL layers on a
+    side stream while the main stream runs the convolutions (`prepare`)."""
     if self.downsample:
         raise RuntimeError("tensor-core ModulatedConv2d: downsample is not used by the generator")
+    s, d, wn = self.scales(style, fold_scale=True)
     k = self.kernel_size
     cout = self.out_channel
-    if cout % 8:  # ToRGB: pad the 3 output channels to 8 (zero rows), sliced off below
+    if cout % 8:  # ToRGB: pad the 3 output channels to 8 (zero rows), sliced off after the conv
         wn = F.pad(wn, (0, 0, 0, 0, 0, 0, 0, 8 - cout % 8))
         if d is not None:
             d = F.pad(d, (0, 8 - cout % 8), value=1.0)
-    hw = x.shape[2] * x.shape[3]
+    ops = {"s": s, "d": d, "w": wn, "wb": None}
     if hw >= 128 and hw >= 4 * wn.shape[0] * k * k:
         # High resolution: per-sample weights W*s*d (the reference's own formulation, :299-304) are tiny
         # next to the activations (1-15 % of their size), so fold modulation AND demodulation into them
@@ -322,6 +334,48 @@ def _modconv_forward_tc(self, x, s, d, wn, wscale, bias, noise, noise_weight, ac
         wb = wn.unsqueeze(0) * s[:, None, :, None, None]
         if d is not None:
             wb = wb * d[:, :, None, None, None]
+        ops["wb"] = wb
+    return ops
+
+
+def _modconv_prepare(self, style, hw, side, main):
+    """Compute tc_operands on the stream `side`; forward() picks them up after waiting on the event."""
+    with torch.cuda.stream(side):
+        ops = self.tc_operands(style, hw)
+        ev = torch.cuda.Event()
+        ev.record(side)
+    # temporaries allocated on the side stream but consumed (and later freed) under the main stream
+    temps = [ops["s"], ops["d"], ops["wb"]]
+    if ops["w"].data_ptr() != self.weight.data_ptr():
+        temps.append(ops["w"])
+    for t in temps:
+        if t is not None and t.is_cuda:
+            t.record_stream(main)
+    self._prepared = (ops, ev, hw)
+
+
+def _modconv_take_prepared(self, x):
+    prep = getattr(self, "_prepared", None)
+    if prep is None:
+        return None
+    self._prepared = None
+    ops, ev, hw = prep
+    if hw != x.shape[2] * x.shape[3] or ops["s"].shape[0] != x.shape[0]:
+        return None
+    torch.cuda.current_stream(x.device).wait_event(ev)
+    return ops
+
+
+def _modconv_forward_tc(self, x, ops, bias, noise, noise_weight, activate, fused_ok):
+    """bf16 channels-last route on the tcgen05 kernels: y = d * conv(x * s, W * wscale) as
+    scale_bc -> conv (-> blur) -> scale_bc, every piece a twice-differentiable custom op.  Without
+    autograd the demodulation, bias and activation ride in the conv kernel's epilogue.  ops["w"] is the RAW
+    master weight; the equalised-lr scale is applied when the weight is repacked to bf16."""
+    s, d, wn, wb = ops["s"], ops["d"], ops["w"], ops["wb"]
+    wscale = self.scale
+    k = self.kernel_size
+    cout = self.out_channel
+    if wb is not None:
         if self.upsample:
             v = self.blur(tc.conv_transpose2d(x, wb, wscale=wscale))
         elif fused_ok and noise is None:
@@ -354,6 +408,9 @@ def _modconv_forward_tc(self, x, s, d, wn, wscale, bias, noise, noise_weight, ac
 
 
 ModulatedConv2d._forward_tc = _modconv_forward_tc
+ModulatedConv2d.tc_operands = _modconv_tc_operands
+ModulatedConv2d.prepare = _modconv_prepare
+ModulatedConv2d._take_prepared = _modconv_take_prepared
 
 
 def _epilogue(out, bias, noise, noise_weight, activate):
@@ -582,6 +639,30 @@ class Generator(nn.Module):
             noises += [torch.randn(1, 1, 2 ** i, 2 ** i, device=device) for _ in range(2)]
         return noises
 
+    def _prepare_styles(self, latent):
+        """bf16 route: the per-layer style work (modulation linear, demodulation coefficients, per-sample
+        weights; ~11 small kernels per layer forward, ~3x that backward) depends only on `latent` and the
+        weights, so it is issued up front on a SIDE stream and overlaps the convolutions on the main stream —
+        in the backward pass too, since autograd runs each node on its forward stream.  Each layer waits on its
+        own event.  Disabled with TE_STYLE_STREAM=0."""
+        layers = [(self.conv1.conv, 0, 4), (self.to_rgb1.conv, 1, 4)]
+        i, res = 1, 4
+        for conv1, conv2, to_rgb in zip(self.convs[::2], self.convs[1::2], self.to_rgbs):
+            layers.append((conv1.conv, i, res))      # the upsampling conv sees the LOW-resolution input
+            res *= 2
+            layers.append((conv2.conv, i + 1, res))
+            layers.append((to_rgb.conv, i + 2, res))
+            i += 2
+        for m, _, _ in layers:
+            m._prepared = None
+        if not latent.is_cuda or os.environ.get("TE_STYLE_STREAM", "1") == "0":
+            return
+        main = torch.cuda.current_stream(latent.device)
+        side = _side_stream(latent.device)
+        side.wait_stream(main)
+        for m, idx, r in layers:
+            m.prepare(latent[:, idx], r * r, side, main)
+
     def _map_columns(self, code, network, count):
         """:626-646 as ONE batched GEMM: column i of `code` [B,D,C] goes through its own
         EqualLinear(+fused lrelu).  Returns [B,D,C]."""
@@ -657,6 +738,7 @@ class Generator(nn.Module):
         out = spatialcode.permute(0, 2, 1).reshape(batch, 512, 4, 4)
         if _PRECISION == "bf16":
             out = _to_bf16_cl(out)
+            self._prepare_styles(latent)
         out = self.conv1(out, latent[:, 0], noise=noise[0])
         skip = self.to_rgb1(out, latent[:, 1])
         i = 1
