@@ -94,3 +94,16 @@ def upfirdn2d_index_form(x, fir, up, down, pad0, pad1):
                         acc = acc + x[yy, xx] * flipped[tap_y + dy * up, tap_x + dx * up]
             out[oy, ox] = acc
     return out
+
+
+def linear_interpolate_np(latent_code, boundary, start_distance=-100, end_distance=100, steps=10):
+    """numpy restatement of our_interfaceGAN/linear_interpolation.py:36-48 (test oracle for
+    transeditor_b200.inference.linear_interpolate): offsets = linspace(start, end, steps); a [1, D] code first
+    loses its own projection on the boundary normal; a [1, N, D] code is shifted row-wise by the raw offsets."""
+    import numpy as np
+    offs = np.linspace(start_distance, end_distance, steps)
+    if latent_code.ndim == 2:
+        offs = (offs - latent_code.dot(boundary.T)).reshape(-1, 1).astype(np.float32)
+        return latent_code + offs * boundary
+    offs = offs.reshape(-1, 1, 1).astype(np.float32)
+    return latent_code + offs * boundary.reshape(1, 1, -1)
