@@ -286,3 +286,36 @@ def test_tc_bias_act_gain(gain):
     _close(gx, gxr, "gain dgrad")
     _close(gw, gwr, "gain wgrad", rel=2e-2)
     _close(gb, gbr, "gain bias grad", rel=2e-2)
+
+
+def test_tc_carry_sums_fanout_gradient_in_dgrad_epilogue():
+    """x feeds conv+act AND a second branch: with the carry form the second branch's gradient arrives as the
+    dgrad kernel's residual; result and second order (R1-style) equal the plain two-consumer graph."""
+    from transeditor_b200 import tc
+    b, c, h, k = 4, 64, 32, 3
+    wscale = 1.0 / math.sqrt(c * k * k)
+    x0 = _bf(_rand(b, c, h, h, seed=81))
+    w = _rand(c, c, k, k, seed=82).requires_grad_(True)
+    bias = _rand(c, seed=83).requires_grad_(True)
+    m2 = _bf(_rand(b, c, h, h, seed=84))
+    gy = _bf(_rand(b, c, h, h, seed=85))
+
+    def run(carry):
+        x = x0.clone().requires_grad_(True)
+        if carry:
+            y, xa = tc.conv2d_bias_act_carry(x, w, bias, wscale=wscale)
+        else:
+            y, xa = tc.conv2d_bias_act(x, w, bias, wscale=wscale), x
+        z = y + (xa * m2) * xa            # the second branch, non-linear in x so that second order is exercised
+        (gx,) = torch.autograd.grad(z, x, gy, create_graph=True)
+        pen = gx.float().square().mean()
+        gw, gb = torch.autograd.grad(pen, (w, bias), allow_unused=True)
+        return z, gx, gw, gb
+
+    z0, gx0, gw0, gb0 = run(False)
+    z1, gx1, gw1, gb1 = run(True)
+    assert torch.equal(z0, z1)
+    _close(gx1, gx0, "carry dgrad", rel=2e-2)
+    _close(gw1, gw0, "carry second-order weight grad", rel=3e-2)
+    if gb0 is not None:
+        _close(gb1, gb0, "carry second-order bias grad", rel=3e-2)

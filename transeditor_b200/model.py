@@ -785,6 +785,20 @@ class ConvLayer(nn.Sequential):
             return super().forward(input)
         return self.forward_tc(input)
 
+    def forward_tc_carry(self, input):
+        """(layer(input), input_alias) for a layer that is exactly EqualConv2d + FusedLeakyReLU: the alias feeds
+        the input's second consumer so that the two gradient contributions are summed inside this layer's
+        data-gradient kernel (tc.TcConvBiasActCarry).  Falls back to (forward_tc(input), input)."""
+        mods = list(self)
+        if (len(mods) == 2 and isinstance(mods[0], EqualConv2d) and isinstance(mods[1], FusedLeakyReLU)
+                and mods[1].bias is not None and mods[0].bias is None and mods[0].weight.shape[0] % 8 == 0
+                and mods[1].negative_slope == 0.2 and mods[0].stride == 1 and torch.is_grad_enabled()
+                and input.requires_grad):
+            m, act = mods
+            return tc.conv2d_bias_act_carry(input, m._tc_weight(input), act.bias, stride=1, wscale=m.scale,
+                                            gain=act.scale)
+        return self.forward_tc(input), input
+
     def forward_tc(self, input, out_mul=1.0, residual=None):
         """bf16 tensor-core route, returns layer(input) * out_mul + residual.  [Blur] -> EqualConv2d +
         FusedLeakyReLU run as ONE kernel (bias and activation in the convolution epilogue); the equalised-lr
@@ -838,8 +852,10 @@ class ResBlock(nn.Module):
         if input.dtype == torch.bfloat16:
             # (conv2(conv1(x)) + skip(x)) / sqrt(2) with the 1/sqrt(2) folded into conv2's activation gain and the
             # skip convolution's weight scale, and the sum taken in the skip convolution's epilogue
-            out = self.conv2.forward_tc(self.conv1(input), out_mul=1 / _SQRT2)
-            return self.skip.forward_tc(input, out_mul=1 / _SQRT2, residual=out)
+            # and the two gradient contributions of `input` summed in conv1's data-gradient epilogue (carry)
+            h, input_alias = self.conv1.forward_tc_carry(input)
+            out = self.conv2.forward_tc(h, out_mul=1 / _SQRT2)
+            return self.skip.forward_tc(input_alias, out_mul=1 / _SQRT2, residual=out)
         out = self.conv2(self.conv1(input))
         return (out + self.skip(input)) / _SQRT2
 

@@ -266,6 +266,48 @@ class TcConvBiasAct(Function):
         return gx, gw, (g_b if ctx.needs_input_grad[2] else None), None, None, None
 
 
+class TcConvBiasActCarry(Function):
+    """TcConvBiasAct that also hands its INPUT on: returns (out, x_alias).  A second consumer of x (the ResBlock
+    skip branch, model_spatial_query.py:795-797) reads x_alias instead of x, so this node receives BOTH gradient
+    contributions of x and forms their sum in the data-gradient kernel's epilogue (dgrad + residual) — instead
+    of autograd adding two activation-sized tensors in a pass of its own."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, mode, wscale=1.0, gain=2 ** 0.5):
+        if not gain > 0:
+            raise ValueError("TcConvBiasActCarry: the gain must be positive")
+        out = conv_raw(x, pack_weight(w, mode.transposed, wscale), mode, bias=bias, act=True, act_gain=gain)
+        ctx.save_for_backward(x, w, out)
+        ctx.mode, ctx.wscale, ctx.gain = mode, wscale, gain
+        ctx.bias_dtype = bias.dtype
+        return out, x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g_out, g_alias):
+        from .op import FusedLeakyReLUFunctionBackward
+        x, w, out = ctx.saved_tensors
+        mode, wscale = ctx.mode, ctx.wscale
+        gx = gw = g_b = None
+        if g_out is None:
+            return g_alias, None, None, None, None, None
+        g_y, g_b = FusedLeakyReLUFunctionBackward.apply(g_out, out, True, 0.2, ctx.gain, ctx.bias_dtype)
+        if ctx.needs_input_grad[0]:
+            adj = mode.adjoint((x.shape[2], x.shape[3]))
+            fusable = (g_alias is not None and adj.covers_output() and w.shape[-3] % 8 == 0
+                       and g_alias.dtype == torch.bfloat16)
+            if fusable:
+                gx = TcConvResidual.apply(g_y, w, g_alias, adj, wscale)
+            else:
+                gx = TcConv.apply(g_y, w, adj, wscale)
+                if gx.shape[1] != x.shape[1]:
+                    gx = gx[:, :x.shape[1]]
+                if g_alias is not None:
+                    gx = gx + g_alias
+        if ctx.needs_input_grad[1]:
+            gw = TcWeightGrad.apply(x, g_y, mode, tuple(w.shape), wscale)
+        return gx, gw, (g_b if ctx.needs_input_grad[2] else None), None, None, None
+
+
 class TcConvResidual(Function):
     """y = conv(x, W * wscale; mode) + residual with the sum taken in the convolution epilogue (the ResBlock
     skip connection, model_spatial_query.py:795-797): no separate pass over the two activations."""
@@ -299,6 +341,13 @@ def conv2d_bias_act(x, w, bias, stride=1, wscale=1.0, gain=2 ** 0.5):
     if w.shape[-4] % 8:
         raise RuntimeError("conv2d_bias_act needs an output channel count that is a multiple of 8")
     return TcConvBiasAct.apply(x, w, bias, _fwd_mode(w, stride), wscale, gain)
+
+
+def conv2d_bias_act_carry(x, w, bias, stride=1, wscale=1.0, gain=2 ** 0.5):
+    """conv2d_bias_act that returns (out, x_alias); feed x's other consumer from x_alias (see TcConvBiasActCarry)."""
+    if w.shape[-4] % 8:
+        raise RuntimeError("conv2d_bias_act needs an output channel count that is a multiple of 8")
+    return TcConvBiasActCarry.apply(x, w, bias, _fwd_mode(w, stride), wscale, gain)
 
 
 def conv2d_residual(x, w, residual, stride=1, wscale=1.0):
