@@ -181,6 +181,46 @@ def test_upfirdn2d_tma_staged_channels_last(dtype, case):
     assert (y.double().cpu() - ref).abs().max().item() <= tol * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("case", [
+    # (n, c, h, w, up, down, pad, fir): 16-bit channels-last factor-2 resampling on the TMA-staged kernels
+    (2, 64, 64, 64, 1, 2, (1, 1), "sep"), (1, 128, 33, 70, 1, 2, (1, 1), "sep"), (1, 64, 40, 36, 1, 2, (2, 2), "sep"),
+    (2, 64, 40, 40, 1, 2, (0, 0), "full"), (1, 64, 90, 50, 1, 2, (-1, 2), "sep"), (4, 64, 16, 16, 1, 2, (1, 1), "sep"),
+    (2, 64, 32, 32, 2, 1, (2, 1), "sep"), (1, 64, 31, 45, 2, 1, (2, 1), "sep"), (1, 128, 40, 40, 2, 1, (1, 1), "sep"),
+    (1, 64, 40, 36, 2, 1, (3, 2), "full"), (1, 64, 30, 30, 2, 1, (0, 0), "sep"), (1, 64, 25, 25, 2, 1, (-1, 3), "k3"),
+    (8, 64, 8, 8, 2, 1, (2, 1), "sep"), (1, 192, 64, 64, 1, 2, (1, 1), "k3"),
+])
+def test_upfirdn2d_tma_resample_channels_last(dtype, case):
+    from utils.op import upfirdn2d
+    n, c, h, w, up, down, pad, kind = case
+    x = _rand(n, c, h, w, dtype=dtype, seed=41)
+    if kind == "sep":
+        fir = torch.outer(torch.tensor([1., 3., 3., 1.]), torch.tensor([1., 3., 3., 1.])) / 64 * up * up
+    elif kind == "full":
+        fir = _rand(4, 4, seed=42).abs() / 8 * up * up
+    else:
+        fir = _rand(3, 3, seed=43).abs() / 4 * up * up
+    y = upfirdn2d(x.to(DEV).contiguous(memory_format=torch.channels_last), fir.to(DEV), up=up, down=down, pad=pad)
+    ref = ops_cpu.upfirdn2d(x.double(), fir.double(), up, down, pad)
+    assert y.shape == ref.shape and y.is_contiguous(memory_format=torch.channels_last)
+    tol = {torch.float16: 2e-3, torch.bfloat16: 1.6e-2}[dtype]
+    assert (y.double().cpu() - ref).abs().max().item() <= tol * max(1.0, ref.abs().max().item())
+
+
+def test_upfirdn2d_down2_gradient_is_the_up2_kernel():
+    """Backward of the decimating FIR (ResBlock skip) = up=2 FIR of the compact gradient; both TMA kernels."""
+    from utils.op import upfirdn2d
+    x = _rand(2, 64, 64, 64, dtype=torch.bfloat16, seed=45)
+    fir = torch.outer(torch.tensor([1., 3., 3., 1.]), torch.tensor([1., 3., 3., 1.])) / 64
+    xd = x.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    y = upfirdn2d(xd, fir.to(DEV), down=2, pad=(1, 1))
+    g = _rand(*y.shape, dtype=torch.bfloat16, seed=46)
+    (gx,) = torch.autograd.grad(y, xd, g.to(DEV).contiguous(memory_format=torch.channels_last))
+    xr = x.double().requires_grad_(True)
+    (gr,) = torch.autograd.grad(ops_cpu.upfirdn2d(xr, fir.double(), 1, 2, (1, 1)), xr, g.double())
+    assert (gx.double().cpu() - gr).abs().max().item() <= 1.6e-2 * max(1.0, gr.abs().max().item())
+
+
 def test_upfirdn2d_channels_last_nonseparable_fir():
     """The vectorised channels-last kernel takes a separable fast path; a random (rank-4) FIR must go
     through its general path and still match."""

@@ -135,6 +135,16 @@ inline PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   return fn;
 }
 
+// cuTensorMapEncodeTiled is a DRIVER entry point and needs a current context; a thread that has not made a runtime
+// call yet (autograd's backward thread running one of our ops first) has none bound: CUDA_ERROR_INVALID_CONTEXT.
+inline void bind_primary_context() {
+  thread_local bool bound = false;
+  if (!bound) {
+    cudaFree(nullptr);
+    bound = true;
+  }
+}
+
 // bf16 tensor map, 128-byte swizzle, zero fill out of bounds.  estr = traversal strides (nullptr: all 1).
 inline int encode_map_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                            const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* estr) {
@@ -143,6 +153,7 @@ inline int encode_map_bf16(CUtensorMap* map, const void* base, int rank, const u
     set_error("tensor-core path: cuTensorMapEncodeTiled entry point unavailable");
     return TE_ERR_CUDA;
   }
+  bind_primary_context();
   uint32_t ones[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides_bytes, box,
                   estr ? estr : ones, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -162,6 +173,7 @@ inline int encode_map_u16_linear(CUtensorMap* map, const void* base, int rank, c
     set_error("TMA path: cuTensorMapEncodeTiled entry point unavailable");
     return TE_ERR_CUDA;
   }
+  bind_primary_context();
   uint32_t ones[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, rank, const_cast<void*>(base), dims, strides_bytes, box, ones,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

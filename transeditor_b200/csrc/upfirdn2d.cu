@@ -935,6 +935,236 @@ static int launch_fir_nhwc_tma(T* out, const T* in, const float* fir, const Upfi
   }
 }
 
+
+// ---- channels-last, 16-bit, TMA-staged, factor-2 resampling ----------------------------------------------------
+// down = 2 (blur + decimate: the ResBlock skip branch evaluated only where the stride-2 1x1 convolution reads it,
+// model_spatial_query.py:744-750,788) and up = 2 (its gradient, and the RGB-skip Upsample geometry).  Same
+// producer/consumer ring as fir_nhwc_tma_kernel.  Every output is a direct sum over the taps that touch it (16 for
+// down = 2, 4 for up = 2 — neighbouring outputs share no horizontal partial sums at stride 2, so a separable
+// evaluation would not save anything).
+struct FirResampleTiling {
+  int tw, th;                    // output tile
+  int box_w, box_h;              // input box (pixels)
+  int groups_x, groups_y;        // thread groups per tile: (tw, th/2) for down=2, (tw/2, th/4) for up=2
+  int tiles_x, tiles_y, chunks;
+  int org_x, org_y;              // input coordinate of the box of tile (0, 0)
+  int64_t jobs;
+};
+
+template <typename T, int MODE>  // MODE 0: down=2; 1: up=2 with even pad0; 2: up=2 with odd pad0
+__global__ void __launch_bounds__(256, 2)
+fir_nhwc_resample_tma_kernel(T* __restrict__ out, const __grid_constant__ CUtensorMap in_map,
+                             const float* __restrict__ fir, UpfirdnParams p, FirResampleTiling t) {
+  extern __shared__ __align__(128) uint8_t fir_smem_raw[];
+  __shared__ __align__(8) uint64_t full[FIR_TMA_STAGES];
+  __shared__ float sk[4][4];
+  uint8_t* stage0 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fir_smem_raw) + 127) & ~uintptr_t(127));
+  const uint32_t stage_bytes = uint32_t(t.box_h) * t.box_w * 128u;
+  const int tid = threadIdx.x;
+  if (tid < 16) {
+    int ky = tid >> 2, kx = tid & 3;
+    sk[ky][kx] = (ky < p.kh && kx < p.kw) ? fir[(p.kh - 1 - ky) * p.kw + (p.kw - 1 - kx)] : 0.f;
+  }
+  if (tid == 32) {
+    for (int s = 0; s < FIR_TMA_STAGES; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  constexpr int IN_PER_OUT_NUM = MODE == 0 ? 2 : 1, IN_PER_OUT_DEN = MODE == 0 ? 1 : 2;
+  auto issue = [&](int64_t job, int s) {
+    const int chunk = int(job % t.chunks);
+    int64_t r = job / t.chunks;
+    const int tx = int(r % t.tiles_x); r /= t.tiles_x;
+    const int ty = int(r % t.tiles_y); r /= t.tiles_y;
+    mbar_expect_tx(&full[s], stage_bytes);
+    tma_load_4d(stage0 + size_t(s) * stage_bytes, &in_map, &full[s], chunk * 64,
+                t.org_x + tx * t.tw * IN_PER_OUT_NUM / IN_PER_OUT_DEN,
+                t.org_y + ty * t.th * IN_PER_OUT_NUM / IN_PER_OUT_DEN, int(r));
+  };
+  if (tid == 32) {
+    int64_t job = blockIdx.x;
+    for (int s = 0; s < FIR_TMA_STAGES && job < t.jobs; ++s, job += gridDim.x) issue(job, s);
+  }
+  float2 wt[4][4];
+#pragma unroll
+  for (int ky = 0; ky < 4; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 4; ++kx) wt[ky][kx] = make_float2(sk[ky][kx], sk[ky][kx]);
+  const int q8 = tid & 7;
+  const int gx = (tid >> 3) % t.groups_x;
+  const int gy = (tid >> 3) / t.groups_x;
+  const bool active = gy < t.groups_y;
+
+  int it = 0;
+  for (int64_t job = blockIdx.x; job < t.jobs; job += gridDim.x, ++it) {
+    const int s = it % FIR_TMA_STAGES;
+    mbar_wait(&full[s], (it / FIR_TMA_STAGES) & 1);
+    if (active) {
+      const int chunk = int(job % t.chunks);
+      int64_t r = job / t.chunks;
+      const int tx = int(r % t.tiles_x); r /= t.tiles_x;
+      const int ty = int(r % t.tiles_y); r /= t.tiles_y;
+      const uint8_t* tile = stage0 + size_t(s) * stage_bytes + q8 * 16;
+      if (MODE == 0) {
+        // thread: output column gx, output rows 2*gy, 2*gy+1 of the tile; window rows 4*gy .. 4*gy+5, cols 2*gx .. +3
+        const int ox = tx * t.tw + gx, oy0 = ty * t.th + 2 * gy;
+        if (ox < p.out_w && oy0 < p.out_h) {
+          float2 acc[2][4];
+#pragma unroll
+          for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[a][q] = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int rr = 0; rr < 6; ++rr) {
+#pragma unroll
+            for (int kx = 0; kx < 4; ++kx) {
+              const uint4 raw = *reinterpret_cast<const uint4*>(tile + (size_t(4 * gy + rr) * t.box_w + 2 * gx + kx) * 128);
+#pragma unroll
+              for (int a = 0; a < 2; ++a) {
+                const int ky = rr - 2 * a;
+                if (ky >= 0 && ky < 4) {
+#pragma unroll
+                  for (int q = 0; q < 4; ++q)
+                    acc[a][q] = __ffma2_rn(Unpack2<T>::get((&raw.x)[q]), wt[ky][kx], acc[a][q]);
+                }
+              }
+            }
+          }
+          T* dst = out + ((r * p.out_h + oy0) * int64_t(p.out_w) + ox) * p.minor + chunk * 64 + q8 * 8;
+#pragma unroll
+          for (int a = 0; a < 2; ++a) {
+            if (oy0 + a >= p.out_h) break;
+            uint4 o;
+            o.x = Unpack2<T>::put(acc[a][0]); o.y = Unpack2<T>::put(acc[a][1]);
+            o.z = Unpack2<T>::put(acc[a][2]); o.w = Unpack2<T>::put(acc[a][3]);
+            *reinterpret_cast<uint4*>(dst + int64_t(a) * p.out_w * p.minor) = o;
+          }
+        }
+      } else {
+        // up = 2, pad0 = 2m + E.  Output o = 2i + par reads compact inputs i - m + j + (E == 0 ? par : 0), j = 0, 1,
+        // through taps (E ^ par) + 2j.  Thread: output columns 2*gx, 2*gx+1 and rows 4*gy .. 4*gy+3 of the tile;
+        // the box starts at compact (i0 - m): rows 2*gy .. 2*gy+3, columns gx .. gx+2.
+        constexpr int E = MODE == 1 ? 0 : 1;
+        const int ox0 = tx * t.tw + 2 * gx, oy0 = ty * t.th + 4 * gy;
+        if (ox0 < p.out_w && oy0 < p.out_h) {
+          float2 acc[4][2][4];
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int w = 0; w < 2; ++w)
+#pragma unroll
+              for (int q = 0; q < 4; ++q) acc[a][w][q] = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr) {
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) {
+              if (E == 1 && cc == 2) continue;
+              const uint4 raw = *reinterpret_cast<const uint4*>(tile + (size_t(2 * gy + rr) * t.box_w + gx + cc) * 128);
+              float2 v[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) v[q] = Unpack2<T>::get((&raw.x)[q]);
+#pragma unroll
+              for (int a = 0; a < 4; ++a) {
+                const int pa = a & 1, h = a >> 1;
+                const int jy = rr - h - (E == 0 ? pa : 0);
+                if (jy < 0 || jy > 1) continue;
+                const int ky = (E ^ pa) + 2 * jy;
+#pragma unroll
+                for (int w = 0; w < 2; ++w) {
+                  const int jx = cc - (E == 0 ? w : 0);
+                  if (jx < 0 || jx > 1) continue;
+                  const int kx = (E ^ w) + 2 * jx;
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) acc[a][w][q] = __ffma2_rn(v[q], wt[ky][kx], acc[a][w][q]);
+                }
+              }
+            }
+          }
+          T* dst = out + ((r * p.out_h + oy0) * int64_t(p.out_w) + ox0) * p.minor + chunk * 64 + q8 * 8;
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            if (oy0 + a >= p.out_h) break;
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+              if (ox0 + w >= p.out_w) continue;
+              uint4 o;
+              o.x = Unpack2<T>::put(acc[a][w][0]); o.y = Unpack2<T>::put(acc[a][w][1]);
+              o.z = Unpack2<T>::put(acc[a][w][2]); o.w = Unpack2<T>::put(acc[a][w][3]);
+              *reinterpret_cast<uint4*>(dst + (int64_t(a) * p.out_w + w) * p.minor) = o;
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    const int64_t next = job + int64_t(FIR_TMA_STAGES) * gridDim.x;
+    if (tid == 32 && next < t.jobs) issue(next, s);
+  }
+}
+
+template <typename T, int MODE>
+static int launch_resample_mode(T* out, const CUtensorMap& map, const float* fir, const UpfirdnParams& p,
+                                const FirResampleTiling& t, int threads, size_t smem, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(fir_nhwc_resample_tma_kernel<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    attr_done = true;
+  }
+  const int64_t cap = int64_t(kNumSMs) * 2;
+  const int grid = int(t.jobs < cap ? t.jobs : cap);
+  fir_nhwc_resample_tma_kernel<T, MODE><<<grid, threads, smem, st>>>(out, map, fir, p, t);
+  return 1;
+}
+
+// returns 1 when a kernel was launched (or *status carries an error), 0 when the geometry is not covered
+template <typename T>
+static int launch_fir_nhwc_resample(T* out, const T* in, const float* fir, const UpfirdnParams& p, cudaStream_t st,
+                                    int* status) {
+  *status = TE_OK;
+  if constexpr (Is16<T>::value) {
+    const bool down2 = p.up_x == 1 && p.up_y == 1 && p.down_x == 2 && p.down_y == 2;
+    const bool up2 = p.up_x == 2 && p.up_y == 2 && p.down_x == 1 && p.down_y == 1;
+    if (!(down2 || up2) || p.pad_x0 != p.pad_y0 || p.kh > 4 || p.kw > 4 || p.minor % 64 != 0) return 0;
+    FirResampleTiling t;
+    int mode;
+    if (down2) {
+      mode = 0;
+      t.tw = p.out_w >= 16 ? 16 : p.out_w;
+      t.th = 4;
+      t.box_w = 2 * t.tw + 2; t.box_h = 2 * t.th + 2;
+      t.groups_x = t.tw; t.groups_y = t.th / 2;
+      t.org_x = -p.pad_x0; t.org_y = -p.pad_y0;
+    } else {
+      const int e = p.pad_x0 & 1, m = (p.pad_x0 - e) / 2;  // pad0 = 2m + e, floor semantics for negative pads
+      mode = e == 0 ? 1 : 2;
+      t.tw = p.out_w >= 32 ? 32 : (p.out_w + 1) & ~1;
+      t.th = 8;
+      t.box_w = t.tw / 2 + 2; t.box_h = t.th / 2 + 2;
+      t.groups_x = t.tw / 2; t.groups_y = t.th / 4;
+      t.org_x = -m; t.org_y = -m;
+    }
+    const int threads = (t.groups_x * t.groups_y * 8 + 31) / 32 * 32;
+    if (threads > 256 || t.tw < 2) return 0;
+    t.tiles_x = (p.out_w + t.tw - 1) / t.tw;
+    t.tiles_y = (p.out_h + t.th - 1) / t.th;
+    t.chunks = p.minor / 64;
+    t.jobs = int64_t(p.major) * t.tiles_y * t.tiles_x * t.chunks;
+    const size_t smem = size_t(FIR_TMA_STAGES) * t.box_h * t.box_w * 128 + 128;
+    CUtensorMap map;
+    const uint64_t dims[4] = {uint64_t(p.minor), uint64_t(p.in_w), uint64_t(p.in_h), uint64_t(p.major)};
+    const uint64_t strides[3] = {uint64_t(p.minor) * 2, uint64_t(p.in_w) * p.minor * 2,
+                                 uint64_t(p.in_h) * p.in_w * p.minor * 2};
+    const uint32_t box[4] = {64, uint32_t(t.box_w), uint32_t(t.box_h), 1};
+    *status = encode_map_u16_linear(&map, in, 4, dims, strides, box);
+    if (*status != TE_OK) return 1;
+    if (mode == 0) return launch_resample_mode<T, 0>(out, map, fir, p, t, threads, smem, st);
+    if (mode == 1) return launch_resample_mode<T, 1>(out, map, fir, p, t, threads, smem, st);
+    return launch_resample_mode<T, 2>(out, map, fir, p, t, threads, smem, st);
+  } else {
+    return 0;
+  }
+}
+
 template <typename T>
 static int upfirdn2d_typed(void* out_, const void* in_, const float* fir, const UpfirdnParams& p,
                            cudaStream_t st) {
@@ -950,7 +1180,12 @@ static int upfirdn2d_typed(void* out_, const void* in_, const float* fir, const 
                       (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
   static const bool use_tma = getenv("TE_FIR_TMA") == nullptr || atoi(getenv("TE_FIR_TMA")) != 0;
   int tma_status = TE_OK;
-  if (hot_cl && use_tma && p.minor % 64 == 0 && total >= (int64_t(1) << 20) &&
+  const bool aligned16 = (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+  if (use_tma && aligned16 && p.minor > 1 && total >= (int64_t(1) << 16) &&
+      launch_fir_nhwc_resample<T>(out, in, fir, p, st, &tma_status)) {
+    // 16-bit channels-last factor-2 resampling: TMA-staged kernel launched
+    if (tma_status != TE_OK) return tma_status;
+  } else if (hot_cl && use_tma && p.minor % 64 == 0 && total >= (int64_t(1) << 20) &&
       launch_fir_nhwc_tma<T>(out, in, fir, p, st, &tma_status)) {
     // 16-bit channels-last, large: TMA-staged kernel launched (or the tensor map could not be encoded)
     if (tma_status != TE_OK) return tma_status;

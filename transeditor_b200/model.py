@@ -807,9 +807,19 @@ class ConvLayer(nn.Sequential):
         mods = list(self)
         x = input
         i = 0
+        stride1 = False
         while i < len(mods):
             m = mods[i]
             nxt = mods[i + 1] if i + 1 < len(mods) else None
+            if (isinstance(m, Blur) and isinstance(nxt, EqualConv2d) and nxt.weight.shape[2] == 1
+                    and nxt.stride == 2 and nxt.padding == 0):
+                # blur + stride-2 1x1 conv (the ResBlock skip): evaluate the FIR only where the conv reads it
+                # (upfirdn2d down=2, a quarter of the outputs) and run the 1x1 conv at stride 1; the backward
+                # becomes an up=2 FIR of the compact gradient instead of a zero-filled full-resolution one
+                x = upfirdn2d(x, m.kernel, down=2, pad=m.pad)
+                stride1 = True
+                i += 1
+                continue
             last = i + (2 if isinstance(nxt, FusedLeakyReLU) else 1) >= len(mods)
             if (isinstance(m, EqualConv2d) and isinstance(nxt, FusedLeakyReLU) and nxt.bias is not None
                     and m.bias is None and m.weight.shape[0] % 8 == 0 and nxt.negative_slope == 0.2
@@ -821,11 +831,12 @@ class ConvLayer(nn.Sequential):
                 i += 2
             elif isinstance(m, EqualConv2d) and m.bias is None and nxt is None and m.weight.shape[0] % 8 == 0:
                 wscale = m.scale * out_mul
+                stride = 1 if stride1 else m.stride
                 if residual is not None:
-                    x = tc.conv2d_residual(x, m._tc_weight(x), residual, stride=m.stride, wscale=wscale)
+                    x = tc.conv2d_residual(x, m._tc_weight(x), residual, stride=stride, wscale=wscale)
                     residual = None
                 else:
-                    x = tc.conv2d(x, m._tc_weight(x), stride=m.stride, wscale=wscale)
+                    x = tc.conv2d(x, m._tc_weight(x), stride=stride, wscale=wscale)
                 out_mul = 1.0
                 i += 1
             else:
