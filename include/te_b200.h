@@ -209,6 +209,63 @@ int te_gemm_tc_selftest(float* d, const void* a, const void* b, int m, int n, in
 int te_attn_core(float* out, float* sim_out, const float* q, const float* k, const float* v,
                  int batch, int tokens, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * The whole dual-space interaction network in ONE launch.
+ * Replaces: the `self.interact[i](x, spatialcode)` loop of Generator.forward
+ *           (model_spatial_query.py:668-679) over AttentionBlock.forward (:920-936) and
+ *           Attention.forward (:883-901): per block
+ *     xn = layer_norm(x over [16, in_dim])                       (no affine, eps 1e-5)
+ *     q = EL_q(P)  k = EL_k(xn)  v = EL_v(xn)                    (EL = EqualLinear, :194-221)
+ *     att = softmax_l(q.k * 128^-0.5) v   per head (4 x 32)      (te_attn_core's definition)
+ *     x1 = (in_dim != 512 ? EL_proj(x) : x) + EL_o(att)
+ *     x2 = x1 + EL_m2(gelu_erf(EL_m1(layer_norm(x1))))
+ *   EL(x) = x (W * lr_mul / sqrt(in))^T + b * lr_mul, W stored [out, in] row-major as the reference's parameter.
+ * 16 query tokens (P) x 16 key tokens (Z), width 512, 128 attention planes; f32 in and out.
+ * precision 0: products in 3xTF32 (error ~1e-6 relative: the fp32 parity bar holds); 1: single-pass TF32 (what
+ * cuBLAS does under allow_tf32, ~1e-3).  One thread-block CLUSTER of 8 (or 4, chosen per batch so that the
+ * samples fit the device in the fewest waves) CTAs per sample: every CTA owns 1/8 of each layer's output columns
+ * and streams only that slice of the weights; activations are exchanged through distributed shared memory.
+ *
+ * Block 0 reads x0 [B,16,blocks[0].in_dim] and p0 [B,16,blocks[0].param_dim]; blocks >= 1 read the previous
+ * block's output and p [B,16,512] (their in_dim and param_dim must be 512).  in_dim / param_dim: multiples of
+ * 16 in [64, 528].  w_proj / b_proj are required iff in_dim != 512, else NULL.  n_blocks in [1, 8].  Weight
+ * matrices (and the buffers receiving their gradients) must be 16-byte aligned.
+ */
+typedef struct te_attn_block {
+  const float* w_proj; const float* b_proj; /* [512, in_dim], [512]   (AttentionBlock.proj)        */
+  const float* w_q;    const float* b_q;    /* [128, param_dim], [128] (Attention.q_transform)     */
+  const float* w_k;    const float* b_k;    /* [128, in_dim], [128]                                */
+  const float* w_v;    const float* b_v;    /* [128, in_dim], [128]                                */
+  const float* w_o;    const float* b_o;    /* [512, 128], [512]       (Attention.proj)            */
+  const float* w_m1;   const float* b_m1;   /* [512, 512], [512]       (AttentionBlock.mlp[0])     */
+  const float* w_m2;   const float* b_m2;   /* [512, 512], [512]       (AttentionBlock.mlp[2])     */
+  int in_dim;
+  int param_dim;
+} te_attn_block;
+
+/* Sizes (in floats) of the two workspaces below for this stack and batch. */
+int te_attn_stack_workspace(const te_attn_block* blocks, int n_blocks, int batch, int64_t* save_floats,
+                            int64_t* gws_floats);
+
+/* How many clusters (= samples) of the forward / backward kernel the device holds at once
+ * (cudaOccupancyMaxActiveClusters): [0] with 8 CTAs per sample, [1] with 4.  Batches beyond that run in waves. */
+int te_attn_stack_occupancy(int fwd_clusters[2], int bwd_clusters[2]);
+
+/* y [B,16,512].  `save` (save_floats, may be NULL for inference) receives what the backward pass needs. */
+int te_attn_stack_fwd(float* y, const float* x0, const float* p0, const float* p,
+                      const te_attn_block* blocks, int n_blocks, int batch, float lr_mul, int precision,
+                      float* save, void* stream);
+
+/* First-order backward of te_attn_stack_fwd (two launches: the per-sample data-gradient chain, then one
+ * grouped weight-gradient GEMM over all B*16 rows).  gy [B,16,512] is the gradient of y.
+ * Writes (never accumulates): g_x0, g_p0 (shapes of x0, p0), g_p [B,16,512] (summed over blocks >= 1; may be
+ * NULL when n_blocks == 1), and through `grads` — the same struct with every pointer naming the OUTPUT buffer
+ * of that parameter's gradient (in_dim/param_dim ignored).  `gws` is scratch of gws_floats. */
+int te_attn_stack_bwd(float* g_x0, float* g_p0, float* g_p, const te_attn_block* grads, const float* gy,
+                      const float* x0, const float* p0, const float* p, const te_attn_block* blocks,
+                      int n_blocks, int batch, float lr_mul, int precision, const float* save, float* gws,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -148,8 +148,33 @@ def adam_ema_devstep(p, g, m, v, ema, lr, beta1, beta2, eps, step_dev, ema_decay
     adam_ema(p, g, m, v, ema, lr, beta1, beta2, eps, int(step_dev.item()), ema_decay, grad_scale)
 
 
+def attn_stack_fwd(y, x0, p0, p, blocks, batch, lr_mul, tf32, save):
+    from transeditor_b200.op import attn_stack_reference
+    with torch.no_grad():
+        y.copy_(attn_stack_reference(x0, p0, p, blocks, lr_mul))
+
+
+def attn_stack_bwd(g_x0, g_p0, g_p, grads, gy, x0, p0, p, blocks, batch, lr_mul, tf32, save, gws):
+    from transeditor_b200.op import attn_stack_reference
+    fields = [f for f in lib.ATTN_FIELDS]
+    leaf = lambda t: None if t is None else t.detach().clone().requires_grad_(True)  # noqa: E731
+    lx0, lp0, lp = leaf(x0), leaf(p0), leaf(p)
+    lblocks = [{**{f: leaf(b.get(f)) for f in fields}, "in_dim": b["in_dim"], "param_dim": b["param_dim"]}
+               for b in blocks]
+    with torch.enable_grad():
+        y = attn_stack_reference(lx0, lp0, lp, lblocks, lr_mul)
+        wanted = [(lx0, g_x0), (lp0, g_p0)] + ([(lp, g_p)] if (lp is not None and g_p is not None) else [])
+        for lb, gb in zip(lblocks, grads):
+            wanted += [(lb[f], gb[f]) for f in fields if lb[f] is not None]
+        got = torch.autograd.grad(y, [w for w, _ in wanted], gy, allow_unused=True)
+    for (_, out), g in zip(wanted, got):
+        if out is not None:
+            out.copy_(torch.zeros_like(out) if g is None else g)
+
+
 def install(monkeypatch):
     monkeypatch.setattr(lib, "require_cuda", lambda *a: None)
     for name in ("fused_bias_act", "fused_bias_act_bwd", "upfirdn2d", "conv2d_simt",
-                 "conv2d_wgrad_simt", "attn_core", "adam_ema", "adam_ema_devstep", "scale_bc", "dot_bc"):
+                 "conv2d_wgrad_simt", "attn_core", "adam_ema", "adam_ema_devstep", "scale_bc", "dot_bc",
+                 "attn_stack_fwd", "attn_stack_bwd"):
         monkeypatch.setattr(lib, name, globals()[name])

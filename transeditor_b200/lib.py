@@ -42,6 +42,15 @@ class TcConvDesc(ctypes.Structure):
                 ("act_gain", ctypes.c_float), ("wgrad_alpha", ctypes.c_float), ("residual", ctypes.c_void_p)]
 
 
+ATTN_FIELDS = ("w_proj", "b_proj", "w_q", "b_q", "w_k", "b_k", "w_v", "b_v", "w_o", "b_o", "w_m1", "b_m1",
+               "w_m2", "b_m2")
+
+
+class AttnBlock(ctypes.Structure):
+    """Mirror of te_attn_block."""
+    _fields_ = [(f, ctypes.c_void_p) for f in ATTN_FIELDS] + [("in_dim", ctypes.c_int), ("param_dim", ctypes.c_int)]
+
+
 _P, _I, _L, _F = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
 _SIGNATURES = {
     "te_version": ([], _I),
@@ -60,6 +69,11 @@ _SIGNATURES = {
     "te_conv2d_tc": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _L, _P], _I),
     "te_gemm_tc_selftest": ([_P, _P, _P, _I, _I, _I, _P], _I),
     "te_attn_core": ([_P, _P, _P, _P, _P, _I, _I, _P], _I),
+    "te_attn_stack_workspace": ([ctypes.POINTER(AttnBlock), _I, _I, ctypes.POINTER(_L), ctypes.POINTER(_L)], _I),
+    "te_attn_stack_occupancy": ([ctypes.POINTER(_I), ctypes.POINTER(_I)], _I),
+    "te_attn_stack_fwd": ([_P, _P, _P, _P, ctypes.POINTER(AttnBlock), _I, _I, _F, _I, _P, _P], _I),
+    "te_attn_stack_bwd": ([_P, _P, _P, ctypes.POINTER(AttnBlock), _P, _P, _P, _P, ctypes.POINTER(AttnBlock), _I, _I,
+                           _F, _I, _P, _P, _P], _I),
 }
 
 _lib = None
@@ -176,6 +190,52 @@ def attn_core(out, sim, q, k, v, batch, tokens):
     _check(load().te_attn_core(ptr(out), ptr(sim), ptr(q), ptr(k), ptr(v), batch, tokens, stream()),
            "attn_core")
     _count()
+
+
+def _attn_table(blocks):
+    """blocks: list of dicts {field: tensor or None for each of ATTN_FIELDS, "in_dim": int, "param_dim": int}
+    (parameters, or the buffers receiving their gradients) -> C array of te_attn_block."""
+    table = (AttnBlock * len(blocks))()
+    for entry, blk in zip(table, blocks):
+        for f in ATTN_FIELDS:
+            t = blk.get(f)
+            if t is not None:
+                if t.dtype != torch.float32 or not t.is_contiguous():
+                    raise TypeError("attn_stack: %s must be a contiguous float32 tensor" % f)
+                setattr(entry, f, t.data_ptr())
+        entry.in_dim, entry.param_dim = blk["in_dim"], blk["param_dim"]
+    return table
+
+
+def attn_stack_workspace(blocks, batch):
+    """(save_floats, gws_floats) for te_attn_stack_fwd / te_attn_stack_bwd."""
+    table = _attn_table(blocks)
+    a, b = ctypes.c_int64(0), ctypes.c_int64(0)
+    _check(load().te_attn_stack_workspace(table, len(blocks), batch, ctypes.byref(a), ctypes.byref(b)),
+           "attn_stack_workspace")
+    return a.value, b.value
+
+
+def attn_stack_occupancy():
+    """Samples resident at once on the current device: {"fwd": (8-CTA clusters, 4-CTA clusters), "bwd": (...)}."""
+    a, b = (ctypes.c_int * 2)(), (ctypes.c_int * 2)()
+    _check(load().te_attn_stack_occupancy(a, b), "attn_stack_occupancy")
+    return {"fwd": (a[0], a[1]), "bwd": (b[0], b[1])}
+
+
+def attn_stack_fwd(y, x0, p0, p, blocks, batch, lr_mul, tf32, save):
+    table = _attn_table(blocks)
+    _check(load().te_attn_stack_fwd(ptr(y), ptr(x0), ptr(p0), ptr(p), table, len(blocks), batch, lr_mul,
+                                    1 if tf32 else 0, ptr(save), stream()), "attn_stack_fwd")
+    _count()
+
+
+def attn_stack_bwd(g_x0, g_p0, g_p, grads, gy, x0, p0, p, blocks, batch, lr_mul, tf32, save, gws):
+    table, gtable = _attn_table(blocks), _attn_table(grads)
+    _check(load().te_attn_stack_bwd(ptr(g_x0), ptr(g_p0), ptr(g_p), gtable, ptr(gy), ptr(x0), ptr(p0), ptr(p), table,
+                                    len(blocks), batch, lr_mul, 1 if tf32 else 0, ptr(save), ptr(gws), stream()),
+           "attn_stack_bwd")
+    _count(2)
 
 
 def conv2d_tc(y, x, w, out_scale, bias, batch, hin, win, cin, cout, kh, kw, act, w_bstride):

@@ -540,6 +540,16 @@ class AttentionBlock(nn.Module):
         if out_dim != in_dim:
             self.proj = EqualLinear(in_dim, out_dim, lr_mul=lr_mul)
 
+    def fused_params(self):
+        """This block's parameters as te_attn_stack's table entry (include/te_b200.h: te_attn_block)."""
+        a, has_proj = self.atten, self.out_dim != self.in_dim
+        return {"w_proj": self.proj.weight if has_proj else None, "b_proj": self.proj.bias if has_proj else None,
+                "w_q": a.q_transform.weight, "b_q": a.q_transform.bias, "w_k": a.k_transform.weight,
+                "b_k": a.k_transform.bias, "w_v": a.v_transform.weight, "b_v": a.v_transform.bias,
+                "w_o": a.proj.weight, "b_o": a.proj.bias, "w_m1": self.mlp[0].weight, "b_m1": self.mlp[0].bias,
+                "w_m2": self.mlp[2].weight, "b_m2": self.mlp[2].bias, "in_dim": self.in_dim,
+                "param_dim": self.param_dim}
+
     def forward(self, x, op_param, return_similarity=False):
         normed = F.layer_norm(x, x.shape[1:])
         attention, similarity = self.atten(normed, op_param, return_similarity=True)
@@ -717,9 +727,16 @@ class Generator(nn.Module):
         spatialcode = spatialcode.permute(0, 2, 1)  # [B, 16, 512]
         if trans_interact:
             eye = self.token_spatial.repeat(stylecode.size(0), 1, 1)
-            x = self.interact[0](torch.cat([stylecode, eye], 2), torch.cat([spatialcode, eye], 2))
-            for i in range(1, self.n_trans):
-                x = self.interact[i](x, spatialcode)
+            x0, p0 = torch.cat([stylecode, eye], 2), torch.cat([spatialcode, eye], 2)
+            blocks = [blk.fused_params() for blk in self.interact]
+            if os.environ.get("TE_ATTN_STACK", "1") != "0" and op.attn_stack_supported(x0, p0, spatialcode, blocks):
+                # :668-679 in one launch (backward: two) instead of ~35 per block
+                x = op.attn_stack(x0, p0, spatialcode if self.n_trans > 1 else None, blocks, self.lr_mlp,
+                                  tf32=_PRECISION == "bf16")
+            else:
+                x = self.interact[0](x0, p0)
+                for i in range(1, self.n_trans):
+                    x = self.interact[i](x, spatialcode)
 
         if self.no_trans:
             latent = self.adjust_style(stylecode.permute(0, 2, 1)).permute(0, 2, 1)

@@ -488,6 +488,136 @@ def attn_core(q, k, v):
 
 
 # --------------------------------------------------------------------------------------------
+# the whole interaction network (all AttentionBlocks) in one launch
+
+_ATTN_FIELDS = lib.ATTN_FIELDS
+
+
+def _equal_linear(x, w, b, lr_mul):
+    """EqualLinear (model_spatial_query.py:194-221) as one addmm."""
+    x2 = x.reshape(-1, x.shape[-1])
+    out = torch.addmm(b, x2, w.t(), beta=lr_mul, alpha=lr_mul / math.sqrt(w.shape[1]))
+    return out.reshape(*x.shape[:-1], w.shape[0])
+
+
+def attn_stack_reference(x0, p0, p, blocks, lr_mul):
+    """The stack written with differentiable ops (`AttentionBlock.forward` :920-936 over `Attention.forward`
+    :883-901): what te_attn_stack_fwd computes.  Used when a gradient OF the gradient is requested (the optional
+    spatial path regulariser, train_spatial_query.py:252-277), for dtypes the kernel does not take, and as the
+    definition the tests compare the kernel with."""
+    x = x0
+    for i, w in enumerate(blocks):
+        pm = p0 if i == 0 else p
+        xn = torch.nn.functional.layer_norm(x, x.shape[1:])
+        q = _equal_linear(pm, w["w_q"], w["b_q"], lr_mul)
+        k = _equal_linear(xn, w["w_k"], w["b_k"], lr_mul)
+        v = _equal_linear(xn, w["w_v"], w["b_v"], lr_mul)
+        att, _ = attn_core(q, k, v)
+        a = _equal_linear(att, w["w_o"], w["b_o"], lr_mul)
+        x = (_equal_linear(x, w["w_proj"], w["b_proj"], lr_mul) if w.get("w_proj") is not None else x) + a
+        h = _equal_linear(torch.nn.functional.layer_norm(x, x.shape[1:]), w["w_m1"], w["b_m1"], lr_mul)
+        x = x + _equal_linear(torch.nn.functional.gelu(h), w["w_m2"], w["b_m2"], lr_mul)
+    return x
+
+
+def _blocks_from_flat(flat, dims):
+    n = len(_ATTN_FIELDS)
+    blocks = []
+    for i, (din, dp) in enumerate(dims):
+        blk = dict(zip(_ATTN_FIELDS, flat[i * n:(i + 1) * n]))
+        blk["in_dim"], blk["param_dim"] = din, dp
+        blocks.append(blk)
+    return blocks
+
+
+class AttnStack(Function):
+    """y = interact(x0, p0, p) through te_attn_stack_fwd; first-order backward through te_attn_stack_bwd (two
+    launches).  Under create_graph=True the backward is re-expressed with `attn_stack_reference`, so second-order
+    gradients exist (they are only needed by the optional spatial path regulariser)."""
+
+    @staticmethod
+    def forward(ctx, x0, p0, p, lr_mul, dims, tf32, *flat):
+        lib.require_cuda(x0, p0, p, *flat)
+        blocks = _blocks_from_flat(flat, dims)
+        batch = x0.shape[0]
+        y = torch.empty((batch, 16, 512), dtype=torch.float32, device=x0.device)
+        need = any(ctx.needs_input_grad)
+        save = None
+        if need:
+            n_save, _ = lib.attn_stack_workspace(blocks, batch)
+            save = torch.empty(n_save, dtype=torch.float32, device=x0.device)
+        lib.attn_stack_fwd(y, x0, p0, p, blocks, batch, lr_mul, tf32, save)
+        ctx.lr_mul, ctx.dims, ctx.has_p, ctx.tf32 = lr_mul, dims, p is not None, tf32
+        ctx.save_for_backward(x0, p0, p if p is not None else x0.new_empty(0), save if need else x0.new_empty(0), *flat)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x0, p0, p, save, *flat = ctx.saved_tensors
+        p = p if ctx.has_p else None
+        dims, lr_mul = ctx.dims, ctx.lr_mul
+        if torch.is_grad_enabled():  # create_graph=True: stay differentiable
+            with torch.enable_grad():
+                ins = [t for t in (x0, p0, p, *flat) if t is not None]
+                live = [t for t in ins if t.requires_grad]
+                y = attn_stack_reference(x0, p0, p, _blocks_from_flat(flat, dims), lr_mul)
+                got = dict(zip(map(id, live), torch.autograd.grad(y, live, gy, create_graph=True, allow_unused=True)))
+            pick = lambda t: None if t is None else got.get(id(t))  # noqa: E731
+            return (pick(x0), pick(p0), pick(p), None, None, None, *[pick(t) for t in flat])
+        blocks = _blocks_from_flat(flat, dims)
+        batch = x0.shape[0]
+        _, n_gws = lib.attn_stack_workspace(blocks, batch)
+        gws = torch.empty(n_gws, dtype=torch.float32, device=x0.device)
+        g_x0, g_p0 = torch.empty_like(x0), torch.empty_like(p0)
+        g_p = torch.empty_like(p) if (p is not None and len(dims) > 1) else None
+        # one buffer for all parameter gradients; the kernel writes every element
+        sizes = [0 if t is None else t.numel() for t in flat]
+        gflat = torch.empty(sum(sizes), dtype=torch.float32, device=x0.device)
+        views, off = [], 0
+        for t, n in zip(flat, sizes):
+            views.append(None if t is None else gflat[off:off + n].view(t.shape))
+            off += n
+        lib.attn_stack_bwd(g_x0, g_p0, g_p, _blocks_from_flat(views, dims), gy.contiguous(), x0, p0, p, blocks, batch,
+                           lr_mul, ctx.tf32, save, gws)
+        if p is not None and g_p is None:
+            g_p = torch.zeros_like(p)
+        return (g_x0, g_p0, g_p, None, None, None, *views)
+
+
+def attn_stack_supported(x0, p0, p, blocks):
+    """Shapes / dtypes te_attn_stack_fwd is built for (include/te_b200.h)."""
+    if x0.dtype != torch.float32 or x0.dim() != 3 or x0.shape[1] != 16 or p0.shape[1] != 16:
+        return False
+    if not 1 <= len(blocks) <= 8:
+        return False
+    for i, w in enumerate(blocks):
+        din, dp = w["in_dim"], w["param_dim"]
+        if din % 16 or dp % 16 or not (64 <= din <= 528 and 64 <= dp <= 528):
+            return False
+        if any(w[f] is not None and w[f].data_ptr() % 16 for f in _ATTN_FIELDS if f.startswith("w_")):
+            return False
+        if i > 0 and (din != 512 or dp != 512):
+            return False
+        if (w.get("w_proj") is not None) != (din != 512):
+            return False
+        if tuple(w["w_q"].shape) != (128, dp) or tuple(w["w_o"].shape) != (512, 128) or tuple(w["w_m1"].shape) != (512, 512):
+            return False
+    return x0.shape[2] == blocks[0]["in_dim"] and p0.shape[2] == blocks[0]["param_dim"] and \
+        (p is None or tuple(p.shape[1:]) == (16, 512))
+
+
+def attn_stack(x0, p0, p, blocks, lr_mul, tf32=False):
+    """blocks: list of dicts {w_proj, b_proj (None unless in_dim != 512), w_q, b_q, w_k, b_k, w_v, b_v, w_o, b_o,
+    w_m1, b_m1, w_m2, b_m2, in_dim, param_dim}.  tf32: single-pass TF32 products (the bf16 mode's choice, like
+    allow_tf32 for the library GEMMs) instead of the fp32-equivalent 3xTF32.  Returns [B, 16, 512]."""
+    flat = [w.get(f) for w in blocks for f in _ATTN_FIELDS]
+    dims = tuple((w["in_dim"], w["param_dim"]) for w in blocks)
+    # made contiguous HERE (differentiably), so that the tensors the Function saves are its own inputs
+    return AttnStack.apply(x0.contiguous(), p0.contiguous(), None if p is None else p.contiguous(), float(lr_mul),
+                           dims, bool(tf32), *flat)
+
+
+# --------------------------------------------------------------------------------------------
 # tensor-core (tcgen05) convolution, bf16 channels-last
 
 
