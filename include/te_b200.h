@@ -159,11 +159,11 @@ typedef struct {
   int w_slices;              /* slices in W (per sample when w_bstride != 0) */
   int in_stride, out_stride, out_off_y, out_off_x;
   int grid_h, grid_w;
-  int act;                   /* 0 identity, 1 leaky_relu(0.2) * act_gain */
+  int act;                   /* 0 identity, 1 leaky_relu(0.2) * act_gain, 2 leaky_relu(0.01) * act_gain (nn.LeakyReLU) */
   int out_f32;
   int64_t w_bstride;
   /* optional extras; an all-zero tail keeps the plain behaviour */
-  float act_gain;            /* gain after the leaky ReLU; 0 selects sqrt(2) (FusedLeakyReLU's scale) */
+  float act_gain;            /* gain after the leaky ReLU; 0 selects sqrt(2) (FusedLeakyReLU's scale) for act 1, 1 for act 2 */
   float wgrad_alpha;         /* te_conv_wgrad_tc accumulates wgrad_alpha * gradient; 0 selects 1 */
   const void* residual;      /* bf16 [batch, hout, wout, cout] added AFTER bias/activation (ResBlock skip sum,
                                 model_spatial_query.py:795-797), or NULL; bf16 output only */

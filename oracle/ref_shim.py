@@ -59,6 +59,30 @@ def load_reference_module():
     return mod
 
 
+def load_reference_psp_encoders():
+    """Return the reference's pSp/models/encoders/psp_encoders_new.py module (its `from model_spatial_query import
+    EqualLinear` resolved to the REFERENCE's model file, not to this repository's drop-in of the same name)."""
+    if "_te_ref_psp_encoders" in sys.modules:
+        return sys.modules["_te_ref_psp_encoders"]
+    ref_model = load_reference_module()
+    saved = {k: sys.modules.get(k) for k in ("model_spatial_query",)}
+    sys.modules["model_spatial_query"] = ref_model
+    sys.path.insert(0, REFERENCE_ROOT)
+    try:
+        mod = importlib.import_module("pSp.models.encoders.psp_encoders_new")
+    finally:
+        sys.path.remove(REFERENCE_ROOT)
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+        for k in [k for k in sys.modules if k == "pSp" or k.startswith("pSp.")]:
+            sys.modules.pop(k)
+    sys.modules["_te_ref_psp_encoders"] = mod
+    return mod
+
+
 @contextlib.contextmanager
 def cpu_mode():
     """Neutralise the hard-coded `.cuda()` calls while reference code runs on CPU."""

@@ -319,3 +319,18 @@ def test_tc_carry_sums_fanout_gradient_in_dgrad_epilogue():
     _close(gw1, gw0, "carry second-order weight grad", rel=3e-2)
     if gb0 is not None:
         _close(gb1, gb0, "carry second-order bias grad", rel=3e-2)
+
+
+@pytest.mark.parametrize("case", [(32, 512, 512, 16), (4, 512, 512, 2), (3, 64, 128, 64), (32, 512, 512, 4), (2, 128, 64, 33)])
+def test_tc_padded_stride2_with_leaky001_epilogue(case):
+    """Geometry `down1` (3x3, stride 2, padding 1) with bias + LeakyReLU(0.01) in the epilogue: the pSp heads'
+    layer (pSp/models/encoders/psp_encoders_new.py:19-26)."""
+    from transeditor_b200 import tc
+    b, cin, cout, h = case
+    x = _bf(_rand(b, cin, h, h, seed=1))
+    w = _rand(cout, cin, 3, 3, seed=2, scale=1 / math.sqrt(cin * 9))
+    bias = _rand(cout, seed=3, scale=0.3)
+    y = tc.conv_raw(x, tc.pack_weight(w, False), tc.Mode("down1", 3), bias=bias, act=2)
+    ref = F.leaky_relu(F.conv2d(x.float(), w.to(torch.bfloat16).float(), bias, stride=2, padding=1), 0.01)
+    assert y.shape == ref.shape
+    _close(y, ref, "down1 %s" % (case,))

@@ -248,10 +248,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             f[j] = a;
           }
         }
-        if (p.act == 1) {
-          const float gain = p.act_gain;
+        if (p.act != 0) {
+          const float gain = p.act_gain, slope = p.act == 2 ? 0.01f : 0.2f;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = (f[j] > 0.f ? f[j] : 0.2f * f[j]) * gain;
+          for (int j = 0; j < 32; ++j) f[j] = (f[j] > 0.f ? f[j] : slope * f[j]) * gain;
         }
         if (p.residual != nullptr && valid) {
           const uint4* rsrc = reinterpret_cast<const uint4*>(p.residual + pix * p.cout + n0 + c0);
@@ -496,10 +496,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             f[j] = a;
           }
         }
-        if (p.act == 1) {
-          const float gain = p.act_gain;
+        if (p.act != 0) {
+          const float gain = p.act_gain, slope = p.act == 2 ? 0.01f : 0.2f;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = (f[j] > 0.f ? f[j] : 0.2f * f[j]) * gain;
+          for (int j = 0; j < 32; ++j) f[j] = (f[j] > 0.f ? f[j] : slope * f[j]) * gain;
         }
         if (p.residual != nullptr && valid) {
           const uint4* rsrc = reinterpret_cast<const uint4*>(p.residual + pix * p.cout + n0 + c0);
@@ -622,7 +622,8 @@ static int conv_tc_dispatch(void* y, const void* x, const void* w, const float* 
   p.tiles_b = (d.batch + p.nb - 1) / p.nb;
   p.n_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
   p.act = d.act; p.out_scale = out_scale; p.bias = bias; p.y = y;
-  p.act_gain = d.act_gain != 0.f ? d.act_gain : 1.4142135623730951f;
+  TE_CHECK_ARG(d.act >= 0 && d.act <= 2, "conv_tc: act must be 0, 1 or 2");
+  p.act_gain = d.act_gain != 0.f ? d.act_gain : (d.act == 2 ? 1.f : 1.4142135623730951f);
   p.residual = static_cast<const __nv_bfloat16*>(d.residual);
   TE_CHECK_ARG(!(d.residual && d.out_f32), "conv_tc: a residual input needs bf16 output");
   TE_CHECK_ARG((reinterpret_cast<uintptr_t>(d.residual) & 15) == 0, "conv_tc: residual must be 16-byte aligned");

@@ -4,6 +4,7 @@ gradient of every convolution on the path, as twice-differentiable autograd Func
 Three geometries ("modes"), written for one axis (K taps, p = K // 2):
     s1    y[a]      = sum_k x[a + k - p] . Wsel[k]       stride-1 "same" convolution
     down  y[a]      = sum_k x[2a + k]    . Wsel[k]       stride-2 convolution, no padding
+    down1 y[a]      = sum_k x[2a + k - 1]. Wsel[k]       stride-2 convolution, padding 1 (inference only: the pSp heads)
     up    y[2i + k] += x[i]              . Wsel[k]       transposed stride-2 convolution (full)
 where Wsel[k] = W[k] or W[K-1-k] (`flip`) taken as [Cout, Cin] or transposed (`transposed`) slices of
 the master weight W [O, I, K, K].  The set is closed under differentiation:
@@ -39,6 +40,8 @@ class Mode:
             return Mode("s1", self.k, not self.transposed, not self.flip, in_hw)
         if self.kind == "down":
             return Mode("up", self.k, not self.transposed, self.flip, in_hw)
+        if self.kind == "down1":
+            raise NotImplementedError("the padded stride-2 geometry is forward-only")
         return Mode("down", self.k, not self.transposed, self.flip, in_hw)
 
     def output_hw(self, hin, win):
@@ -49,6 +52,8 @@ class Mode:
             return hin, win
         if self.kind == "down":
             return (hin - k) // 2 + 1, (win - k) // 2 + 1
+        if self.kind == "down1":
+            return (hin + 2 - k) // 2 + 1, (win + 2 - k) // 2 + 1
         return (hin - 1) * 2 + k, (win - 1) * 2 + k
 
     def launches(self, hin, win, hout, wout):
@@ -61,6 +66,9 @@ class Mode:
             return [(taps, 1, 1, 0, 0, hout, wout)]
         if self.kind == "down":
             taps = [(ky, kx, widx(ky, kx)) for ky in range(k) for kx in range(k)]
+            return [(taps, 2, 1, 0, 0, hout, wout)]
+        if self.kind == "down1":
+            taps = [(ky - 1, kx - 1, widx(ky, kx)) for ky in range(k) for kx in range(k)]
             return [(taps, 2, 1, 0, 0, hout, wout)]
         out = []
         for ry in (0, 1):
@@ -140,7 +148,8 @@ def _cl_bf16(x):
 
 def conv_raw(x, wp, mode, out_scale=None, bias=None, act=False, act_gain=0.0, residual=None):
     """x [B, Cin, H, W] bf16 channels-last, wp = pack_weight(...).  Returns bf16 channels-last:
-    act(conv * out_scale + bias) * act_gain + residual."""
+    act(conv * out_scale + bias) * act_gain + residual.  act: False/0, True/1 = leaky 0.2 (gain sqrt 2 by default),
+    2 = leaky 0.01 (gain 1 by default)."""
     lib.require_cuda(x, wp, out_scale, bias, residual)
     x = _cl_bf16(x)
     b, cin, hin, win = x.shape
@@ -159,7 +168,7 @@ def conv_raw(x, wp, mode, out_scale=None, bias=None, act=False, act_gain=0.0, re
     f32 = lambda t: None if t is None else t.to(torch.float32).contiguous()  # noqa: E731
     osc, bi = f32(out_scale), f32(bias)
     for launch in mode.launches(hin, win, hout, wout):
-        lib.conv_tc(y, x, wp, osc, bi, _desc(x, cout, hout, wout, launch, wp.shape[-3], 1 if act else 0,
+        lib.conv_tc(y, x, wp, osc, bi, _desc(x, cout, hout, wout, launch, wp.shape[-3], int(act),
                                              per_sample=per_sample, act_gain=act_gain, residual=residual))
     return y
 
