@@ -133,13 +133,19 @@ class KernelMeter:
             return 0.0, float((args[0].numel() + args[1].numel()) * es(args[1]))
         if name == "adam_ema":
             return 0.0, 7.0 * args[0].numel() * 4
+        if name in ("attn_stack_fwd", "attn_stack_bwd"):
+            # 16 tokens per sample through every weight matrix of the stack: 2 FLOP per weight and token forward,
+            # twice that backward (data + weight gradients); the weights are the algorithmic bytes
+            blocks, batch = (args[4], args[5]) if name == "attn_stack_fwd" else (args[8], args[9])
+            nw = sum(t.numel() for b in blocks for k, t in b.items() if k.startswith("w_") and t is not None)
+            return (2.0 if name == "attn_stack_fwd" else 4.0) * 16 * batch * nw, 4.0 * nw
         return 0.0, 0.0
 
     def install(self):
         from transeditor_b200 import lib
         for name in ("fused_bias_act", "fused_bias_act_bwd", "upfirdn2d", "conv2d_simt",
                      "conv2d_wgrad_simt", "adam_ema", "attn_core", "conv2d_tc", "conv_tc",
-                     "conv_wgrad_tc", "scale_bc", "dot_bc"):
+                     "conv_wgrad_tc", "scale_bc", "dot_bc", "attn_stack_fwd", "attn_stack_bwd"):
             fn = getattr(lib, name)
             self._saved[name] = fn
 
