@@ -196,6 +196,21 @@ int te_scale_bc(void* y, const void* x, const float* s, int64_t batch, int64_t p
 int te_dot_bc(float* out, const void* a, const void* b, int64_t batch, int64_t pixels, int channels,
               int dtype, void* stream);
 
+/* Repack a TABLE of f32 master weights [out_ch, in_ch, K, K] (K*K = taps = 1 or 9, contiguous) into te_conv_tc's bf16
+ * operand layouts in ONE launch: dst_n = [taps, out_pad, in_pad] (in_ch contiguous; the forward convolution's weights),
+ * dst_t = [taps, in_pad, out_pad] (the data gradient's), each value times `scale`; pads = channel counts rounded up to
+ * 8, never written (allocate the buffers zeroed once).  Either destination may be NULL.  `tasks` is a HOST array.
+ * Replaces the `weight * self.scale` elementwise kernel the reference runs on every forward
+ * (model_spatial_query.py:178,299) plus the layout change cuDNN does internally: done once per optimiser step. */
+typedef struct te_pack_task {
+  const float* src;
+  void* dst_n;
+  void* dst_t;
+  int out_ch, in_ch, taps;
+  float scale;
+} te_pack_task;
+int te_pack_weights_tc(const te_pack_task* tasks, int n_tasks, void* stream);
+
 /* Self-test of the tcgen05 GEMM core: D[M,N] (f32) = A[M,K] (bf16, K-major) * B[N,K]^T (bf16). */
 int te_gemm_tc_selftest(float* d, const void* a, const void* b, int m, int n, int k, void* stream);
 

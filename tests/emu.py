@@ -172,9 +172,19 @@ def attn_stack_bwd(g_x0, g_p0, g_p, grads, gy, x0, p0, p, blocks, batch, lr_mul,
             out.copy_(torch.zeros_like(out) if g is None else g)
 
 
+def pack_weights_tc(tasks):
+    for src, dst_n, dst_t, scale in tasks:
+        o, i, k, _ = src.shape
+        v = (src.detach().double() * scale).permute(2, 3, 0, 1).reshape(k * k, o, i)
+        if dst_n is not None:
+            dst_n[:, :o, :i].copy_(v.to(dst_n.dtype))
+        if dst_t is not None:
+            dst_t[:, :i, :o].copy_(v.transpose(1, 2).to(dst_t.dtype))
+
+
 def install(monkeypatch):
     monkeypatch.setattr(lib, "require_cuda", lambda *a: None)
     for name in ("fused_bias_act", "fused_bias_act_bwd", "upfirdn2d", "conv2d_simt",
                  "conv2d_wgrad_simt", "attn_core", "adam_ema", "adam_ema_devstep", "scale_bc", "dot_bc",
-                 "attn_stack_fwd", "attn_stack_bwd"):
+                 "attn_stack_fwd", "attn_stack_bwd", "pack_weights_tc"):
         monkeypatch.setattr(lib, name, globals()[name])

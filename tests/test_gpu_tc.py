@@ -334,3 +334,53 @@ def test_tc_padded_stride2_with_leaky001_epilogue(case):
     ref = F.leaky_relu(F.conv2d(x.float(), w.to(torch.bfloat16).float(), bias, stride=2, padding=1), 0.01)
     assert y.shape == ref.shape
     _close(y, ref, "down1 %s" % (case,))
+
+
+def test_pack_weights_table_matches_per_call_pack():
+    """te_pack_weights_tc (all weights of a model, both orientations, one launch) == the per-call repack."""
+    from transeditor_b200 import lib, tc
+    shapes = [(512, 512, 3), (128, 3, 1), (3, 128, 1), (520, 512, 3), (512, 513, 3), (64, 128, 3), (256, 128, 1), (40, 72, 3)]
+    tasks, want = [], []
+    for n, (o, i, k) in enumerate(shapes):
+        w = _rand(o, i, k, k, seed=n)
+        scale = 1.0 / math.sqrt(i * k * k) if n % 2 else 1.0
+        po, pi = (o + 7) // 8 * 8, (i + 7) // 8 * 8
+        dn = torch.zeros(k * k, po, pi, dtype=torch.bfloat16, device=DEV) if n != 2 else None
+        dt = torch.zeros(k * k, pi, po, dtype=torch.bfloat16, device=DEV) if n != 3 else None
+        tasks.append((w, dn, dt, scale))
+        want.append((tc.pack_weight(w, False, scale), tc.pack_weight(w, True, scale)))
+    lib.pack_weights_tc(tasks * 10)   # 80 tasks: two launches
+    for (w, dn, dt, scale), (rn, rt) in zip(tasks, want):
+        if dn is not None:
+            assert torch.equal(dn, rn), tuple(w.shape)
+        if dt is not None:
+            assert torch.equal(dt, rt), tuple(w.shape)
+
+
+def test_pack_cache_serves_registered_weights_and_tracks_changes():
+    from transeditor_b200 import tc
+    w = torch.nn.Parameter(_rand(64, 32, 3, 3, seed=1))
+    other = _rand(64, 32, 3, 3, seed=2)
+    cache = tc.PackCache()
+    cache.register([w])
+    tc.set_pack_cache(cache)
+    try:
+        a = tc.pack_weight(w, False, 0.5)
+        assert tc.pack_weight(w, False, 0.5) is a                      # served from the cache
+        assert tc.pack_weight(other, False, 0.5) is not a              # unregistered: packed per call
+        ref = a.clone()
+        with torch.no_grad():
+            w.copy_(other)                                             # torch-side change: version bump -> repacked
+        b = tc.pack_weight(w, False, 0.5)
+        assert b is a and not torch.equal(b, ref)
+        tc.set_pack_cache(None)
+        assert torch.equal(b, tc.pack_weight(other, False, 0.5))
+        tc.set_pack_cache(cache)
+        w.data.mul_(2.0)                                               # raw change (what the fused Adam does): explicit refresh
+        cache.refresh()
+        tc.set_pack_cache(None)
+        assert torch.equal(a, tc.pack_weight(w.detach(), False, 0.5))
+        t = cache.lookup(w, True, 0.5)
+        assert torch.equal(t, tc.pack_weight(w.detach(), True, 0.5))
+    finally:
+        tc.set_pack_cache(None)

@@ -136,3 +136,98 @@ extern "C" int te_dot_bc(float* out, const void* a, const void* b, int64_t batch
   set_error("dot_bc: unsupported dtype %d", dtype);
   return TE_ERR_UNSUPPORTED;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// f32 master weights [O, I, K, K] -> bf16 tap-major [K*K, Opad, Ipad] (dst_n) and/or its transpose
+// [K*K, Ipad, Opad] (dst_t), times `scale`, for a whole TABLE of weights in one launch: the operand layouts of
+// te_conv_tc for the forward convolution and for its data gradient.  One CTA moves a 32 x 32 (o, i) tile with all its
+// taps through shared memory (coalesced reads of 32*K*K consecutive floats per output channel, 64-byte writes).
+namespace te {
+
+struct PackTask {
+  const float* src;
+  __nv_bfloat16* dst_n;
+  __nv_bfloat16* dst_t;
+  int O, I, kk, opad, ipad;
+  float scale;
+  int tile0;
+};
+constexpr int PACK_MAX_TASKS = 64;
+struct PackParams {
+  PackTask t[PACK_MAX_TASKS];
+  int n_tasks, total_tiles;
+};
+
+__global__ void __launch_bounds__(256) pack_weights_kernel(const __grid_constant__ PackParams P) {
+  __shared__ float tile[32][32 * 9 + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int j = 0;
+  for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+    while (j + 1 < P.n_tasks && t >= P.t[j + 1].tile0) ++j;
+    const PackTask& T = P.t[j];
+    const int tiles_i = (T.I + 31) >> 5;
+    const int local = t - T.tile0;
+    const int o0 = (local / tiles_i) * 32, i0 = (local % tiles_i) * 32;
+    const int no = T.O - o0 < 32 ? T.O - o0 : 32, ni = T.I - i0 < 32 ? T.I - i0 : 32;
+    const int kk = T.kk, row_len = ni * kk;
+    for (int r = warp; r < no; r += 8) {
+      const float* s = T.src + (int64_t(o0 + r) * T.I + i0) * kk;
+      for (int e = lane; e < row_len; e += 32) tile[r][e] = s[e];
+    }
+    __syncthreads();
+    if (T.dst_n) {
+      for (int q = warp; q < kk * no; q += 8) {
+        const int tap = q / no, r = q - tap * no;
+        if (lane < ni)
+          T.dst_n[(int64_t(tap) * T.opad + o0 + r) * T.ipad + i0 + lane] = __float2bfloat16_rn(tile[r][lane * kk + tap] * T.scale);
+      }
+    }
+    if (T.dst_t) {
+      for (int q = warp; q < kk * ni; q += 8) {
+        const int tap = q / ni, c = q - tap * ni;
+        if (lane < no)
+          T.dst_t[(int64_t(tap) * T.ipad + i0 + c) * T.opad + o0 + lane] = __float2bfloat16_rn(tile[lane][c * kk + tap] * T.scale);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace te
+
+extern "C" int te_pack_weights_tc(const te_pack_task* tasks, int n_tasks, void* stream) {
+  using namespace te;
+  TE_CHECK_ARG(tasks || n_tasks == 0, "pack_weights_tc: null task table");
+  TE_CHECK_ARG(n_tasks >= 0, "pack_weights_tc: negative task count");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int base = 0; base < n_tasks; base += PACK_MAX_TASKS) {
+    PackParams P;
+    const int n = n_tasks - base < PACK_MAX_TASKS ? n_tasks - base : PACK_MAX_TASKS;
+    int tiles = 0;
+    for (int i = 0; i < n; ++i) {
+      const te_pack_task& s = tasks[base + i];
+      TE_CHECK_ARG(s.src && (s.dst_n || s.dst_t), "pack_weights_tc: task %d has a null pointer", base + i);
+      TE_CHECK_ARG(s.out_ch > 0 && s.in_ch > 0 && (s.taps == 1 || s.taps == 9),
+                   "pack_weights_tc: task %d: need positive channel counts and 1 or 9 taps", base + i);
+      PackTask& t = P.t[i];
+      t.src = s.src;
+      t.dst_n = static_cast<__nv_bfloat16*>(s.dst_n);
+      t.dst_t = static_cast<__nv_bfloat16*>(s.dst_t);
+      t.O = s.out_ch;
+      t.I = s.in_ch;
+      t.kk = s.taps;
+      t.opad = (s.out_ch + 7) / 8 * 8;
+      t.ipad = (s.in_ch + 7) / 8 * 8;
+      t.scale = s.scale;
+      t.tile0 = tiles;
+      tiles += ((s.out_ch + 31) / 32) * ((s.in_ch + 31) / 32);
+    }
+    P.n_tasks = n;
+    P.total_tiles = tiles;
+    if (tiles == 0) continue;
+    const int grid = tiles < 8 * kNumSMs ? tiles : 8 * kNumSMs;
+    pack_weights_kernel<<<grid, 256, 0, st>>>(P);
+    TE_CHECK_LAUNCH();
+  }
+  return TE_OK;
+}

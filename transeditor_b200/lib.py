@@ -51,6 +51,12 @@ class AttnBlock(ctypes.Structure):
     _fields_ = [(f, ctypes.c_void_p) for f in ATTN_FIELDS] + [("in_dim", ctypes.c_int), ("param_dim", ctypes.c_int)]
 
 
+class PackTask(ctypes.Structure):
+    """Mirror of te_pack_task."""
+    _fields_ = [("src", ctypes.c_void_p), ("dst_n", ctypes.c_void_p), ("dst_t", ctypes.c_void_p),
+                ("out_ch", ctypes.c_int), ("in_ch", ctypes.c_int), ("taps", ctypes.c_int), ("scale", ctypes.c_float)]
+
+
 _P, _I, _L, _F = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
 _SIGNATURES = {
     "te_version": ([], _I),
@@ -69,6 +75,7 @@ _SIGNATURES = {
     "te_conv2d_tc": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _L, _P], _I),
     "te_gemm_tc_selftest": ([_P, _P, _P, _I, _I, _I, _P], _I),
     "te_attn_core": ([_P, _P, _P, _P, _P, _I, _I, _P], _I),
+    "te_pack_weights_tc": ([ctypes.POINTER(PackTask), _I, _P], _I),
     "te_attn_stack_workspace": ([ctypes.POINTER(AttnBlock), _I, _I, ctypes.POINTER(_L), ctypes.POINTER(_L)], _I),
     "te_attn_stack_occupancy": ([ctypes.POINTER(_I), ctypes.POINTER(_I)], _I),
     "te_attn_stack_fwd": ([_P, _P, _P, _P, ctypes.POINTER(AttnBlock), _I, _I, _F, _I, _P, _P], _I),
@@ -190,6 +197,25 @@ def attn_core(out, sim, q, k, v, batch, tokens):
     _check(load().te_attn_core(ptr(out), ptr(sim), ptr(q), ptr(k), ptr(v), batch, tokens, stream()),
            "attn_core")
     _count()
+
+
+def pack_weights_tc(tasks):
+    """tasks: list of (src f32 [O, I, K, K] contiguous, dst_n bf16 or None, dst_t bf16 or None, scale)."""
+    if not tasks:
+        return
+    table = (PackTask * len(tasks))()
+    for e, (src, dst_n, dst_t, scale) in zip(table, tasks):
+        if src.dtype != torch.float32 or not src.is_contiguous() or src.dim() != 4 or src.shape[2] != src.shape[3]:
+            raise TypeError("pack_weights_tc: source must be a contiguous float32 [O, I, K, K] tensor")
+        for d in (dst_n, dst_t):
+            if d is not None and (d.dtype != torch.bfloat16 or not d.is_contiguous()):
+                raise TypeError("pack_weights_tc: destinations must be contiguous bfloat16 tensors")
+        e.src = src.data_ptr()
+        e.dst_n = None if dst_n is None else dst_n.data_ptr()
+        e.dst_t = None if dst_t is None else dst_t.data_ptr()
+        e.out_ch, e.in_ch, e.taps, e.scale = src.shape[0], src.shape[1], src.shape[2] * src.shape[3], scale
+    _check(load().te_pack_weights_tc(table, len(tasks), stream()), "pack_weights_tc")
+    _count((len(tasks) + 63) // 64)
 
 
 def _attn_table(blocks):

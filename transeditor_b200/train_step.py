@@ -19,7 +19,7 @@ import torch
 import torch.distributed as dist
 import torch.nn.functional as F
 
-from . import lib
+from . import lib, tc
 from .model import Discriminator, Generator
 
 
@@ -211,6 +211,15 @@ class Trainer:
         self.use_graphs = False
         self._graphs = {}
         self._real = None  # static input buffer (graph replays read from it)
+        # bf16 route: tap-major bf16 copies of the shared conv weights, re-packed once per optimiser step
+        self._packs = tc.PackCache()
+        self._packs.register(p for _, p in self.g_flat.params + self.d_flat.params)
+        tc.set_pack_cache(self._packs)
+
+    def _step_optim(self, flat, optim, n_groups):
+        optim.step(n_groups, grad_scale=1.0 / self.world)
+        lo = flat.data.data_ptr()
+        self._packs.refresh(lo, lo + flat.data.numel() * flat.data.element_size())
 
     # ------------------------------------------------------------------ CUDA graphs
     def enable_graphs(self, flag=True):
@@ -233,7 +242,7 @@ class Trainer:
                 fwdbwd()
             gb = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gb):
-                optim.step(n_groups, grad_scale=1.0 / self.world)
+                self._step_optim(flat, optim, n_groups)
             entry = (ga, gb, lib.launch_count - n0)
             self._graphs[name] = entry
         ga, gb, launches = entry
@@ -253,7 +262,7 @@ class Trainer:
     def _reduce_and_step(self, flat, optim, n_groups):
         if self.world > 1:
             dist.all_reduce(flat.grad, op=dist.ReduceOp.SUM)
-        optim.step(n_groups, grad_scale=1.0 / self.world)
+        self._step_optim(flat, optim, n_groups)
 
     def _d_fwdbwd(self):
         _set_requires_grad(self.g_flat, False)
