@@ -159,7 +159,7 @@ typedef struct {
   int w_slices;              /* slices in W (per sample when w_bstride != 0) */
   int in_stride, out_stride, out_off_y, out_off_x;
   int grid_h, grid_w;
-  int act;                   /* 0 identity, 1 leaky_relu(0.2) * act_gain, 2 leaky_relu(0.01) * act_gain (nn.LeakyReLU) */
+  int act;                   /* 0 identity, 1 leaky_relu(0.2) * act_gain, 2 leaky_relu(0.01) * act_gain (nn.LeakyReLU), 3 PReLU(slope[c]) */
   int out_f32;
   int64_t w_bstride;
   /* optional extras; an all-zero tail keeps the plain behaviour */
@@ -167,6 +167,7 @@ typedef struct {
   float wgrad_alpha;         /* te_conv_wgrad_tc accumulates wgrad_alpha * gradient; 0 selects 1 */
   const void* residual;      /* bf16 [batch, hout, wout, cout] added AFTER bias/activation (ResBlock skip sum,
                                 model_spatial_query.py:795-797), or NULL; bf16 output only */
+  const void* slope;         /* act 3: FLOAT32 [cout] negative slopes (nn.PReLU of the pSp trunk, helpers.py:90,112) */
 } te_tc_conv_desc;
 
 int te_conv_tc(void* y, const void* x, const void* w, const float* out_scale, const float* bias,

@@ -384,3 +384,18 @@ def test_pack_cache_serves_registered_weights_and_tracks_changes():
         assert torch.equal(t, tc.pack_weight(w.detach(), True, 0.5))
     finally:
         tc.set_pack_cache(None)
+
+
+@pytest.mark.parametrize("case", [(4, 64, 64, 32, "s1", 3), (2, 128, 256, 16, "down1", 3), (3, 64, 128, 16, "down", 1), (2, 512, 512, 8, "s1", 3)])
+def test_tc_prelu_epilogue(case):
+    """act=3: per-channel PReLU slopes in the epilogue (the pSp trunk's conv + PReLU, helpers.py:87-91)."""
+    from transeditor_b200 import tc
+    b, cin, cout, h, kind, k = case
+    x = _bf(_rand(b, cin, h, h, seed=1))
+    w = _rand(cout, cin, k, k, seed=2, scale=1 / math.sqrt(cin * k * k))
+    slope = torch.rand(cout, generator=torch.Generator().manual_seed(3)).to(DEV) * 0.5
+    y = tc.conv_raw(x, tc.pack_weight(w, False), tc.Mode(kind, k), act=3, slope=slope)
+    stride, pad = {"s1": (1, k // 2), "down1": (2, 1), "down": (2, 0)}[kind]
+    ref = F.prelu(F.conv2d(x.float(), w.to(torch.bfloat16).float(), stride=stride, padding=pad), slope)
+    assert y.shape == ref.shape
+    _close(y, ref, "prelu %s" % (case,))

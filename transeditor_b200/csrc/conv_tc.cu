@@ -48,6 +48,7 @@ struct TcParams {
   int act;
   float act_gain;
   const __nv_bfloat16* residual;  // [B, hout, wout, cout] added after the activation, or null
+  const float* slope;      // act 3 (PReLU): negative slope per output channel [cout]
   int debug;               // TE_TC_DEBUG bits (profiling aid): 1 no stores, 2 no epilogue work, 4 no MMAs
   const float* out_scale;  // [B, cout] or null
   const float* bias;       // [cout] or null
@@ -248,7 +249,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             f[j] = a;
           }
         }
-        if (p.act != 0) {
+        if (p.act == 3) {  // PReLU: one slope per output channel (inference side path: plain cached loads)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = n0 + c0 + j;
+            if (f[j] < 0.f && n < p.cout) f[j] *= __ldg(p.slope + n);
+          }
+        } else if (p.act != 0) {
           const float gain = p.act_gain, slope = p.act == 2 ? 0.01f : 0.2f;
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = (f[j] > 0.f ? f[j] : slope * f[j]) * gain;
@@ -496,7 +503,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             f[j] = a;
           }
         }
-        if (p.act != 0) {
+        if (p.act == 3) {  // PReLU: one slope per output channel (inference side path: plain cached loads)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = n0 + c0 + j;
+            if (f[j] < 0.f && n < p.cout) f[j] *= __ldg(p.slope + n);
+          }
+        } else if (p.act != 0) {
           const float gain = p.act_gain, slope = p.act == 2 ? 0.01f : 0.2f;
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = (f[j] > 0.f ? f[j] : slope * f[j]) * gain;
@@ -622,7 +635,9 @@ static int conv_tc_dispatch(void* y, const void* x, const void* w, const float* 
   p.tiles_b = (d.batch + p.nb - 1) / p.nb;
   p.n_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
   p.act = d.act; p.out_scale = out_scale; p.bias = bias; p.y = y;
-  TE_CHECK_ARG(d.act >= 0 && d.act <= 2, "conv_tc: act must be 0, 1 or 2");
+  TE_CHECK_ARG(d.act >= 0 && d.act <= 3, "conv_tc: act must be 0, 1, 2 or 3");
+  TE_CHECK_ARG(d.act != 3 || d.slope != nullptr, "conv_tc: act 3 (PReLU) needs the per-channel slopes");
+  p.slope = static_cast<const float*>(d.slope);
   p.act_gain = d.act_gain != 0.f ? d.act_gain : (d.act == 2 ? 1.f : 1.4142135623730951f);
   p.residual = static_cast<const __nv_bfloat16*>(d.residual);
   TE_CHECK_ARG(!(d.residual && d.out_f32), "conv_tc: a residual input needs bf16 output");
@@ -695,7 +710,7 @@ static void same_conv_desc(te_tc_conv_desc& d, int batch, int h, int wd, int cin
   d.w_slices = kh * kw;
   d.in_stride = 1; d.out_stride = 1; d.out_off_y = 0; d.out_off_x = 0;
   d.grid_h = h; d.grid_w = wd; d.act = act; d.out_f32 = out_f32; d.w_bstride = w_bstride;
-  d.act_gain = 0.f; d.wgrad_alpha = 0.f; d.residual = nullptr;
+  d.act_gain = 0.f; d.wgrad_alpha = 0.f; d.residual = nullptr; d.slope = nullptr;
 }
 
 }  // namespace te

@@ -9,12 +9,15 @@ checkpoints — keys `encoder.*` / `decoder.*` — load unchanged):
   pSp/models/psp_new.py:90-131                 pSp.forward / only_decode (encode, add the average code, decode, pool)
   dual_space_encoder.py:12-33                  DualSpaceEncoder.encode / decode
 
-The encoder's arithmetic is stock PyTorch convolutions (cuDNN: library code, as SURVEY.md §8d config 5 states);
-what this file adds for B200 is the shape of the work:
+SURVEY.md §8d lists the encoder of config 5 as stock PyTorch; the module classes here are exactly that (any device,
+any dtype).  `FusedEncoder` is the B200 inference form:
   * the 30 heads (16 spatial, 3/4/7 style per pyramid level) are 142 stride-2 3x3 convolutions 512 -> 512 — 44 % of
     the encoder's FLOPs: in bf16 they run on this package's tcgen05 convolution kernel (bias + LeakyReLU in the
     epilogue), and each group's EqualLinears are one batched product;
-  * eval-mode batch norms that follow a convolution are folded into it; bf16 channels-last activations;
+  * the IR-SE50 trunk's 3x3 and strided 1x1 convolutions run on the same kernel, per-channel PReLU and the folded
+    batch-norm shift in its epilogue (eval-mode batch norms that FOLLOW a convolution are folded into it; the one in
+    front of conv1 stays a fused multiply-add because zero padding comes after it); bf16 channels-last activations;
+    stem, lateral 1x1 layers and squeeze-excite gates are library / elementwise calls;
   * encoder + generator are captured into one CUDA graph for fixed shapes (`InversionPipeline`).
 The generator half runs on this package's own kernels (bf16 tcgen05 route).
 """
@@ -222,7 +225,17 @@ class FusedEncoder:
         if enc.training:
             raise RuntimeError("FusedEncoder needs the encoder in eval mode (batch norms are folded)")
         self.dtype = dtype
+        dev = enc.input_layer[0].weight.device
+        # bf16 on a CUDA device: the trunk's 3x3 / strided 1x1 convolutions run on the tcgen05 kernel too (PReLU and
+        # the folded batch-norm shift in its epilogue); the 3-channel stem, the two lateral 1x1 layers and the
+        # squeeze-excite arithmetic stay library / elementwise calls
+        self.use_tc = dtype == torch.bfloat16 and dev.type == "cuda"
         cl = lambda w: w.to(dtype).contiguous(memory_format=torch.channels_last)  # noqa: E731
+        if self.use_tc:
+            from . import tc
+            conv_w = lambda w: tc.pack_weight(w.detach(), False)  # noqa: E731
+        else:
+            conv_w = lambda w: cl(w.detach())  # noqa: E731
         with torch.no_grad():
             w, b = _fold_bn(enc.input_layer[0].weight, enc.input_layer[1])
             self.stem = (cl(w), b.to(dtype), enc.input_layer[2].weight.detach().to(dtype))
@@ -234,13 +247,15 @@ class FusedEncoder:
                 w2, b2 = _fold_bn(r[3].weight, r[4])
                 unit = {"bn1_scale": inv1.to(dtype).view(1, -1, 1, 1),
                         "bn1_shift": (bn1.bias - bn1.running_mean * inv1).to(dtype).view(1, -1, 1, 1),
-                        "w1": cl(r[1].weight.detach()), "prelu": r[2].weight.detach().to(dtype),
-                        "w2": cl(w2), "b2": b2.to(dtype), "stride": r[3].stride[0], "se": None, "short": None}
+                        "w1": conv_w(r[1].weight),
+                        "prelu": r[2].weight.detach().float().contiguous() if self.use_tc else r[2].weight.detach().to(dtype),
+                        "w2": conv_w(w2), "b2": b2.float().contiguous() if self.use_tc else b2.to(dtype),
+                        "stride": r[3].stride[0], "se": None, "short": None}
                 if len(r) > 5:
                     unit["se"] = (cl(r[5].fc1.weight.detach()), cl(r[5].fc2.weight.detach()))
                 if isinstance(u.shortcut_layer, nn.Sequential):
                     ws, bs = _fold_bn(u.shortcut_layer[0].weight, u.shortcut_layer[1])
-                    unit["short"] = (cl(ws), bs.to(dtype))
+                    unit["short"] = (conv_w(ws), bs.float().contiguous() if self.use_tc else bs.to(dtype))
                 self.units.append(unit)
             self.lat1 = (cl(enc.latlayer1.weight.detach()), enc.latlayer1.bias.detach().to(dtype))
             self.lat2 = (cl(enc.latlayer2.weight.detach()), enc.latlayer2.bias.detach().to(dtype))
@@ -254,14 +269,23 @@ class FusedEncoder:
 
     def _unit(self, x, u):
         s = u["stride"]
-        if u["short"] is not None:
-            short = F.conv2d(x, u["short"][0], u["short"][1], stride=s)
-        else:
-            short = x if s == 1 else x[:, :, ::s, ::s]      # MaxPool2d(1, stride) == strided sampling
         # the batch norm in FRONT of conv1 cannot be folded (zero padding follows it): one fused multiply-add
         r = torch.addcmul(u["bn1_shift"], x, u["bn1_scale"])
-        r = F.prelu(F.conv2d(r, u["w1"], None, stride=1, padding=1), u["prelu"])
-        r = F.conv2d(r, u["w2"], u["b2"], stride=s, padding=1)
+        if self.use_tc:
+            from . import tc
+            if u["short"] is not None:
+                short = tc.conv_raw(x, u["short"][0], tc.Mode("down" if s == 2 else "s1", 1), bias=u["short"][1])
+            else:
+                short = x if s == 1 else x[:, :, ::s, ::s]
+            r = tc.conv_raw(r, u["w1"], tc.Mode("s1", 3), act=3, slope=u["prelu"])
+            r = tc.conv_raw(r, u["w2"], tc.Mode("down1" if s == 2 else "s1", 3), bias=u["b2"])
+        else:
+            if u["short"] is not None:
+                short = F.conv2d(x, u["short"][0], u["short"][1], stride=s)
+            else:
+                short = x if s == 1 else x[:, :, ::s, ::s]      # MaxPool2d(1, stride) == strided sampling
+            r = F.prelu(F.conv2d(r, u["w1"], None, stride=1, padding=1), u["prelu"])
+            r = F.conv2d(r, u["w2"], u["b2"], stride=s, padding=1)
         if u["se"] is not None:
             g = torch.sigmoid(F.conv2d(F.relu(F.conv2d(r.mean((2, 3), keepdim=True), u["se"][0])), u["se"][1]))
             return torch.addcmul(short, r, g)

@@ -39,7 +39,8 @@ class TcConvDesc(ctypes.Structure):
                 ("out_off_y", ctypes.c_int), ("out_off_x", ctypes.c_int),
                 ("grid_h", ctypes.c_int), ("grid_w", ctypes.c_int),
                 ("act", ctypes.c_int), ("out_f32", ctypes.c_int), ("w_bstride", ctypes.c_int64),
-                ("act_gain", ctypes.c_float), ("wgrad_alpha", ctypes.c_float), ("residual", ctypes.c_void_p)]
+                ("act_gain", ctypes.c_float), ("wgrad_alpha", ctypes.c_float), ("residual", ctypes.c_void_p),
+                ("slope", ctypes.c_void_p)]
 
 
 ATTN_FIELDS = ("w_proj", "b_proj", "w_q", "b_q", "w_k", "b_k", "w_v", "b_v", "w_o", "b_o", "w_m1", "b_m1",

@@ -180,7 +180,7 @@ def pack_weight(w, transposed, scale=1.0):
 
 
 def _desc(x, cout, hout, wout, launch, w_slices, act=0, out_f32=0, per_sample=False, act_gain=0.0,
-          wgrad_alpha=0.0, residual=None):
+          wgrad_alpha=0.0, residual=None, slope=None):
     taps, ist, ost, oy, ox, gh, gw = launch
     b, cin, hin, win = x.shape
     d = lib.TcConvDesc()
@@ -196,6 +196,7 @@ def _desc(x, cout, hout, wout, launch, w_slices, act=0, out_f32=0, per_sample=Fa
     d.w_bstride = w_slices * cout * cin if per_sample else 0
     d.act_gain, d.wgrad_alpha = act_gain, wgrad_alpha
     d.residual = residual.data_ptr() if residual is not None else None
+    d.slope = slope.data_ptr() if slope is not None else None
     return d
 
 
@@ -207,11 +208,15 @@ def _cl_bf16(x):
     return x.contiguous(memory_format=torch.channels_last)
 
 
-def conv_raw(x, wp, mode, out_scale=None, bias=None, act=False, act_gain=0.0, residual=None):
+def conv_raw(x, wp, mode, out_scale=None, bias=None, act=False, act_gain=0.0, residual=None, slope=None):
     """x [B, Cin, H, W] bf16 channels-last, wp = pack_weight(...).  Returns bf16 channels-last:
     act(conv * out_scale + bias) * act_gain + residual.  act: False/0, True/1 = leaky 0.2 (gain sqrt 2 by default),
-    2 = leaky 0.01 (gain 1 by default)."""
-    lib.require_cuda(x, wp, out_scale, bias, residual)
+    2 = leaky 0.01 (gain 1 by default), 3 = PReLU with the f32 per-channel `slope` [Cout]."""
+    lib.require_cuda(x, wp, out_scale, bias, residual, slope)
+    if (int(act) == 3) != (slope is not None):
+        raise RuntimeError("conv_tc: act=3 (PReLU) and `slope` go together")
+    if slope is not None:
+        slope = slope.to(torch.float32).contiguous()
     x = _cl_bf16(x)
     b, cin, hin, win = x.shape
     per_sample = wp.dim() == 4
@@ -230,7 +235,8 @@ def conv_raw(x, wp, mode, out_scale=None, bias=None, act=False, act_gain=0.0, re
     osc, bi = f32(out_scale), f32(bias)
     for launch in mode.launches(hin, win, hout, wout):
         lib.conv_tc(y, x, wp, osc, bi, _desc(x, cout, hout, wout, launch, wp.shape[-3], int(act),
-                                             per_sample=per_sample, act_gain=act_gain, residual=residual))
+                                             per_sample=per_sample, act_gain=act_gain, residual=residual,
+                                             slope=slope))
     return y
 
 
