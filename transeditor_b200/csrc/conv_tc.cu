@@ -657,7 +657,19 @@ static int conv_tc_dispatch(void* y, const void* x, const void* w, const float* 
   // the 128 B/cycle shared-memory port: every K16 step reads 4 KB of A + 4 KB of B in 64 cycles); used when
   // the layer still yields >= 1 tile per SM.
   int block_n = (d.cout % 128 == 0) ? 128 : 64;
-  if (d.cout % 256 == 0 && int64_t(p.n_tiles) * (d.cout / 256) >= kNumSMs) block_n = 256;
+  if (d.cout % 256 == 0) {
+    // waves x cost per tile: an N=256 tile does twice the work of an N=128 tile in ~1.4x the time (measured
+    // 1.67 vs 1.10 PFLOP/s at 512 channels), so it wins whenever it does not cost an extra wave of its own
+    const int64_t t256 = int64_t(p.n_tiles) * (d.cout / 256), t128 = 2 * t256;
+    const int64_t w256 = (t256 + kNumSMs - 1) / kNumSMs, w128 = (t128 + kNumSMs - 1) / kNumSMs;
+    if (t256 >= kNumSMs || 14 * w256 < 10 * w128) block_n = 256;
+  }
+  {  // TE_TC_BLOCK_N=128|256 (profiling aid): force the N tile where the layer allows it
+    static int force_n = -1;
+    if (force_n < 0) { const char* e = getenv("TE_TC_BLOCK_N"); force_n = e ? atoi(e) : 0; }
+    if (force_n == 256 && d.cout % 256 == 0) block_n = 256;
+    if (force_n == 128 && d.cout % 128 == 0) block_n = 128;
+  }
 
   // 2-CTA pairs (cta_group::2) when the layer has enough tiles and, for per-sample weights, both tiles of
   // a pair always belong to one sample.  TE_TC_2CTA=0 forces the single-CTA kernel.
