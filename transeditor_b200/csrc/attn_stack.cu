@@ -172,46 +172,55 @@ __device__ __forceinline__ void gemm16_impl(const float* __restrict__ A, int lda
 
   const int ntiles = N >> 3;
   const int mine = (ntiles - rank + CL - 1) / CL;
-  for (int c0 = 0; c0 < mine; c0 += CH) {
-    constexpr int TB = KS == 3 ? 2 : 4;  // tiles whose weights are in flight together (register budget)
+  constexpr int TB = KS == 3 ? 2 : 4;  // tiles whose weights are in flight together (register budget)
+  float4 bw[TB][KS];
+  // weights of tiles i0 .. i0+TB-1 of the chunk at c0 (this warp's share) -> registers
+  auto load_b = [&](int c0, int i0) {
 #pragma unroll
-    for (int i0 = 0; i0 < 4; i0 += TB) {
-      float4 bw[TB][KS];
+    for (int i = 0; i < TB; ++i) {
+      const int li = c0 + tw + TW * (i0 + i);
+      const int n = (rank + CL * li) * 8 + g;
 #pragma unroll
-      for (int i = 0; i < TB; ++i) {
-        const int li = c0 + tw + TW * (i0 + i);
-        const int n = (rank + CL * li) * 8 + g;
-#pragma unroll
-        for (int j = 0; j < KS; ++j) {
-          const int s = kw + KW * j;
-          bw[i][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (li < mine && s < k16) {
-            if constexpr (KCONTIG) {
-              bw[i][j] = __ldg(reinterpret_cast<const float4*>(W + n * ld + 16 * s + 4 * t));
-            } else {
-              const float* wp = W + (16 * s + 4 * t) * ld + n;
-              bw[i][j] = make_float4(__ldg(wp), __ldg(wp + ld), __ldg(wp + 2 * ld), __ldg(wp + 3 * ld));
-            }
+      for (int j = 0; j < KS; ++j) {
+        const int s = kw + KW * j;
+        bw[i][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (li < mine && s < k16) {
+          if constexpr (KCONTIG) {
+            bw[i][j] = __ldg(reinterpret_cast<const float4*>(W + n * ld + 16 * s + 4 * t));
+          } else {
+            const float* wp = W + (16 * s + 4 * t) * ld + n;
+            bw[i][j] = make_float4(__ldg(wp), __ldg(wp + ld), __ldg(wp + 2 * ld), __ldg(wp + 3 * ld));
           }
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < TB; ++i) {
-        const int ti = tw + TW * (i0 + i);
-        if (c0 + ti < mine) {
-          float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-          for (int j = 0; j < KS; ++j) {
-            if (kw + KW * j < k16) {
-              mma_step<X3>(acc, af[j], 0, bw[i][j].x, bw[i][j].y);
-              mma_step<X3>(acc, af[j], 1, bw[i][j].z, bw[i][j].w);
-            }
-          }
-          *reinterpret_cast<float4*>(part + (kw * CH + ti) * 128 + lane * 4) =
-              make_float4(acc[0], acc[1], acc[2], acc[3]);
         }
       }
     }
+  };
+  auto mma_b = [&](int c0, int i0) {
+#pragma unroll
+    for (int i = 0; i < TB; ++i) {
+      const int ti = tw + TW * (i0 + i);
+      if (c0 + ti < mine) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < KS; ++j) {
+          if (kw + KW * j < k16) {
+            mma_step<X3>(acc, af[j], 0, bw[i][j].x, bw[i][j].y);
+            mma_step<X3>(acc, af[j], 1, bw[i][j].z, bw[i][j].w);
+          }
+        }
+        *reinterpret_cast<float4*>(part + (kw * CH + ti) * 128 + lane * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      }
+    }
+  };
+  if (mine > 0) load_b(0, 0);
+  for (int c0 = 0; c0 < mine; c0 += CH) {
+#pragma unroll
+    for (int i0 = 0; i0 < 4; i0 += TB) {
+      if (i0 > 0) load_b(c0, i0);
+      mma_b(c0, i0);
+    }
+    // the NEXT chunk's weights travel while this chunk is reduced and its epilogue runs (its registers are free now)
+    if (c0 + CH < mine) load_b(c0 + CH, 0);
     __syncthreads();
     const int nvalid = mine - c0 < CH ? mine - c0 : CH;
     for (int idx = threadIdx.x; idx < nvalid * 64; idx += AS_NT) {
@@ -389,7 +398,8 @@ __device__ __forceinline__ float gelu_erf_grad(float u) {
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-constexpr int AS_FWD_SMEM = (4 * AS_WIDE + AS_PART + 64) * 4;
+constexpr int AS_NBIAS = 3 * AS_PL + 4 * AS_C;  // b_q | b_k | b_v | b_o | b_m1 | b_m2 | b_proj of one block
+constexpr int AS_FWD_SMEM = (4 * AS_WIDE + AS_PART + 64 + AS_NBIAS) * 4;
 
 template <int CL, bool X3>
 __global__ void __launch_bounds__(AS_NT, 1) attn_stack_fwd_kernel(const __grid_constant__ AsParams P) {
@@ -403,11 +413,19 @@ __global__ void __launch_bounds__(AS_NT, 1) attn_stack_fwd_kernel(const __grid_c
   float* HB = X1 + AS_WIDE;      // gelu(mlp[0]); q | k | v | att live here before it
   float* PART = HB + AS_WIDE;
   float* RED = PART + AS_PART;
+  float* BIAS = RED + 64;        // this block's biases times lr_mul (fetched while the first layer norm runs)
   float* Qs = HB;
   float* Ks = Qs + AS_NARROW;
   float* Vs = Ks + AS_NARROW;
   float* ATT = Vs + AS_NARROW;
   const float lr = P.lr_mul;
+  const float* Bq = BIAS;
+  const float* Bk = Bq + AS_PL;
+  const float* Bv = Bk + AS_PL;
+  const float* Bo = Bv + AS_PL;
+  const float* Bm1 = Bo + AS_C;
+  const float* Bm2 = Bm1 + AS_C;
+  const float* Bp = Bm2 + AS_C;
 
   load_sample(X, AS_LD, P.x0 + int64_t(b) * AS_T * P.blk[0].in_dim, P.blk[0].in_dim);
   __syncthreads();
@@ -425,8 +443,30 @@ __global__ void __launch_bounds__(AS_NT, 1) attn_stack_fwd_kernel(const __grid_c
     const float s_in = lr * rsqrtf(float(din)), s_p = lr * rsqrtf(float(dp));
     const float s_pl = lr * rsqrtf(float(AS_PL)), s_c = lr * rsqrtf(float(AS_C));
 
+    // ---- biases: loads issued now, parked in shared memory after the layer norm (their L2 round trip is hidden)
+    constexpr int NB_PER = (AS_NBIAS + AS_NT - 1) / AS_NT;
+    float bias_reg[NB_PER];
+#pragma unroll
+    for (int j = 0; j < NB_PER; ++j) {
+      const int e = threadIdx.x + j * AS_NT;
+      const float* src = nullptr;
+      if (e < AS_PL) src = W.b_q + e;
+      else if (e < 2 * AS_PL) src = W.b_k + (e - AS_PL);
+      else if (e < 3 * AS_PL) src = W.b_v + (e - 2 * AS_PL);
+      else if (e < 3 * AS_PL + AS_C) src = W.b_o + (e - 3 * AS_PL);
+      else if (e < 3 * AS_PL + 2 * AS_C) src = W.b_m1 + (e - 3 * AS_PL - AS_C);
+      else if (e < 3 * AS_PL + 3 * AS_C) src = W.b_m2 + (e - 3 * AS_PL - 2 * AS_C);
+      else if (e < AS_NBIAS && has_proj) src = W.b_proj + (e - 3 * AS_PL - 3 * AS_C);
+      bias_reg[j] = src ? __ldg(src) * lr : 0.f;
+    }
+
     // ---- layer norm of the block input
     const float rstd0 = layer_norm_sample(X, XN, din, RED);
+#pragma unroll
+    for (int j = 0; j < NB_PER; ++j) {
+      const int e = threadIdx.x + j * AS_NT;
+      if (e < AS_NBIAS) BIAS[e] = bias_reg[j];
+    }
     __syncthreads();
     if (sv) {
       store_rows<CL>(sv + so.xn + row0 * din, XN, AS_LD, din, rank);
@@ -435,13 +475,13 @@ __global__ void __launch_bounds__(AS_NT, 1) attn_stack_fwd_kernel(const __grid_c
 
     // ---- q from the P tokens, k and v from the normalised Z tokens -> all CTAs
     gemm16<CL, X3, true>(Pm, dp, W.w_q, dp, dp, AS_PL, rank, PART, [&](int row, int col, float v0, float v1, int) {
-      bcast2<CL>(cl, Qs, row * AS_LDS + col, v0 * s_p + W.b_q[col] * lr, v1 * s_p + W.b_q[col + 1] * lr);
+      bcast2<CL>(cl, Qs, row * AS_LDS + col, v0 * s_p + Bq[col], v1 * s_p + Bq[col + 1]);
     });
     gemm16<CL, X3, true>(XN, AS_LD, W.w_k, din, din, AS_PL, rank, PART, [&](int row, int col, float v0, float v1, int) {
-      bcast2<CL>(cl, Ks, row * AS_LDS + col, v0 * s_in + W.b_k[col] * lr, v1 * s_in + W.b_k[col + 1] * lr);
+      bcast2<CL>(cl, Ks, row * AS_LDS + col, v0 * s_in + Bk[col], v1 * s_in + Bk[col + 1]);
     });
     gemm16<CL, X3, true>(XN, AS_LD, W.w_v, din, din, AS_PL, rank, PART, [&](int row, int col, float v0, float v1, int) {
-      bcast2<CL>(cl, Vs, row * AS_LDS + col, v0 * s_in + W.b_v[col] * lr, v1 * s_in + W.b_v[col + 1] * lr);
+      bcast2<CL>(cl, Vs, row * AS_LDS + col, v0 * s_in + Bv[col], v1 * s_in + Bv[col + 1]);
     });
     cl.sync();
 
@@ -467,17 +507,17 @@ __global__ void __launch_bounds__(AS_NT, 1) attn_stack_fwd_kernel(const __grid_c
     if (has_proj) {
       gemm16<CL, X3, true>(ATT, AS_LDS, W.w_o, AS_PL, AS_PL, AS_C, rank, PART, [&](int row, int col, float v0, float v1, int) {
         *reinterpret_cast<float2*>(X1 + row * AS_LD + col) =
-            make_float2(v0 * s_pl + W.b_o[col] * lr, v1 * s_pl + W.b_o[col + 1] * lr);
+            make_float2(v0 * s_pl + Bo[col], v1 * s_pl + Bo[col + 1]);
       });
       gemm16<CL, X3, true>(X, AS_LD, W.w_proj, din, din, AS_C, rank, PART, [&](int row, int col, float v0, float v1, int) {
         const float2 a = *reinterpret_cast<const float2*>(X1 + row * AS_LD + col);
-        bcast2<CL>(cl, X1, row * AS_LD + col, v0 * s_in + W.b_proj[col] * lr + a.x,
-                   v1 * s_in + W.b_proj[col + 1] * lr + a.y);
+        bcast2<CL>(cl, X1, row * AS_LD + col, v0 * s_in + Bp[col] + a.x,
+                   v1 * s_in + Bp[col + 1] + a.y);
       });
     } else {
       gemm16<CL, X3, true>(ATT, AS_LDS, W.w_o, AS_PL, AS_PL, AS_C, rank, PART, [&](int row, int col, float v0, float v1, int) {
         const float2 x = *reinterpret_cast<const float2*>(X + row * AS_LD + col);
-        bcast2<CL>(cl, X1, row * AS_LD + col, v0 * s_pl + W.b_o[col] * lr + x.x, v1 * s_pl + W.b_o[col + 1] * lr + x.y);
+        bcast2<CL>(cl, X1, row * AS_LD + col, v0 * s_pl + Bo[col] + x.x, v1 * s_pl + Bo[col + 1] + x.y);
       });
     }
     cl.sync();
@@ -492,7 +532,7 @@ __global__ void __launch_bounds__(AS_NT, 1) attn_stack_fwd_kernel(const __grid_c
 
     // ---- h = gelu(mlp[0](ln1)) -> all CTAs
     gemm16<CL, X3, true>(XN, AS_LD, W.w_m1, AS_C, AS_C, AS_C, rank, PART, [&](int row, int col, float v0, float v1, int) {
-      const float u0 = v0 * s_c + W.b_m1[col] * lr, u1 = v1 * s_c + W.b_m1[col + 1] * lr;
+      const float u0 = v0 * s_c + Bm1[col], u1 = v1 * s_c + Bm1[col + 1];
       const float h0 = gelu_erf(u0), h1 = gelu_erf(u1);
       if (sv) {
         *reinterpret_cast<float2*>(sv + so.u + (row0 + row) * AS_C + col) = make_float2(u0, u1);
@@ -505,7 +545,7 @@ __global__ void __launch_bounds__(AS_NT, 1) attn_stack_fwd_kernel(const __grid_c
     // ---- x2 = x1 + mlp[2](h) -> next block's input in all CTAs
     gemm16<CL, X3, true>(HB, AS_LD, W.w_m2, AS_C, AS_C, AS_C, rank, PART, [&](int row, int col, float v0, float v1, int) {
       const float2 x = *reinterpret_cast<const float2*>(X1 + row * AS_LD + col);
-      const float y0 = v0 * s_c + W.b_m2[col] * lr + x.x, y1 = v1 * s_c + W.b_m2[col + 1] * lr + x.y;
+      const float y0 = v0 * s_c + Bm2[col] + x.x, y1 = v1 * s_c + Bm2[col + 1] + x.y;
       if (last) *reinterpret_cast<float2*>(P.y + (row0 + row) * AS_C + col) = make_float2(y0, y1);
       bcast2<CL>(cl, X, row * AS_LD + col, y0, y1);
     });
