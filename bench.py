@@ -162,6 +162,14 @@ class KernelMeter:
                     tag = "%s b%d cin%d cout%d grid%dx%d taps%d is%d os%d ps%d" % (
                         _name, d.batch, d.cin, d.cout, d.grid_h, d.grid_w, d.ntaps, d.in_stride, d.out_stride,
                         1 if d.w_bstride else 0)
+                elif _name in ("scale_bc", "dot_bc"):
+                    tag = "%s b%d pix%d c%d %s" % (_name, args[3], args[4], args[5], str(args[1].dtype)[6:])
+                elif _name in ("fused_bias_act", "fused_bias_act_bwd"):
+                    t = args[1] if _name == "fused_bias_act" else args[2]
+                    tag = "%s %s %s" % (_name, tuple(t.shape), str(t.dtype)[6:])
+                elif _name == "upfirdn2d":
+                    tag = "%s %s->%s up%d down%d %s" % (_name, tuple(args[1].shape), tuple(args[0].shape), args[7], args[9],
+                                                      str(args[1].dtype)[6:])
                 self.records.append((_name, e0, e1, flops, byts, tag))
             setattr(lib, name, wrapped)
 

@@ -115,3 +115,35 @@ def test_noise_injection_routes():
     zz = z.clone().requires_grad_(True)
     img_g, _, _ = g(zz, p, noise=noise)
     assert np.abs(img_g.detach().numpy() - gold["img"]).max() < 1e-3
+
+
+def test_pack_cache_host_logic(cpu_emulation):
+    """tc.PackCache (weights repacked once per optimiser step): hits only for registered whole parameters, repacks on
+    torch-side version bumps, refresh() after raw-pointer updates; emulated table-pack kernel == per-call repack."""
+    from transeditor_b200 import tc
+    g = torch.Generator().manual_seed(0)
+    w = torch.nn.Parameter(torch.randn(24, 40, 3, 3, generator=g))
+    w1 = torch.nn.Parameter(torch.randn(1, 8, 16, 1, 1, generator=g))   # ModulatedConv2d keeps a leading 1
+    cache = tc.PackCache()
+    cache.register([w, w1])
+    tc.set_pack_cache(None)
+    plain = tc.pack_weight(w.detach(), False, 0.25), tc.pack_weight(w.detach(), True, 0.25)
+    tc.set_pack_cache(cache)
+    torch.set_grad_enabled(False)   # pack_weight runs inside autograd.Function.forward in the product
+    try:
+        a, at = tc.pack_weight(w, False, 0.25), tc.pack_weight(w, True, 0.25)
+        assert torch.equal(a, plain[0]) and torch.equal(at, plain[1])
+        assert tc.pack_weight(w, False, 0.25) is a and tc.pack_weight(w[:, :8], False, 0.25) is not a
+        assert tc.pack_weight(w1[0], False, 1.0) is tc.pack_weight(w1[0], False, 1.0)
+        w.mul_(3.0)                                       # version bump -> both orientations repacked on next use
+        assert torch.equal(tc.pack_weight(w, True, 0.25).float(), (plain[1].float() * 3).to(torch.bfloat16).float()) or \
+            torch.allclose(tc.pack_weight(w, True, 0.25).float(), plain[1].float() * 3, rtol=1e-2)
+        w.data.add_(1.0)                                  # raw update, no version bump: stale until refresh()
+        lo = w.data_ptr()
+        cache.refresh(lo, lo + 1)
+        tc.set_pack_cache(None)
+        fresh = tc.pack_weight(w.detach(), False, 0.25)
+        assert torch.equal(a, fresh)
+    finally:
+        torch.set_grad_enabled(True)
+        tc.set_pack_cache(None)

@@ -1223,6 +1223,7 @@ extern "C" int te_upfirdn2d(void* out, const void* in, const float* fir, int64_t
                             int down_y, int pad_x0, int pad_x1, int pad_y0, int pad_y1, int dtype,
                             void* stream) {
   using namespace te;
+  if (major == 0) return TE_OK;  // empty batch: nothing to do (empty tensors carry null data pointers)
   TE_CHECK_ARG(out && in && fir, "upfirdn2d: null pointer");
   TE_CHECK_ARG(major >= 0 && in_h > 0 && in_w > 0 && minor > 0, "upfirdn2d: bad input shape");
   TE_CHECK_ARG(kh >= 1 && kw >= 1 && kh <= 16 && kw <= 16, "upfirdn2d: FIR must be 1..16 taps per axis");
