@@ -276,7 +276,8 @@ def cpu_train_rate(steps, warmup, batch=1, seconds_cap=None, lazy=True):
 def run_reference(args, rank):
     if rank != 0:
         return
-    rate, cores, done, dt = cpu_train_rate(args.steps, min(args.warmup, 1), batch=1)
+    # bounded: a CPU iteration takes seconds, so the timed region stops after ~2.5 minutes whatever --steps says
+    rate, cores, done, dt = cpu_train_rate(args.steps, min(args.warmup, 1), batch=1, seconds_cap=150)
     sample = ("oracle CPU port of the train loop (oracle/train_cpu.py), 256^2, batch 1 per step, "
               "%d timed steps incl. lazy R1 (i%%16==0) and path (i%%4==0), fp32, %d torch threads" % (done, cores))
     line = {"impl": "reference", "metric": METRIC, "value": round(rate, 4), "unit": UNIT,
