@@ -138,6 +138,41 @@ def golden_noise(ref):
     print("g32_noise", float(img.std()))
 
 
+def golden_spatial_path(ref):
+    """The optional spatial path regulariser (train_spatial_query.py:252-277) in both of its spaces, with an explicit
+    projection noise: path lengths and a few parameter gradients of the penalty (second order through the mapping
+    network and the cross-attention stack)."""
+    size, cm, b = 32, 2, 2
+    g, _, sdg, _ = build_models(ref, size, cm)
+    z, p = _inputs(91, b)
+    gn = torch.Generator().manual_seed(92)
+    noise = torch.randn(b, 3, size, size, generator=gn) / np.sqrt(size * size)
+    rec = {"size": size, "cm": cm, "z": z.numpy(), "p": p.numpy(), "noise": noise.numpy(), "g_checksum": _checksum(sdg)}
+    gp = dict(g.named_parameters())
+    keys = ("spatial_mapping_network.1.weight", "interact.0.atten.q_transform.weight", "interact.3.mlp.0.bias",
+            "conv1.conv.weight", "adjust_style.weight", "convs.0.conv.modulation.bias")
+    with ref_shim.cpu_mode():
+        for space in ("p", "p_plus"):
+            for q in g.parameters():
+                q.grad = None
+            if space == "p":                       # :258-265
+                target = p.clone().requires_grad_()
+                img, _, _ = g(z, target)
+            else:                                  # :266-272
+                target = g(z, p, return_only_mapped_p=True)
+                target.requires_grad_()
+                img, _, _ = g(z, target, use_spatial_mapping=False)
+            (gl,) = torch.autograd.grad((img * noise).sum(), target, create_graph=True)
+            pl = torch.sqrt(gl.pow(2).sum(2).mean(1))          # g_path_regularize, :92-105
+            (pl - 0.25).pow(2).mean().backward()
+            rec[space + ".lengths"] = pl.detach().numpy()
+            for k in keys:
+                if gp[k].grad is not None:
+                    rec[space + ".grad." + k] = _small(gp[k].grad)
+    np.savez_compressed(os.path.join(OUT, "gd32_spatial_path.npz"), **rec)
+    print("gd32_spatial_path", {k: v.shape for k, v in rec.items() if k.endswith("lengths")})
+
+
 def golden_ops():
     """Operator-level vectors.  upfirdn2d: every live parameter set with an
     ASYMMETRIC random FIR, produced by the literal kernel-index transcription
@@ -180,6 +215,7 @@ def main():
     golden_model(ref, "gd64_b2", 64, 1, 2, 21, with_grads=False)
     golden_model(ref, "gd256_b1", 256, 2, 1, 31, with_grads=False)
     golden_noise(ref)
+    golden_spatial_path(ref)
 
 
 if __name__ == "__main__":

@@ -200,3 +200,23 @@ def test_rejects_bad_tables():
         lib.attn_stack_fwd(y, x0, p0, p, bad, 2, LR, False, None)
     with pytest.raises(RuntimeError, match="n_blocks"):
         lib.attn_stack_fwd(y, x0, p0, p, bd * 5, 2, LR, False, None)
+
+
+@pytest.mark.parametrize("create_graph", [False, True])
+def test_partial_derivatives_when_arguments_depend_on_each_other(create_graph):
+    """Generator.forward passes p AND p0 = cat(p, eye): both backward routes (kernel / differentiable re-expression)
+    must return PARTIAL derivatives per argument, or the p0 path is counted twice."""
+    from transeditor_b200 import op
+    bd = _to(_blocks(3, 528, seed=5), torch.float32, DEV, grad=True)
+    g = torch.Generator().manual_seed(6)
+    q = torch.randn(2, 16, 512, generator=g).to(DEV).requires_grad_(True)
+    s = torch.randn(2, 16, 512, generator=g).to(DEV).requires_grad_(True)
+    eye = torch.eye(16, device=DEV).repeat(2, 1, 1)
+    gy = torch.randn(2, 16, 512, generator=g).to(DEV)
+
+    def run(fn):
+        y = fn(torch.cat([s, eye], 2), torch.cat([q, eye], 2), q, bd, LR)
+        return torch.autograd.grad(y, [q, s], gy, create_graph=create_graph)
+
+    for a, b in zip(run(op.attn_stack), run(op.attn_stack_reference)):
+        assert _rel(a, b) < 1e-4

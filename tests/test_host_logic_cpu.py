@@ -147,3 +147,34 @@ def test_pack_cache_host_logic(cpu_emulation):
     finally:
         torch.set_grad_enabled(True)
         tc.set_pack_cache(None)
+
+
+@pytest.mark.parametrize("space", ["p", "p_plus"])
+def test_spatial_path_regulariser_matches_reference(space):
+    """train_spatial_query.py:252-277 in both spaces: second order through the spatial mapping network, the
+    cross-attention stack (fused route: AttnStack re-expresses its backward differentiably) and the const-input
+    convolutions, against the reference's own numbers."""
+    gold = load_golden("gd32_spatial_path")
+    g, _ = _models(32, 2)
+    gp = dict(g.named_parameters())
+    z, p = torch.from_numpy(gold["z"]), torch.from_numpy(gold["p"])
+    noise = torch.from_numpy(gold["noise"])
+    if space == "p":
+        target = p.clone().requires_grad_()
+        img, _, _ = g(z, target)
+    else:
+        target = g(z, p, return_only_mapped_p=True)
+        target.requires_grad_()
+        img, _, _ = g(z, target, use_spatial_mapping=False)
+    (gl,) = torch.autograd.grad((img * noise).sum(), target, create_graph=True)
+    pl = torch.sqrt(gl.pow(2).sum(2).mean(1))
+    (pl - 0.25).pow(2).mean().backward()
+    ref = gold[space + ".lengths"]
+    assert np.abs(pl.detach().numpy() - ref).max() < 1e-3 * max(1.0, np.abs(ref).max())
+    seen = 0
+    for key, val in gold.items():
+        if key.startswith(space + ".grad."):
+            got = small(gp[key[len(space) + 6:]].grad)
+            assert np.abs(got - val).max() < 2e-3 * max(1.0, float(np.abs(val).max())), key
+            seen += 1
+    assert seen >= 4

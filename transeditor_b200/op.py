@@ -558,12 +558,18 @@ class AttnStack(Function):
         dims, lr_mul = ctx.dims, ctx.lr_mul
         if torch.is_grad_enabled():  # create_graph=True: stay differentiable
             with torch.enable_grad():
-                ins = [t for t in (x0, p0, p, *flat) if t is not None]
-                live = [t for t in ins if t.requires_grad]
-                y = attn_stack_reference(x0, p0, p, _blocks_from_flat(flat, dims), lr_mul)
+                # PARTIAL derivatives with respect to each argument are wanted, but the arguments may depend on each
+                # other in the caller's graph (Generator.forward builds p0 = cat(p, eye) from p): differentiate with
+                # respect to fresh view nodes, which no other argument descends from, and which still lead back to
+                # the originals for the second-order terms
+                alias = lambda t: None if t is None else t.view_as(t)  # noqa: E731
+                ax0, ap0, ap = alias(x0), alias(p0), alias(p)
+                aflat = [alias(t) for t in flat]
+                live = [t for t in (ax0, ap0, ap, *aflat) if t is not None and t.requires_grad]
+                y = attn_stack_reference(ax0, ap0, ap, _blocks_from_flat(aflat, dims), lr_mul)
                 got = dict(zip(map(id, live), torch.autograd.grad(y, live, gy, create_graph=True, allow_unused=True)))
             pick = lambda t: None if t is None else got.get(id(t))  # noqa: E731
-            return (pick(x0), pick(p0), pick(p), None, None, None, *[pick(t) for t in flat])
+            return (pick(ax0), pick(ap0), pick(ap), None, None, None, *[pick(t) for t in aflat])
         blocks = _blocks_from_flat(flat, dims)
         batch = x0.shape[0]
         _, n_gws = lib.attn_stack_workspace(blocks, batch)

@@ -39,6 +39,9 @@ class TrainConfig:
         self.r1 = 10.0
         self.path_regularize = 2.0
         self.path_batch_shrink = 2
+        self.spatial_regu = False            # --spatial_regu (:405): second path regulariser, on the spatial code
+        self.spatial_path_regularize = 2.0   # :388
+        self.regu_space = "p+"               # --regu_sapce (:406): "p" = raw spatial code, "p+" = mapped code
         self.d_reg_every = 16
         self.g_reg_every = 4
         self.ema_decay = 0.5 ** (32 / (10 * 1000))  # :157
@@ -206,6 +209,7 @@ class Trainer:
         self.d_optim = FlatAdam(self.d_flat, cfg.lr * d_ratio, (0 ** d_ratio, 0.99 ** d_ratio))
         torch.manual_seed(1234 + self.rank)  # per-rank latent / noise streams
         self.mean_path_length = torch.zeros((), device=self.device)
+        self.mean_spatial_path_length = torch.zeros((), device=self.device)
         self.iteration = 0
         self.losses = {}
         self.use_graphs = False
@@ -318,6 +322,33 @@ class Trainer:
         self.mean_path_length.copy_(path_mean)  # in place: a static buffer for graph replays
         self.losses.update(path=path_loss.detach(), path_length=path_lengths.mean().detach())
 
+    def _gsreg_fwdbwd(self):
+        """Spatial path regulariser (train_spatial_query.py:252-277): the path-length penalty taken with respect to
+        the spatial code — the raw p ("p") or the mapped p+ ("p+") — instead of the style latents.  Second order
+        runs through the const-input convolutions, the cross-attention stack (as queries) and, for "p", the spatial
+        mapping network."""
+        c = self.cfg
+        _set_requires_grad(self.g_flat, True)
+        _set_requires_grad(self.d_flat, False)
+        n = max(1, c.batch // c.path_batch_shrink)
+        z, p = self._latents(n)
+        if c.regu_space == "p":
+            target = p.requires_grad_()
+            fake_img, _, _ = self.generator(z, target)
+        else:
+            target = self.generator(z, p, return_only_mapped_p=True)
+            target.requires_grad_()
+            fake_img, _, _ = self.generator(z, target, use_spatial_mapping=False)
+        path_loss, path_mean, path_lengths = g_path_regularize(fake_img, target, self.mean_spatial_path_length)
+        self.g_flat.clear_grads()
+        weighted = c.spatial_path_regularize * c.g_reg_every * path_loss
+        if c.path_batch_shrink:
+            weighted = weighted + 0 * fake_img[0, 0, 0, 0]
+        weighted.backward()
+        self.g_flat.gather_grads()
+        self.mean_spatial_path_length.copy_(path_mean)
+        self.losses.update(spatial_path=path_loss.detach(), spatial_path_length=path_lengths.mean().detach())
+
     def _set_real(self, real_img):
         if real_img is self._real:
             return
@@ -341,6 +372,9 @@ class Trainer:
         # to_rgb biases get no gradient from the path penalty -> skipped like Adam skips grad=None
         self._phase("greg", self._greg_fwdbwd, self.g_flat, self.g_optim, 1)
 
+    def g_spatial_regularize(self):
+        self._phase("gsreg", self._gsreg_fwdbwd, self.g_flat, self.g_optim, 1)
+
     def ema_update(self):
         """accumulate(g_ema, g_module, 0.5 ** (32 / 10000)), train_spatial_query.py:56-61,294"""
         self.ema_flat.data.lerp_(self.g_flat.data, 1.0 - self.cfg.ema_decay)
@@ -355,6 +389,8 @@ class Trainer:
         self.g_step()
         if i % self.cfg.g_reg_every == 0:
             self.g_regularize()
+            if self.cfg.spatial_regu:
+                self.g_spatial_regularize()
         self.ema_update()
         self.iteration += 1
         return self.losses
