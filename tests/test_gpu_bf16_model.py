@@ -149,3 +149,22 @@ def test_bf16_generator_1024_batch8_inference():
         full, _, _ = g(z, p)
     assert img.shape == (8, 3, 1024, 1024) and torch.isfinite(img).all()
     assert (img - full).abs().max().item() < 1e-3 * max(1.0, full.abs().max().item())
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("space", ["p", "p+"])
+def test_trainer_with_spatial_path_regulariser(precision, space):
+    """--spatial_regu (train_spatial_query.py:252-277): the extra generator phase runs (second order through the
+    mapping network and the fused attention stack) and the bf16 route stays close to fp32."""
+    from transeditor_b200 import model as te_model
+    from transeditor_b200.train_step import TrainConfig, Trainer
+    te_model.set_precision(precision)
+    try:
+        tr = Trainer(TrainConfig(size=32, batch=4, spatial_regu=True, regu_space=space), DEV, seed=0)
+        real = (torch.rand(4, 3, 32, 32, generator=torch.Generator().manual_seed(1)) * 2 - 1).to(DEV)
+        tr.step(real)
+        assert torch.isfinite(tr.g_flat.data).all()
+        sp = float(tr.losses["spatial_path_length"])
+        assert 0.05 < sp < 0.6, sp          # fp32: 0.18 for this seed
+    finally:
+        te_model.set_precision("fp32")
