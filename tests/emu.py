@@ -172,10 +172,71 @@ def attn_stack_bwd(g_x0, g_p0, g_p, grads, gy, x0, p0, p, blocks, batch, lr_mul,
             out.copy_(torch.zeros_like(out) if g is None else g)
 
 
+def _tc_gather(x, d, dy, dx):
+    """x [B, C, Hin, Win] -> the anchors' input pixels for one tap, [B, C, grid_h, grid_w], zeros outside."""
+    iy = torch.arange(d.grid_h) * d.in_stride + dy
+    ix = torch.arange(d.grid_w) * d.in_stride + dx
+    vy, vx = (iy >= 0) & (iy < d.hin), (ix >= 0) & (ix < d.win)
+    g = x[:, :, iy.clamp(0, d.hin - 1)][:, :, :, ix.clamp(0, d.win - 1)]
+    return g * (vy[:, None] & vx[None, :]).to(g.dtype)
+
+
+def _tc_out_index(d):
+    oy = torch.arange(d.grid_h) * d.out_stride + d.out_off_y
+    ox = torch.arange(d.grid_w) * d.out_stride + d.out_off_x
+    return oy, ox
+
+
+def conv_tc(y, x, w, out_scale, bias, desc):
+    """te_conv_tc from its header contract: tap table over an anchor grid, f32 accumulation of bf16 operands, epilogue
+    out_scale / bias / activation / residual, bf16 (or f32) output written at the anchors' output positions only."""
+    d = desc
+    xf = x.float()
+    per_sample = d.w_bstride != 0
+    wf = w.float().reshape((d.batch, d.w_slices, d.cout, d.cin) if per_sample else (d.w_slices, d.cout, d.cin))
+    acc = torch.zeros(d.batch, d.cout, d.grid_h, d.grid_w)
+    for t in range(d.ntaps):
+        g = _tc_gather(xf, d, d.tap_dy[t], d.tap_dx[t])
+        if per_sample:
+            acc += torch.einsum("bchw,boc->bohw", g, wf[:, d.tap_w[t]])
+        else:
+            acc += torch.einsum("bchw,oc->bohw", g, wf[d.tap_w[t]])
+    if out_scale is not None:
+        acc = acc * out_scale.reshape(d.batch, d.cout, 1, 1)
+    if bias is not None:
+        acc = acc + bias.reshape(1, d.cout, 1, 1)
+    residual, slope = getattr(d, "py_refs", (None, None))
+    if d.act == 3:
+        acc = torch.where(acc < 0, acc * slope.reshape(1, -1, 1, 1), acc)
+    elif d.act != 0:
+        gain = d.act_gain if d.act_gain != 0 else (1.0 if d.act == 2 else 2 ** 0.5)
+        acc = F.leaky_relu(acc, 0.01 if d.act == 2 else 0.2) * gain
+    oy, ox = _tc_out_index(d)
+    if residual is not None:
+        acc = acc + residual.float()[:, :, oy][:, :, :, ox]
+    y[:, :, oy[:, None], ox[None, :]] = acc.to(y.dtype)
+
+
+def conv_wgrad_tc(gw, g, x, desc):
+    d = desc
+    alpha = d.wgrad_alpha if d.wgrad_alpha != 0 else 1.0
+    oy, ox = _tc_out_index(d)
+    ga = g.float()[:, :, oy][:, :, :, ox]                      # gradient at the anchors' output positions
+    xf = x.float()
+    per_sample = d.w_bstride != 0
+    view = gw.view((d.batch, d.w_slices, d.cout, d.cin) if per_sample else (d.w_slices, d.cout, d.cin))
+    for t in range(d.ntaps):
+        xs = _tc_gather(xf, d, d.tap_dy[t], d.tap_dx[t])
+        if per_sample:
+            view[:, d.tap_w[t]] += alpha * torch.einsum("bohw,bchw->boc", ga, xs)
+        else:
+            view[d.tap_w[t]] += alpha * torch.einsum("bohw,bchw->oc", ga, xs)
+
+
 def pack_weights_tc(tasks):
     for src, dst_n, dst_t, scale in tasks:
         o, i, k, _ = src.shape
-        v = (src.detach().double() * scale).permute(2, 3, 0, 1).reshape(k * k, o, i)
+        v = (src.detach() * scale).permute(2, 3, 0, 1).reshape(k * k, o, i)  # f32 product, like the kernel
         if dst_n is not None:
             dst_n[:, :o, :i].copy_(v.to(dst_n.dtype))
         if dst_t is not None:
@@ -186,5 +247,5 @@ def install(monkeypatch):
     monkeypatch.setattr(lib, "require_cuda", lambda *a: None)
     for name in ("fused_bias_act", "fused_bias_act_bwd", "upfirdn2d", "conv2d_simt",
                  "conv2d_wgrad_simt", "attn_core", "adam_ema", "adam_ema_devstep", "scale_bc", "dot_bc",
-                 "attn_stack_fwd", "attn_stack_bwd", "pack_weights_tc"):
+                 "attn_stack_fwd", "attn_stack_bwd", "pack_weights_tc", "conv_tc", "conv_wgrad_tc"):
         monkeypatch.setattr(lib, name, globals()[name])

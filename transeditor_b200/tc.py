@@ -197,6 +197,7 @@ def _desc(x, cout, hout, wout, launch, w_slices, act=0, out_f32=0, per_sample=Fa
     d.act_gain, d.wgrad_alpha = act_gain, wgrad_alpha
     d.residual = residual.data_ptr() if residual is not None else None
     d.slope = slope.data_ptr() if slope is not None else None
+    d.py_refs = (residual, slope)  # keeps the two tensors alive for the launch (and lets tests/emu.py read them)
     return d
 
 
