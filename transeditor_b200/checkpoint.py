@@ -103,4 +103,8 @@ def load_checkpoint(trainer, path_or_dict, strict=True):
         load_adam_state_dict(trainer.g_optim, trainer.generator, ckpt["g_optim"])
     if "d_optim" in ckpt:
         load_adam_state_dict(trainer.d_optim, trainer.discriminator, ckpt["d_optim"])
+    # captured graphs read the bf16 weight copies of the repack cache without looking at version counters
+    packs = getattr(trainer, "_packs", None)
+    if packs is not None:
+        packs.refresh()
     return ckpt

@@ -220,6 +220,12 @@ class Trainer:
         self._packs.register(p for _, p in self.g_flat.params + self.d_flat.params)
         tc.set_pack_cache(self._packs)
 
+    def weights_changed(self):
+        """Call after modifying generator / discriminator weights outside this trainer's optimiser steps
+        (load_state_dict, manual edits): re-packs the cached bf16 weight copies, which replayed CUDA graphs read
+        without consulting version counters."""
+        self._packs.refresh()
+
     def _step_optim(self, flat, optim, n_groups):
         optim.step(n_groups, grad_scale=1.0 / self.world)
         lo = flat.data.data_ptr()
