@@ -393,7 +393,10 @@ def run_ours(args, rank, local_rank, world):
                        "size": cfg.size, "num_trans": cfg.num_trans, "parallelism": "dp%d" % world,
                        "precision": ("bf16 activations / tcgen05 MMA with f32 accumulation, f32 master weights, "
                                      "f32 mapping+transformer" if args.precision == "bf16"
-                                     else "fp32 storage and arithmetic (parity mode, SIMT kernels)"),
+                                     else "fp32 storage, split-operand tcgen05 convolutions (parity mode: bf16 hi/mid "
+                                          "planes, 3 tensor-core products per f32 product, f32 accumulation)"
+                                     if args.precision == "fp32"
+                                     else "fp32 storage and arithmetic (SIMT kernels)"),
                        "cuda_graphs": not args.no_graphs,
                        "lazy_regularisers": "R1 on i%16==0, path-length on i%4==0, cadence restarted at i=0 "
                                             "for the timed region",
@@ -420,8 +423,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--size", type=int, default=256)
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
-                    help="bf16: tcgen05 tensor-core path (BASELINE configs[1]); fp32: SIMT parity path")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "fp32_simt"],
+                    help="bf16: tcgen05 tensor-core path (BASELINE configs[1]); fp32: the parity mode (f32 storage, "
+                         "split-operand tcgen05 convolutions); fp32_simt: f32 on the SIMT gather kernels")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     ap.add_argument("--shapes-out", default=None, help="write per-shape conv timings of the instrumented step here")
     ap.add_argument("--no-cpu-baseline", action="store_true")

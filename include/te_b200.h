@@ -165,9 +165,16 @@ typedef struct {
   /* optional extras; an all-zero tail keeps the plain behaviour */
   float act_gain;            /* gain after the leaky ReLU; 0 selects sqrt(2) (FusedLeakyReLU's scale) for act 1, 1 for act 2 */
   float wgrad_alpha;         /* te_conv_wgrad_tc accumulates wgrad_alpha * gradient; 0 selects 1 */
-  const void* residual;      /* bf16 [batch, hout, wout, cout] added AFTER bias/activation (ResBlock skip sum,
-                                model_spatial_query.py:795-797), or NULL; bf16 output only */
+  const void* residual;      /* [batch, hout, wout, cout] in the OUTPUT's dtype (bf16, or float when out_f32), added
+                                AFTER bias/activation (ResBlock skip sum, model_spatial_query.py:795-797), or NULL */
   const void* slope;         /* act 3: FLOAT32 [cout] negative slopes (nn.PReLU of the pSp trunk, helpers.py:90,112) */
+  int split;                 /* 0/1: x, W (and g of the weight gradient) are plain bf16 tensors.  2 or 3: the
+                                SPLIT-OPERAND fp32 mode — each of them is `split` bf16 planes [split][...same layout...]
+                                holding hi = bf16(v), mid = bf16(v - hi)(, lo = bf16(v - hi - mid)) of f32 values v
+                                (te_split_bf16, te_pack_weights_tc); the kernel sums the plane-pair products
+                                hi*hi + hi*mid + mid*hi (+ mid*mid + hi*lo + lo*hi) in the f32 accumulator: the
+                                reference's fp32 F.conv2d arithmetic to ~2^-16 (2^-24) per product, on tensor cores */
+  int reserved;
 } te_tc_conv_desc;
 
 int te_conv_tc(void* y, const void* x, const void* w, const float* out_scale, const float* bias,
@@ -197,6 +204,15 @@ int te_scale_bc(void* y, const void* x, const float* s, int64_t batch, int64_t p
 int te_dot_bc(float* out, const void* a, const void* b, int64_t batch, int64_t pixels, int channels,
               int dtype, void* stream);
 
+/* Split-operand planes of an f32 channels-last activation tensor, optionally modulated on the way:
+ *   v = x[b,p,c] * (s ? s[b,c] : 1) ;  dst[0] = hi = bf16(v), dst[1] = bf16(v - hi), dst[2] = bf16(v - hi - mid)
+ * x [batch, pixels, channels] FLOAT32, dst [nseg][batch, pixels, channels] bf16 (nseg = 1, 2 or 3; nseg 1 is a plain
+ * rounding conversion), s FLOAT32 [batch, channels] or NULL.  channels % 8 == 0, 16-byte aligned pointers.
+ * Feeds te_conv_tc / te_conv_wgrad_tc with te_tc_conv_desc.split = nseg: the fp32 parity mode of the reference's
+ * F.conv2d / F.conv_transpose2d calls (model_spatial_query.py:177-183,318,327,333) on tensor cores. */
+int te_split_bf16(void* dst, const float* x, const float* s, int64_t batch, int64_t pixels, int channels, int nseg,
+                  void* stream);
+
 /* Repack a TABLE of f32 master weights [out_ch, in_ch, K, K] (K*K = taps = 1 or 9, contiguous) into te_conv_tc's bf16
  * operand layouts in ONE launch: dst_n = [taps, out_pad, in_pad] (in_ch contiguous; the forward convolution's weights),
  * dst_t = [taps, in_pad, out_pad] (the data gradient's), each value times `scale`; pads = channel counts rounded up to
@@ -209,6 +225,7 @@ typedef struct te_pack_task {
   void* dst_t;
   int out_ch, in_ch, taps;
   float scale;
+  int split; /* 0/1: one bf16 plane; 2, 3: that many split-operand planes [split][taps][..][..] (te_tc_conv_desc.split) */
 } te_pack_task;
 int te_pack_weights_tc(const te_pack_task* tasks, int n_tasks, void* stream);
 

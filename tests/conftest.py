@@ -34,10 +34,13 @@ def _built_library():
 
 @pytest.fixture(autouse=True)
 def _fp32_math():
-    """The oracle runs with TF32 disabled."""
+    """The oracle runs with TF32 disabled; every test starts in the default precision mode."""
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
+    from transeditor_b200 import model as te_model
+    te_model.set_precision("fp32")
     yield
+    te_model.set_precision("fp32")
 
 
 def load_golden(name):

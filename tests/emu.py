@@ -187,20 +187,45 @@ def _tc_out_index(d):
     return oy, ox
 
 
+_PAIRS = {1: [(0, 0)], 2: [(0, 0), (0, 1), (1, 0)], 3: [(0, 0), (0, 1), (1, 0), (1, 1), (0, 2), (2, 0)]}
+
+
+def _act_planes(x, nseg):
+    """Activation operand -> list of f32 [B, C, H, W] planes (plain bf16 tensor, or split planes [S, B, H, W, C])."""
+    if nseg == 1:
+        return [x.float()]
+    assert x.dim() == 5 and x.shape[0] == nseg and x.dtype == torch.bfloat16
+    return [x[i].permute(0, 3, 1, 2).float() for i in range(nseg)]
+
+
+def split_bf16(dst, x, s, batch, pixels, channels, nseg):
+    v = _storage_flat(x).reshape(batch, pixels, channels).float()
+    if s is not None:
+        v = v * s.reshape(batch, 1, channels).float()
+    for i in range(nseg):
+        h = v.to(torch.bfloat16)
+        dst[i].reshape(batch, pixels, channels).copy_(h)
+        v = v - h.float()
+
+
 def conv_tc(y, x, w, out_scale, bias, desc):
-    """te_conv_tc from its header contract: tap table over an anchor grid, f32 accumulation of bf16 operands, epilogue
-    out_scale / bias / activation / residual, bf16 (or f32) output written at the anchors' output positions only."""
+    """te_conv_tc from its header contract: tap table over an anchor grid, f32 accumulation of bf16 operands (summed
+    over the split-operand plane pairs), epilogue out_scale / bias / activation / residual, bf16 (or f32) output
+    written at the anchors' output positions only."""
     d = desc
-    xf = x.float()
+    nseg = d.split if d.split >= 2 else 1
+    xs = _act_planes(x, nseg)
     per_sample = d.w_bstride != 0
-    wf = w.float().reshape((d.batch, d.w_slices, d.cout, d.cin) if per_sample else (d.w_slices, d.cout, d.cin))
+    wshape = (d.batch, d.w_slices, d.cout, d.cin) if per_sample else (d.w_slices, d.cout, d.cin)
+    ws = [w.float().reshape(wshape)] if nseg == 1 else [w[i].float().reshape(wshape) for i in range(nseg)]
     acc = torch.zeros(d.batch, d.cout, d.grid_h, d.grid_w)
     for t in range(d.ntaps):
-        g = _tc_gather(xf, d, d.tap_dy[t], d.tap_dx[t])
-        if per_sample:
-            acc += torch.einsum("bchw,boc->bohw", g, wf[:, d.tap_w[t]])
-        else:
-            acc += torch.einsum("bchw,oc->bohw", g, wf[d.tap_w[t]])
+        for pa, pw in _PAIRS[nseg]:
+            g = _tc_gather(xs[pa], d, d.tap_dy[t], d.tap_dx[t])
+            if per_sample:
+                acc += torch.einsum("bchw,boc->bohw", g, ws[pw][:, d.tap_w[t]])
+            else:
+                acc += torch.einsum("bchw,oc->bohw", g, ws[pw][d.tap_w[t]])
     if out_scale is not None:
         acc = acc * out_scale.reshape(d.batch, d.cout, 1, 1)
     if bias is not None:
@@ -221,31 +246,38 @@ def conv_wgrad_tc(gw, g, x, desc):
     d = desc
     alpha = d.wgrad_alpha if d.wgrad_alpha != 0 else 1.0
     oy, ox = _tc_out_index(d)
-    ga = g.float()[:, :, oy][:, :, :, ox]                      # gradient at the anchors' output positions
-    xf = x.float()
+    nseg = d.split if d.split >= 2 else 1
+    gas = [gp[:, :, oy][:, :, :, ox] for gp in _act_planes(g, nseg)]   # gradient at the anchors' output positions
+    xps = _act_planes(x, nseg)
     per_sample = d.w_bstride != 0
     view = gw.view((d.batch, d.w_slices, d.cout, d.cin) if per_sample else (d.w_slices, d.cout, d.cin))
     for t in range(d.ntaps):
-        xs = _tc_gather(xf, d, d.tap_dy[t], d.tap_dx[t])
-        if per_sample:
-            view[:, d.tap_w[t]] += alpha * torch.einsum("bohw,bchw->boc", ga, xs)
-        else:
-            view[d.tap_w[t]] += alpha * torch.einsum("bohw,bchw->oc", ga, xs)
+        for pg, px in _PAIRS[nseg]:
+            xs = _tc_gather(xps[px], d, d.tap_dy[t], d.tap_dx[t])
+            if per_sample:
+                view[:, d.tap_w[t]] += alpha * torch.einsum("bohw,bchw->boc", gas[pg], xs)
+            else:
+                view[d.tap_w[t]] += alpha * torch.einsum("bohw,bchw->oc", gas[pg], xs)
 
 
 def pack_weights_tc(tasks):
-    for src, dst_n, dst_t, scale in tasks:
+    for task in tasks:
+        src, dst_n, dst_t, scale = task[:4]
+        nseg = task[4] if len(task) > 4 else 1
         o, i, k, _ = src.shape
         v = (src.detach() * scale).permute(2, 3, 0, 1).reshape(k * k, o, i)  # f32 product, like the kernel
-        if dst_n is not None:
-            dst_n[:, :o, :i].copy_(v.to(dst_n.dtype))
-        if dst_t is not None:
-            dst_t[:, :i, :o].copy_(v.transpose(1, 2).to(dst_t.dtype))
+        for sg in range(nseg):
+            h = v.to(torch.bfloat16)
+            if dst_n is not None:
+                (dst_n if nseg == 1 else dst_n[sg])[:, :o, :i].copy_(h)
+            if dst_t is not None:
+                (dst_t if nseg == 1 else dst_t[sg])[:, :i, :o].copy_(h.transpose(1, 2))
+            v = v - h.float()
 
 
 def install(monkeypatch):
     monkeypatch.setattr(lib, "require_cuda", lambda *a: None)
     for name in ("fused_bias_act", "fused_bias_act_bwd", "upfirdn2d", "conv2d_simt",
                  "conv2d_wgrad_simt", "attn_core", "adam_ema", "adam_ema_devstep", "scale_bc", "dot_bc",
-                 "attn_stack_fwd", "attn_stack_bwd", "pack_weights_tc", "conv_tc", "conv_wgrad_tc"):
+                 "attn_stack_fwd", "attn_stack_bwd", "pack_weights_tc", "conv_tc", "conv_wgrad_tc", "split_bf16"):
         monkeypatch.setattr(lib, name, globals()[name])

@@ -22,6 +22,10 @@
 //     (tmem_full / tmem_empty barriers) let the producer and the MMA issuer run into the next tile
 //     while the epilogue warps drain the previous one.
 //   * Epilogue: out = act(acc * out_scale[b,cout] + bias[cout]) -> bf16 (or f32), 16-byte stores.
+//   * Split-operand mode (te_tc_conv_desc.split = 2 or 3): x and W are stored as 2 (3) bf16 PLANES hi, mid(, lo)
+//     of f32 values (te_split_bf16 / te_pack_weights_tc) and the K loop additionally walks the plane pairs
+//     (hi,hi) (hi,mid) (mid,hi) [(mid,mid) (hi,lo) (lo,hi)], all accumulated in the same f32 TMEM tile: the f32
+//     convolution to ~2^-16 (2^-24) relative accuracy at 3 (6) tensor-core products — the fp32 parity mode.
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -45,9 +49,11 @@ struct TcParams {
   int tw, th, nb;          // tile patch; nb*th*tw == 128
   int tiles_w, tiles_h, tiles_b, n_tiles;
   int w_slices_per_sample; // 0: shared weights; else slices per sample (weights indexed b*slices + w_t)
+  int nseg, npairs;        // split-operand planes and plane pairs (1, 1 = plain bf16)
+  int pair_a[6], pair_w[6];
   int act;
   float act_gain;
-  const __nv_bfloat16* residual;  // [B, hout, wout, cout] added after the activation, or null
+  const void* residual;    // [B, hout, wout, cout] (the output's dtype) added after the activation, or null
   const float* slope;      // act 3 (PReLU): negative slope per output channel [cout]
   int debug;               // TE_TC_DEBUG bits (profiling aid): 1 no stores, 2 no epilogue work, 4 no MMAs
   const float* out_scale;  // [B, cout] or null
@@ -67,6 +73,98 @@ struct TcSmem {
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Epilogue of one 32-column chunk of one accumulator row (= one output pixel): scale, bias, activation,
+// residual, store.  Shared by the 1-CTA and 2-CTA kernels.
+template <bool OUT_F32>
+__device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, const uint32_t (&v)[32], const float* s_osc,
+                                                  const float* s_bias, bool staged, const float* osc, bool valid,
+                                                  int64_t pix, int n0c0) {
+  float f[32];
+  if (staged) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 sc = *reinterpret_cast<const float4*>(s_osc + j);
+      const float4 bi = *reinterpret_cast<const float4*>(s_bias + j);
+      f[j] = __uint_as_float(v[j]) * sc.x + bi.x;
+      f[j + 1] = __uint_as_float(v[j + 1]) * sc.y + bi.y;
+      f[j + 2] = __uint_as_float(v[j + 2]) * sc.z + bi.z;
+      f[j + 3] = __uint_as_float(v[j + 3]) * sc.w + bi.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int n = n0c0 + j;
+      float a = __uint_as_float(v[j]);
+      if (n < p.cout) {
+        if (osc) a *= __ldg(osc + n);
+        if (p.bias) a += __ldg(p.bias + n);
+      }
+      f[j] = a;
+    }
+  }
+  if (p.act == 3) {  // PReLU: one slope per output channel (inference side path: plain cached loads)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int n = n0c0 + j;
+      if (f[j] < 0.f && n < p.cout) f[j] *= __ldg(p.slope + n);
+    }
+  } else if (p.act != 0) {
+    const float gain = p.act_gain, slope = p.act == 2 ? 0.01f : 0.2f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = (f[j] > 0.f ? f[j] : slope * f[j]) * gain;
+  }
+  if (p.residual != nullptr && valid) {
+    if (OUT_F32) {
+      const float4* rsrc = reinterpret_cast<const float4*>(static_cast<const float*>(p.residual) + pix * p.cout + n0c0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (n0c0 + 4 * j >= p.cout) continue;
+        const float4 r = __ldg(rsrc + j);
+        f[4 * j] += r.x; f[4 * j + 1] += r.y; f[4 * j + 2] += r.z; f[4 * j + 3] += r.w;
+      }
+    } else {
+      const uint4* rsrc =
+          reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + pix * p.cout + n0c0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (n0c0 + 8 * j >= p.cout) continue;
+        const uint4 r = __ldg(rsrc + j);
+        const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          f[8 * j + 2 * q] += __uint_as_float(rw[q] << 16);
+          f[8 * j + 2 * q + 1] += __uint_as_float(rw[q] & 0xffff0000u);
+        }
+      }
+    }
+  }
+  if (valid && !(p.debug & 1)) {
+    if (OUT_F32) {
+      float* dst = static_cast<float*>(p.y) + pix * p.cout + n0c0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (n0c0 + 4 * j < p.cout)
+          reinterpret_cast<float4*>(dst)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+    } else {
+      __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.y) + pix * p.cout + n0c0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (n0c0 + 8 * j >= p.cout) continue;
+        uint4 o;
+        __nv_bfloat162 t0 = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]);
+        __nv_bfloat162 t1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
+        __nv_bfloat162 t2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
+        __nv_bfloat162 t3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+        o.x = *reinterpret_cast<uint32_t*>(&t0);
+        o.y = *reinterpret_cast<uint32_t*>(&t1);
+        o.z = *reinterpret_cast<uint32_t*>(&t2);
+        o.w = *reinterpret_cast<uint32_t*>(&t3);
+        reinterpret_cast<uint4*>(dst)[j] = o;
+      }
+    }
+  }
 }
 
 // Persistent kernel: one CTA per SM walks tiles t = blockIdx.x, +gridDim.x, ...; the operand ring and
@@ -91,7 +189,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   const int n_blocks = (p.cout + BLOCK_N - 1) / BLOCK_N;
   const int total_tiles = p.n_tiles * n_blocks;
   const int k_chunks = (p.cin + TC_BLOCK_K - 1) / TC_BLOCK_K;
-  const int num_kb = p.ntaps * k_chunks;
+  const int kb_per_tap = p.npairs * k_chunks;  // plane pairs x 64-channel chunks
+  const int num_kb = p.ntaps * kb_per_tap;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
@@ -138,21 +237,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
           // miss in the middle of the ring stalls every stage behind it (measured: feed-bound at 128 channels)
           int pb, py, px, pn;
           tile_coords(tile + int(gridDim.x), pb, py, px, pn);
-          for (int kc = 0; kc < k_chunks; ++kc)
-            tma_prefetch_4d(&map_x, kc * TC_BLOCK_K, px * p.in_stride, py * p.in_stride, pb);
+          for (int sg = 0; sg < p.nseg; ++sg)
+            for (int kc = 0; kc < k_chunks; ++kc)
+              tma_prefetch_5d(&map_x, kc * TC_BLOCK_K, px * p.in_stride, py * p.in_stride, pb, sg);
         }
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
-          const int tap = kb / k_chunks, kc = kb - tap * k_chunks;
+          const int tap = kb / kb_per_tap, r = kb - tap * kb_per_tap;
+          const int pr = r / k_chunks, kc = r - pr * k_chunks;
           uint8_t* a_dst = smem + s * S::STAGE_BYTES;
           uint8_t* b_dst = a_dst + TC_A_BYTES;
           mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
-          tma_load_4d(a_dst, &map_x, &full_bar[s], kc * TC_BLOCK_K, ax0 * p.in_stride + p.tap_dx[tap],
-                      ay0 * p.in_stride + p.tap_dy[tap], b0);
+          tma_load_5d(a_dst, &map_x, &full_bar[s], kc * TC_BLOCK_K, ax0 * p.in_stride + p.tap_dx[tap],
+                      ay0 * p.in_stride + p.tap_dy[tap], b0, p.pair_a[pr]);
           const int wsl = p.w_slices_per_sample ? b0 * p.w_slices_per_sample + p.tap_w[tap] : p.tap_w[tap];
-          tma_load_3d(b_dst, &map_w, &full_bar[s], kc * TC_BLOCK_K, n0, wsl);
+          tma_load_4d(b_dst, &map_w, &full_bar[s], kc * TC_BLOCK_K, n0, wsl, p.pair_w[pr]);
         }
       }
     }
@@ -226,79 +327,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         if (n0 + c0 >= p.cout || (p.debug & 2)) break;  // warp-uniform
         uint32_t v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * BLOCK_N + c0, v);
-        float f[32];
-        if (staged) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 sc = *reinterpret_cast<const float4*>(s_osc + c0 + j);
-            const float4 bi = *reinterpret_cast<const float4*>(s_bias + c0 + j);
-            f[j] = __uint_as_float(v[j]) * sc.x + bi.x;
-            f[j + 1] = __uint_as_float(v[j + 1]) * sc.y + bi.y;
-            f[j + 2] = __uint_as_float(v[j + 2]) * sc.z + bi.z;
-            f[j + 3] = __uint_as_float(v[j + 3]) * sc.w + bi.w;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = n0 + c0 + j;
-            float a = __uint_as_float(v[j]);
-            if (n < p.cout) {
-              if (osc) a *= __ldg(osc + n);
-              if (p.bias) a += __ldg(p.bias + n);
-            }
-            f[j] = a;
-          }
-        }
-        if (p.act == 3) {  // PReLU: one slope per output channel (inference side path: plain cached loads)
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = n0 + c0 + j;
-            if (f[j] < 0.f && n < p.cout) f[j] *= __ldg(p.slope + n);
-          }
-        } else if (p.act != 0) {
-          const float gain = p.act_gain, slope = p.act == 2 ? 0.01f : 0.2f;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = (f[j] > 0.f ? f[j] : slope * f[j]) * gain;
-        }
-        if (p.residual != nullptr && valid) {
-          const uint4* rsrc = reinterpret_cast<const uint4*>(p.residual + pix * p.cout + n0 + c0);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (n0 + c0 + 8 * j >= p.cout) continue;
-            const uint4 r = __ldg(rsrc + j);
-            const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              f[8 * j + 2 * q] += __uint_as_float(rw[q] << 16);
-              f[8 * j + 2 * q + 1] += __uint_as_float(rw[q] & 0xffff0000u);
-            }
-          }
-        }
-        if (valid && !(p.debug & 1)) {
-          if (OUT_F32) {
-            float* dst = static_cast<float*>(p.y) + pix * p.cout + n0 + c0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (n0 + c0 + 4 * j < p.cout)
-                reinterpret_cast<float4*>(dst)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-          } else {
-            __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.y) + pix * p.cout + n0 + c0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (n0 + c0 + 8 * j >= p.cout) continue;
-              uint4 o;
-              __nv_bfloat162 t0 = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]);
-              __nv_bfloat162 t1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
-              __nv_bfloat162 t2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
-              __nv_bfloat162 t3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
-              o.x = *reinterpret_cast<uint32_t*>(&t0);
-              o.y = *reinterpret_cast<uint32_t*>(&t1);
-              o.z = *reinterpret_cast<uint32_t*>(&t2);
-              o.w = *reinterpret_cast<uint32_t*>(&t3);
-              reinterpret_cast<uint4*>(dst)[j] = o;
-            }
-          }
-        }
+        tc_epilogue_chunk<OUT_F32>(p, v, s_osc + c0, s_bias + c0, staged, osc, valid, pix, n0 + c0);
       }
       // this warp is done reading the accumulator buffer: hand it back to the MMA issuer
       tcgen05_fence_before();
@@ -350,7 +379,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   const int total_work = m_pairs * n_blocks;
   const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
   const int k_chunks = (p.cin + TC_BLOCK_K - 1) / TC_BLOCK_K;
-  const int num_kb = p.ntaps * k_chunks;
+  const int kb_per_tap = p.npairs * k_chunks;  // plane pairs x 64-channel chunks
+  const int num_kb = p.ntaps * kb_per_tap;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
@@ -394,21 +424,24 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         if (w + num_pairs < total_work) {  // L2 prefetch of the next work item's activation patch
           int pb, py, px, pn;
           work_coords(w + num_pairs, pb, py, px, pn);
-          for (int kc = 0; kc < k_chunks; ++kc)
-            tma_prefetch_4d(&map_x, kc * TC_BLOCK_K, px * p.in_stride, py * p.in_stride, pb);
+          for (int sg = 0; sg < p.nseg; ++sg)
+            for (int kc = 0; kc < k_chunks; ++kc)
+              tma_prefetch_5d(&map_x, kc * TC_BLOCK_K, px * p.in_stride, py * p.in_stride, pb, sg);
         }
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
-          const int tap = kb / k_chunks, kc = kb - tap * k_chunks;
+          const int tap = kb / kb_per_tap, r = kb - tap * kb_per_tap;
+          const int pr = r / k_chunks, kc = r - pr * k_chunks;
           uint8_t* a_dst = smem + s * S::STAGE_BYTES;
           uint8_t* b_dst = a_dst + TC_A_BYTES;
           if (leader) mbar_expect_tx(&full_bar[s], 2 * S::STAGE_BYTES);
-          tma2_load_4d(a_dst, &map_x, &full_bar[s], kc * TC_BLOCK_K, ax0 * p.in_stride + p.tap_dx[tap],
-                       ay0 * p.in_stride + p.tap_dy[tap], b0);
+          tma2_load_5d(a_dst, &map_x, &full_bar[s], kc * TC_BLOCK_K, ax0 * p.in_stride + p.tap_dx[tap],
+                       ay0 * p.in_stride + p.tap_dy[tap], b0, p.pair_a[pr]);
           const int wsl = p.w_slices_per_sample ? b0 * p.w_slices_per_sample + p.tap_w[tap] : p.tap_w[tap];
-          tma2_load_3d(b_dst, &map_w, &full_bar[s], kc * TC_BLOCK_K, n0 + int(rank) * (BLOCK_N / 2), wsl);
+          tma2_load_4d(b_dst, &map_w, &full_bar[s], kc * TC_BLOCK_K, n0 + int(rank) * (BLOCK_N / 2), wsl,
+                       p.pair_w[pr]);
         }
       }
     }
@@ -480,79 +513,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         if (n0 + c0 >= p.cout || (p.debug & 2)) break;  // warp-uniform
         uint32_t v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * BLOCK_N + c0, v);
-        float f[32];
-        if (staged) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 sc = *reinterpret_cast<const float4*>(s_osc + c0 + j);
-            const float4 bi = *reinterpret_cast<const float4*>(s_bias + c0 + j);
-            f[j] = __uint_as_float(v[j]) * sc.x + bi.x;
-            f[j + 1] = __uint_as_float(v[j + 1]) * sc.y + bi.y;
-            f[j + 2] = __uint_as_float(v[j + 2]) * sc.z + bi.z;
-            f[j + 3] = __uint_as_float(v[j + 3]) * sc.w + bi.w;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = n0 + c0 + j;
-            float a = __uint_as_float(v[j]);
-            if (n < p.cout) {
-              if (osc) a *= __ldg(osc + n);
-              if (p.bias) a += __ldg(p.bias + n);
-            }
-            f[j] = a;
-          }
-        }
-        if (p.act == 3) {  // PReLU: one slope per output channel (inference side path: plain cached loads)
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = n0 + c0 + j;
-            if (f[j] < 0.f && n < p.cout) f[j] *= __ldg(p.slope + n);
-          }
-        } else if (p.act != 0) {
-          const float gain = p.act_gain, slope = p.act == 2 ? 0.01f : 0.2f;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = (f[j] > 0.f ? f[j] : slope * f[j]) * gain;
-        }
-        if (p.residual != nullptr && valid) {
-          const uint4* rsrc = reinterpret_cast<const uint4*>(p.residual + pix * p.cout + n0 + c0);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (n0 + c0 + 8 * j >= p.cout) continue;
-            const uint4 r = __ldg(rsrc + j);
-            const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              f[8 * j + 2 * q] += __uint_as_float(rw[q] << 16);
-              f[8 * j + 2 * q + 1] += __uint_as_float(rw[q] & 0xffff0000u);
-            }
-          }
-        }
-        if (valid && !(p.debug & 1)) {
-          if (OUT_F32) {
-            float* dst = static_cast<float*>(p.y) + pix * p.cout + n0 + c0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (n0 + c0 + 4 * j < p.cout)
-                reinterpret_cast<float4*>(dst)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-          } else {
-            __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.y) + pix * p.cout + n0 + c0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (n0 + c0 + 8 * j >= p.cout) continue;
-              uint4 o;
-              __nv_bfloat162 t0 = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]);
-              __nv_bfloat162 t1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
-              __nv_bfloat162 t2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
-              __nv_bfloat162 t3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
-              o.x = *reinterpret_cast<uint32_t*>(&t0);
-              o.y = *reinterpret_cast<uint32_t*>(&t1);
-              o.z = *reinterpret_cast<uint32_t*>(&t2);
-              o.w = *reinterpret_cast<uint32_t*>(&t3);
-              reinterpret_cast<uint4*>(dst)[j] = o;
-            }
-          }
-        }
+        tc_epilogue_chunk<OUT_F32>(p, v, s_osc + c0, s_bias + c0, staged, osc, valid, pix, n0 + c0);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -639,9 +600,15 @@ static int conv_tc_dispatch(void* y, const void* x, const void* w, const float* 
   TE_CHECK_ARG(d.act != 3 || d.slope != nullptr, "conv_tc: act 3 (PReLU) needs the per-channel slopes");
   p.slope = static_cast<const float*>(d.slope);
   p.act_gain = d.act_gain != 0.f ? d.act_gain : (d.act == 2 ? 1.f : 1.4142135623730951f);
-  p.residual = static_cast<const __nv_bfloat16*>(d.residual);
-  TE_CHECK_ARG(!(d.residual && d.out_f32), "conv_tc: a residual input needs bf16 output");
+  p.residual = d.residual;
   TE_CHECK_ARG((reinterpret_cast<uintptr_t>(d.residual) & 15) == 0, "conv_tc: residual must be 16-byte aligned");
+  TE_CHECK_ARG(d.split >= 0 && d.split <= 3, "conv_tc: split must be 0/1 (plain bf16), 2 or 3 planes");
+  p.nseg = d.split < 2 ? 1 : d.split;
+  {
+    const SplitPairs sp = split_pairs(p.nseg);
+    p.npairs = sp.n;
+    for (int i = 0; i < 6; ++i) { p.pair_a[i] = sp.a[i]; p.pair_w[i] = sp.b[i]; }
+  }
   {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("TE_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
@@ -681,20 +648,22 @@ static int conv_tc_dispatch(void* y, const void* x, const void* w, const float* 
   CUtensorMap mx, mw;
   {
     const uint32_t is = uint32_t(d.in_stride);
-    uint64_t dims[4] = {uint64_t(d.cin), uint64_t(d.win), uint64_t(d.hin), uint64_t(d.batch)};
-    uint64_t strides[3] = {uint64_t(d.cin) * 2, uint64_t(d.win) * d.cin * 2, uint64_t(d.hin) * d.win * d.cin * 2};
+    // [planes][B][H][W][C]: the split-operand planes are the outermost dimension (1 plane for plain bf16)
+    uint64_t dims[5] = {uint64_t(d.cin), uint64_t(d.win), uint64_t(d.hin), uint64_t(d.batch), uint64_t(p.nseg)};
+    uint64_t strides[4] = {uint64_t(d.cin) * 2, uint64_t(d.win) * d.cin * 2, uint64_t(d.hin) * d.win * d.cin * 2,
+                           uint64_t(d.batch) * d.hin * d.win * d.cin * 2};
     // with a traversal stride e the unit loads ceil(box/e) elements: box = count * e
-    uint32_t box[4] = {TC_BLOCK_K, uint32_t(p.tw) * is, uint32_t(p.th) * is, uint32_t(p.nb)};
-    uint32_t estr[4] = {1, is, is, 1};
-    int rc = encode_map_bf16(&mx, x, 4, dims, strides, box, estr);
+    uint32_t box[5] = {TC_BLOCK_K, uint32_t(p.tw) * is, uint32_t(p.th) * is, uint32_t(p.nb), 1};
+    uint32_t estr[5] = {1, is, is, 1, 1};
+    int rc = encode_map_bf16(&mx, x, 5, dims, strides, box, estr);
     if (rc) return rc;
   }
   {
     const uint64_t nw = uint64_t(d.w_slices) * (d.w_bstride ? d.batch : 1);
-    uint64_t dims[3] = {uint64_t(d.cin), uint64_t(d.cout), nw};
-    uint64_t strides[2] = {uint64_t(d.cin) * 2, uint64_t(d.cout) * d.cin * 2};
-    uint32_t box[3] = {TC_BLOCK_K, uint32_t(two_cta ? block_n / 2 : block_n), 1};
-    int rc = encode_map_bf16(&mw, w, 3, dims, strides, box, nullptr);
+    uint64_t dims[4] = {uint64_t(d.cin), uint64_t(d.cout), nw, uint64_t(p.nseg)};
+    uint64_t strides[3] = {uint64_t(d.cin) * 2, uint64_t(d.cout) * d.cin * 2, nw * d.cout * d.cin * 2};
+    uint32_t box[4] = {TC_BLOCK_K, uint32_t(two_cta ? block_n / 2 : block_n), 1, 1};
+    int rc = encode_map_bf16(&mw, w, 4, dims, strides, box, nullptr);
     if (rc) return rc;
   }
   if (two_cta) {
@@ -722,7 +691,7 @@ static void same_conv_desc(te_tc_conv_desc& d, int batch, int h, int wd, int cin
   d.w_slices = kh * kw;
   d.in_stride = 1; d.out_stride = 1; d.out_off_y = 0; d.out_off_x = 0;
   d.grid_h = h; d.grid_w = wd; d.act = act; d.out_f32 = out_f32; d.w_bstride = w_bstride;
-  d.act_gain = 0.f; d.wgrad_alpha = 0.f; d.residual = nullptr; d.slope = nullptr;
+  d.act_gain = 0.f; d.wgrad_alpha = 0.f; d.residual = nullptr; d.slope = nullptr; d.split = 0; d.reserved = 0;
 }
 
 }  // namespace te

@@ -111,6 +111,41 @@ static int dot_bc_typed(float* out, const void* a, const void* b, int64_t batch,
   return TE_OK;
 }
 
+
+// Split-operand planes of an f32 tensor (see conv_tc.cu): 8 channels per thread = two 16-byte loads and one
+// 16-byte store per plane.  Optional per-(sample, channel) modulation fused in (saves the scale_bc pass).
+template <int NSEG>
+__global__ void __launch_bounds__(256)
+split_bf16_kernel(__nv_bfloat16* __restrict__ dst, const float* __restrict__ x, const float* __restrict__ s,
+                  uint32_t pc_vec, uint32_t c_vec, int64_t plane_vecs) {
+  const int64_t base = int64_t(blockIdx.y) * pc_vec;
+  const float4* xin = reinterpret_cast<const float4*>(x) + 2 * base;
+  uint4* out = reinterpret_cast<uint4*>(dst) + base;
+  const float* srow = s ? s + int64_t(blockIdx.y) * c_vec * 8 : nullptr;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t iv = blockIdx.x * blockDim.x + threadIdx.x; iv < pc_vec; iv += stride) {
+    const float4 a = xin[2 * iv], b = xin[2 * iv + 1];
+    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    if (srow) {
+      const float4 s0 = __ldg(reinterpret_cast<const float4*>(srow + (iv % c_vec) * 8));
+      const float4 s1 = __ldg(reinterpret_cast<const float4*>(srow + (iv % c_vec) * 8) + 1);
+      v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w;
+      v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
+    }
+#pragma unroll
+    for (int sg = 0; sg < NSEG; ++sg) {
+      uint32_t w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
+        v[2 * j] -= __bfloat162float(h0);       // exact in f32: the remainder has at most 16 significant bits
+        v[2 * j + 1] -= __bfloat162float(h1);
+        w[j] = uint32_t(__bfloat16_as_ushort(h0)) | (uint32_t(__bfloat16_as_ushort(h1)) << 16);
+      }
+      out[sg * plane_vecs + iv] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+}
 }  // namespace te
 
 extern "C" int te_scale_bc(void* y, const void* x, const float* s, int64_t batch, int64_t pixels, int channels,
@@ -123,6 +158,31 @@ extern "C" int te_scale_bc(void* y, const void* x, const float* s, int64_t batch
   if (dtype == TE_F16) return scale_bc_typed<__half>(y, x, s, batch, pixels, channels, st);
   set_error("scale_bc: unsupported dtype %d", dtype);
   return TE_ERR_UNSUPPORTED;
+}
+
+extern "C" int te_split_bf16(void* dst, const float* x, const float* s, int64_t batch, int64_t pixels, int channels,
+                             int nseg, void* stream) {
+  using namespace te;
+  TE_CHECK_ARG(dst && x, "split_bf16: null pointer");
+  TE_CHECK_ARG(nseg >= 1 && nseg <= 3, "split_bf16: 1, 2 or 3 planes");
+  TE_CHECK_ARG(channels % 8 == 0, "split_bf16: channel count %d must be a multiple of 8", channels);
+  TE_CHECK_ARG(((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(s)) & 15) == 0,
+               "split_bf16: pointers must be 16-byte aligned");
+  const int64_t pc_vec = pixels * channels / 8;
+  if (batch * pc_vec == 0) return TE_OK;
+  TE_CHECK_ARG(pc_vec < (int64_t(1) << 31) && batch <= 65535, "split_bf16: tensor too large");
+  int64_t want = (int64_t(kNumSMs) * 16 + batch - 1) / batch;
+  int64_t need = (pc_vec + 255) / 256;
+  const unsigned gx = unsigned(need < want ? need : want);
+  dim3 grid(gx > 0 ? gx : 1, unsigned(batch));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  __nv_bfloat16* d = static_cast<__nv_bfloat16*>(dst);
+  const int64_t plane = batch * pc_vec;
+  if (nseg == 1) split_bf16_kernel<1><<<grid, 256, 0, st>>>(d, x, s, uint32_t(pc_vec), uint32_t(channels / 8), plane);
+  else if (nseg == 2) split_bf16_kernel<2><<<grid, 256, 0, st>>>(d, x, s, uint32_t(pc_vec), uint32_t(channels / 8), plane);
+  else split_bf16_kernel<3><<<grid, 256, 0, st>>>(d, x, s, uint32_t(pc_vec), uint32_t(channels / 8), plane);
+  TE_CHECK_LAUNCH();
+  return TE_OK;
 }
 
 extern "C" int te_dot_bc(float* out, const void* a, const void* b, int64_t batch, int64_t pixels, int channels,
@@ -151,6 +211,7 @@ struct PackTask {
   int O, I, kk, opad, ipad;
   float scale;
   int tile0;
+  int nseg;   // split-operand planes written (plane stride = kk * opad * ipad)
 };
 constexpr int PACK_MAX_TASKS = 64;
 struct PackParams {
@@ -175,18 +236,33 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const __grid_constant
       for (int e = lane; e < row_len; e += 32) tile[r][e] = s[e];
     }
     __syncthreads();
+    const int64_t plane = int64_t(kk) * T.opad * T.ipad;
     if (T.dst_n) {
       for (int q = warp; q < kk * no; q += 8) {
         const int tap = q / no, r = q - tap * no;
-        if (lane < ni)
-          T.dst_n[(int64_t(tap) * T.opad + o0 + r) * T.ipad + i0 + lane] = __float2bfloat16_rn(tile[r][lane * kk + tap] * T.scale);
+        if (lane < ni) {
+          float v = tile[r][lane * kk + tap] * T.scale;
+          __nv_bfloat16* d = T.dst_n + (int64_t(tap) * T.opad + o0 + r) * T.ipad + i0 + lane;
+          for (int sg = 0; sg < T.nseg; ++sg) {
+            const __nv_bfloat16 h = __float2bfloat16_rn(v);
+            d[sg * plane] = h;
+            v -= __bfloat162float(h);
+          }
+        }
       }
     }
     if (T.dst_t) {
       for (int q = warp; q < kk * ni; q += 8) {
         const int tap = q / ni, c = q - tap * ni;
-        if (lane < no)
-          T.dst_t[(int64_t(tap) * T.ipad + i0 + c) * T.opad + o0 + lane] = __float2bfloat16_rn(tile[lane][c * kk + tap] * T.scale);
+        if (lane < no) {
+          float v = tile[lane][c * kk + tap] * T.scale;
+          __nv_bfloat16* d = T.dst_t + (int64_t(tap) * T.ipad + i0 + c) * T.opad + o0 + lane;
+          for (int sg = 0; sg < T.nseg; ++sg) {
+            const __nv_bfloat16 h = __float2bfloat16_rn(v);
+            d[sg * plane] = h;
+            v -= __bfloat162float(h);
+          }
+        }
       }
     }
     __syncthreads();
@@ -219,6 +295,8 @@ extern "C" int te_pack_weights_tc(const te_pack_task* tasks, int n_tasks, void* 
       t.opad = (s.out_ch + 7) / 8 * 8;
       t.ipad = (s.in_ch + 7) / 8 * 8;
       t.scale = s.scale;
+      t.nseg = s.split < 2 ? 1 : s.split;
+      TE_CHECK_ARG(s.split >= 0 && s.split <= 3, "pack_weights_tc: task %d: split must be 0..3", base + i);
       t.tile0 = tiles;
       tiles += ((s.out_ch + 31) / 32) * ((s.in_ch + 31) / 32);
     }

@@ -46,10 +46,23 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0,
+                                            int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+      "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 // L2 prefetch of one TMA box (no shared-memory destination, no barrier)
 __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_5d(const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
                : "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -183,6 +196,20 @@ inline int encode_map_u16_linear(CUtensorMap* map, const void* base, int rank, c
     return TE_ERR_CUDA;
   }
   return TE_OK;
+}
+
+// Split-operand ("fp32 on tensor cores") modes: an f32 tensor is stored as `nseg` bf16 PLANES hi, mid(, lo) with
+// hi = bf16(x), mid = bf16(x - hi), lo = bf16(x - hi - mid); a product x*w is the sum of the plane pairs below
+// (terms below 2^-16, resp. 2^-24, of the product are dropped).  nseg 1 is the plain bf16 path.
+struct SplitPairs {
+  int n;
+  int a[6], b[6];
+};
+inline SplitPairs split_pairs(int nseg) {
+  SplitPairs s = {1, {0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}};
+  if (nseg == 2) { s.n = 3; const int a[3] = {0, 0, 1}, b[3] = {0, 1, 0}; for (int i = 0; i < 3; ++i) { s.a[i] = a[i]; s.b[i] = b[i]; } }
+  if (nseg == 3) { s.n = 6; const int a[6] = {0, 0, 1, 1, 0, 2}, b[6] = {0, 1, 0, 1, 2, 0}; for (int i = 0; i < 6; ++i) { s.a[i] = a[i]; s.b[i] = b[i]; } }
+  return s;
 }
 
 inline int next_pow2(int v) {

@@ -13,6 +13,8 @@
 //   * split-K over anchor tiles (grid.z) so the chip is filled even when Cout*Cin is one tile;
 //     partial sums are combined with vectorised f32 reductions (red.global.add.v4.f32).
 //   * Out-of-range anchors / padding taps / channel tails are zero-filled by the TMA unit.
+//   * Split-operand mode (te_tc_conv_desc.split = 2 or 3, see conv_tc.cu): g and x are bf16 plane stacks of f32
+//     values; every anchor tile is walked once per plane pair, all pairs accumulating into the same TMEM tiles.
 #include "tc_common.cuh"
 
 namespace te {
@@ -40,6 +42,7 @@ struct WgParams {
   int tiles_per_sample;
   int64_t gw_bstride;             // elements between two samples' gradients (per-sample mode)
   int use_atomics;
+  int npairs, pair_g[6], pair_x[6];   // split-operand plane pairs (1 pair = plain bf16)
   float alpha;                    // gw += alpha * partial
   float* gw;                      // [w_slices, cout, cin]
 };
@@ -74,7 +77,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
     tile_lo = blockIdx.z * p.tiles_per_split;
     tile_hi = min(p.n_tiles, tile_lo + p.tiles_per_split);
   }
-  const int num_it = max(0, tile_hi - tile_lo);  // pipeline iterations: anchor tiles
+  const int num_it = max(0, tile_hi - tile_lo) * p.npairs;  // pipeline iterations: anchor tiles x plane pairs
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_g)) : "memory");
@@ -104,21 +107,23 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
         const int s = it % WG_STAGES;
         const uint32_t ph = (it / WG_STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
-        int t = tile_lo + it;
+        const int pr = it % p.npairs;
+        const int sg = p.pair_g[pr], sx = p.pair_x[pr];
+        int t = tile_lo + it / p.npairs;
         const int tile_w = t % p.tiles_w; t /= p.tiles_w;
         const int tile_h = t % p.tiles_h; t /= p.tiles_h;
         const int b0 = t * p.nb, ay0 = tile_h * p.th, ax0 = tile_w * p.tw;
         uint8_t* dst = smem + s * WG_STAGE_BYTES;
         mbar_expect_tx(&full_bar[s], (1 + ntap) * WG_TILE_BYTES);
         const int gx = ax0 * p.out_stride + p.out_off_x, gy = ay0 * p.out_stride + p.out_off_y;
-        tma_load_4d(dst, &map_g, &full_bar[s], m0, gx, gy, b0);
-        tma_load_4d(dst + WG_HALF_BYTES, &map_g, &full_bar[s], m0 + 64, gx, gy, b0);
+        tma_load_5d(dst, &map_g, &full_bar[s], m0, gx, gy, b0, sg);
+        tma_load_5d(dst + WG_HALF_BYTES, &map_g, &full_bar[s], m0 + 64, gx, gy, b0, sg);
         for (int tp = 0; tp < ntap; ++tp) {
           const int tap = tap0 + tp;
           uint8_t* xd = dst + (1 + tp) * WG_TILE_BYTES;
           const int xx = ax0 * p.in_stride + p.tap_dx[tap], xy = ay0 * p.in_stride + p.tap_dy[tap];
-          tma_load_4d(xd, &map_x, &full_bar[s], n0, xx, xy, b0);
-          tma_load_4d(xd + WG_HALF_BYTES, &map_x, &full_bar[s], n0 + 64, xx, xy, b0);
+          tma_load_5d(xd, &map_x, &full_bar[s], n0, xx, xy, b0, sx);
+          tma_load_5d(xd + WG_HALF_BYTES, &map_x, &full_bar[s], n0 + 64, xx, xy, b0, sx);
         }
       }
     }
@@ -254,23 +259,32 @@ extern "C" int te_conv_wgrad_tc(float* gw, const void* g, const void* x, const t
     p.use_atomics = splits > 1 ? 1 : 0;
   }
 
+  TE_CHECK_ARG(d.split >= 0 && d.split <= 3, "conv_wgrad_tc: split must be 0/1 (plain bf16), 2 or 3 planes");
+  const int nseg = d.split < 2 ? 1 : d.split;
+  {
+    const SplitPairs sp = split_pairs(nseg);
+    p.npairs = sp.n;
+    for (int i = 0; i < 6; ++i) { p.pair_g[i] = sp.a[i]; p.pair_x[i] = sp.b[i]; }
+  }
   CUtensorMap mg, mx;
   {
     const uint32_t os = uint32_t(d.out_stride);
-    uint64_t dims[4] = {uint64_t(d.cout), uint64_t(d.wout), uint64_t(d.hout), uint64_t(d.batch)};
-    uint64_t strides[3] = {uint64_t(d.cout) * 2, uint64_t(d.wout) * d.cout * 2, uint64_t(d.hout) * d.wout * d.cout * 2};
-    uint32_t box[4] = {64, uint32_t(p.tw) * os, uint32_t(p.th) * os, uint32_t(p.nb)};
-    uint32_t estr[4] = {1, os, os, 1};
-    int rc = encode_map_bf16(&mg, g, 4, dims, strides, box, estr);
+    uint64_t dims[5] = {uint64_t(d.cout), uint64_t(d.wout), uint64_t(d.hout), uint64_t(d.batch), uint64_t(nseg)};
+    uint64_t strides[4] = {uint64_t(d.cout) * 2, uint64_t(d.wout) * d.cout * 2, uint64_t(d.hout) * d.wout * d.cout * 2,
+                           uint64_t(d.batch) * d.hout * d.wout * d.cout * 2};
+    uint32_t box[5] = {64, uint32_t(p.tw) * os, uint32_t(p.th) * os, uint32_t(p.nb), 1};
+    uint32_t estr[5] = {1, os, os, 1, 1};
+    int rc = encode_map_bf16(&mg, g, 5, dims, strides, box, estr);
     if (rc) return rc;
   }
   {
     const uint32_t is = uint32_t(d.in_stride);
-    uint64_t dims[4] = {uint64_t(d.cin), uint64_t(d.win), uint64_t(d.hin), uint64_t(d.batch)};
-    uint64_t strides[3] = {uint64_t(d.cin) * 2, uint64_t(d.win) * d.cin * 2, uint64_t(d.hin) * d.win * d.cin * 2};
-    uint32_t box[4] = {64, uint32_t(p.tw) * is, uint32_t(p.th) * is, uint32_t(p.nb)};
-    uint32_t estr[4] = {1, is, is, 1};
-    int rc = encode_map_bf16(&mx, x, 4, dims, strides, box, estr);
+    uint64_t dims[5] = {uint64_t(d.cin), uint64_t(d.win), uint64_t(d.hin), uint64_t(d.batch), uint64_t(nseg)};
+    uint64_t strides[4] = {uint64_t(d.cin) * 2, uint64_t(d.win) * d.cin * 2, uint64_t(d.hin) * d.win * d.cin * 2,
+                           uint64_t(d.batch) * d.hin * d.win * d.cin * 2};
+    uint32_t box[5] = {64, uint32_t(p.tw) * is, uint32_t(p.th) * is, uint32_t(p.nb), 1};
+    uint32_t estr[5] = {1, is, is, 1, 1};
+    int rc = encode_map_bf16(&mx, x, 5, dims, strides, box, estr);
     if (rc) return rc;
   }
   static bool configured = false;

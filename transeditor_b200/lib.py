@@ -40,7 +40,7 @@ class TcConvDesc(ctypes.Structure):
                 ("grid_h", ctypes.c_int), ("grid_w", ctypes.c_int),
                 ("act", ctypes.c_int), ("out_f32", ctypes.c_int), ("w_bstride", ctypes.c_int64),
                 ("act_gain", ctypes.c_float), ("wgrad_alpha", ctypes.c_float), ("residual", ctypes.c_void_p),
-                ("slope", ctypes.c_void_p)]
+                ("slope", ctypes.c_void_p), ("split", ctypes.c_int), ("reserved", ctypes.c_int)]
 
 
 ATTN_FIELDS = ("w_proj", "b_proj", "w_q", "b_q", "w_k", "b_k", "w_v", "b_v", "w_o", "b_o", "w_m1", "b_m1",
@@ -55,7 +55,8 @@ class AttnBlock(ctypes.Structure):
 class PackTask(ctypes.Structure):
     """Mirror of te_pack_task."""
     _fields_ = [("src", ctypes.c_void_p), ("dst_n", ctypes.c_void_p), ("dst_t", ctypes.c_void_p),
-                ("out_ch", ctypes.c_int), ("in_ch", ctypes.c_int), ("taps", ctypes.c_int), ("scale", ctypes.c_float)]
+                ("out_ch", ctypes.c_int), ("in_ch", ctypes.c_int), ("taps", ctypes.c_int), ("scale", ctypes.c_float),
+                ("split", ctypes.c_int)]
 
 
 _P, _I, _L, _F = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
@@ -73,6 +74,7 @@ _SIGNATURES = {
     "te_conv_wgrad_tc": ([_P, _P, _P, ctypes.POINTER(TcConvDesc), _P], _I),
     "te_scale_bc": ([_P, _P, _P, _L, _L, _I, _I, _P], _I),
     "te_dot_bc": ([_P, _P, _P, _L, _L, _I, _I, _P], _I),
+    "te_split_bf16": ([_P, _P, _P, _L, _L, _I, _I, _P], _I),
     "te_conv2d_tc": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _L, _P], _I),
     "te_gemm_tc_selftest": ([_P, _P, _P, _I, _I, _I, _P], _I),
     "te_attn_core": ([_P, _P, _P, _P, _P, _I, _I, _P], _I),
@@ -201,11 +203,14 @@ def attn_core(out, sim, q, k, v, batch, tokens):
 
 
 def pack_weights_tc(tasks):
-    """tasks: list of (src f32 [O, I, K, K] contiguous, dst_n bf16 or None, dst_t bf16 or None, scale)."""
+    """tasks: list of (src f32 [O, I, K, K] contiguous, dst_n bf16 or None, dst_t bf16 or None, scale[, nseg]);
+    nseg = 2 or 3 writes that many split-operand planes ([nseg, K*K, ., .] destinations)."""
     if not tasks:
         return
     table = (PackTask * len(tasks))()
-    for e, (src, dst_n, dst_t, scale) in zip(table, tasks):
+    for e, task in zip(table, tasks):
+        src, dst_n, dst_t, scale = task[:4]
+        e.split = task[4] if len(task) > 4 else 1
         if src.dtype != torch.float32 or not src.is_contiguous() or src.dim() != 4 or src.shape[2] != src.shape[3]:
             raise TypeError("pack_weights_tc: source must be a contiguous float32 [O, I, K, K] tensor")
         for d in (dst_n, dst_t):
@@ -284,6 +289,11 @@ def conv_wgrad_tc(gw, g, x, desc):
 
 def scale_bc(y, x, s, batch, pixels, channels):
     _check(load().te_scale_bc(ptr(y), ptr(x), ptr(s), batch, pixels, channels, dtype_code(x), stream()), "scale_bc")
+    _count()
+
+
+def split_bf16(dst, x, s, batch, pixels, channels, nseg):
+    _check(load().te_split_bf16(ptr(dst), ptr(x), ptr(s), batch, pixels, channels, nseg, stream()), "split_bf16")
     _count()
 
 

@@ -27,17 +27,24 @@ from .op import FusedLeakyReLU, fused_leaky_relu, upfirdn2d
 
 _SQRT2 = math.sqrt(2.0)
 
-# Precision of the convolution stacks.  "fp32": NCHW f32 on the SIMT kernels — the parity mode, the
-# reference's own arithmetic.  "bf16": channels-last bf16 activations on the tcgen05 kernels (f32
-# accumulation, f32 master weights, f32 mapping / transformer / RGB skip path).  Layers dispatch on
-# the dtype of their input; this flag only decides the conversion at the model boundaries.
+# Precision of the convolution stacks.
+#   "fp32"       the parity mode: f32 channels-last activations, every convolution on the tcgen05 kernels in
+#                SPLIT-OPERAND form (tc.py: bf16 hi/mid planes, three tensor-core products per f32 product, f32
+#                accumulation) — the reference's fp32 arithmetic to ~2^-16 per product, image max-abs error
+#                ~2e-4 at 256^2 against the 1e-3 bar.
+#   "bf16"       the speed mode: channels-last bf16 activations, plain bf16 tcgen05 products (f32 accumulation, f32
+#                master weights, f32 mapping / transformer / RGB skip path).
+#   "fp32_simt"  NCHW f32 on the SIMT gather kernels (exact f32 FMA chains; kept for f64 gradchecks and as a
+#                cross-check of the split-operand mode).
+# Layers dispatch on the dtype of their input (`_tc`); this flag decides the conversion at the model boundaries and
+# which engine f32 tensors use.
 _PRECISION = "fp32"
 
 
 def set_precision(name):
     global _PRECISION
-    if name not in ("fp32", "bf16"):
-        raise ValueError("precision must be 'fp32' or 'bf16'")
+    if name not in ("fp32", "bf16", "fp32_simt"):
+        raise ValueError("precision must be 'fp32', 'bf16' or 'fp32_simt'")
     _PRECISION = name
 
 
@@ -45,16 +52,35 @@ def get_precision():
     return _PRECISION
 
 
-def _to_bf16_cl(x, pad_to=8):
-    """f32/bf16 NCHW -> bf16 channels-last with the channel count padded to a multiple of `pad_to`."""
+def _tc(x):
+    """True when the tensor-core engine handles activations like x."""
+    return x.dtype == torch.bfloat16 or (x.dtype == torch.float32 and _PRECISION == "fp32")
+
+
+def _tc_mode():
+    return _PRECISION in ("bf16", "fp32")
+
+
+def _act_dtype():
+    return torch.bfloat16 if _PRECISION == "bf16" else torch.float32
+
+
+def _to_cl(x, dtype=None, pad_to=8):
+    """NCHW -> channels-last `dtype` (default: the precision mode's activation dtype) with the channel count
+    padded to a multiple of `pad_to`."""
+    dtype = dtype or _act_dtype()
     b, c, h, w = x.shape
     if c % pad_to == 0:
-        return x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-    # one memset of the padded bf16 buffer + one strided convert-copy of the real channels (instead of pad in
+        return x.to(dtype).contiguous(memory_format=torch.channels_last)
+    # one memset of the padded buffer + one strided convert-copy of the real channels (instead of pad in
     # f32, dtype conversion and a layout change: three passes over the PADDED tensor)
-    buf = torch.zeros((b, h, w, c + pad_to - c % pad_to), dtype=torch.bfloat16, device=x.device)
+    buf = torch.zeros((b, h, w, c + pad_to - c % pad_to), dtype=dtype, device=x.device)
     buf[..., :c] = x.permute(0, 2, 3, 1)
     return buf.permute(0, 3, 1, 2)
+
+
+def _to_bf16_cl(x, pad_to=8):
+    return _to_cl(x, torch.bfloat16, pad_to)
 
 
 _SIDE_STREAMS = {}
@@ -155,8 +181,16 @@ class EqualConv2d(nn.Module):
             w = F.pad(w, (0, 0, 0, 0, 0, input.shape[1] - w.shape[1]))
         return w
 
+    def _tc_ok(self, input):
+        k = self.weight.shape[2]
+        return (_tc(input) and self.weight.shape[0] % 8 == 0 and self.stride in (1, 2)
+                and self.padding == (k // 2 if self.stride == 1 else 0)
+                and (input.dtype == torch.bfloat16 or k in (1, 3)))
+
     def forward(self, input):
-        if input.dtype == torch.bfloat16:
+        if self._tc_ok(input):
+            if input.shape[1] % 8:  # odd channel counts (RGB): zero channels, matched by zero weight columns
+                input = F.pad(input, (0, 0, 0, 0, 0, 8 - input.shape[1] % 8))
             out = tc.conv2d(input, self._tc_weight(input), stride=self.stride, wscale=self.scale)
             if self.bias is not None:
                 out = out + self.bias.view(1, -1, 1, 1).to(out.dtype)
@@ -281,7 +315,7 @@ class ModulatedConv2d(nn.Module):
     def forward(self, input, style, bias=None, noise=None, noise_weight=None, activate=False):
         """`bias`/`noise`/`activate` let StyledConv hand its epilogue to the conv kernel on the
         inference path; reference callers pass only (input, style)."""
-        if input.dtype == torch.bfloat16:
+        if _tc(input) and (input.dtype == torch.bfloat16 or (self.in_channel % 8 == 0 and not self.downsample)):
             ops = self._take_prepared(input)
             if ops is None:
                 ops = self.tc_operands(style, input.shape[2] * input.shape[3])
@@ -380,7 +414,8 @@ def _modconv_forward_tc(self, x, ops, bias, noise, noise_weight, activate, fused
             v = self.blur(tc.conv_transpose2d(x, wb, wscale=wscale))
         elif fused_ok and noise is None:
             pb = None if bias is None else F.pad(bias.reshape(-1), (0, wn.shape[0] - cout))
-            v = tc.conv_raw(x, tc.pack_weight(wb, False, wscale), tc.Mode("s1", k), bias=pb, act=activate)
+            v = tc.conv_raw(x, tc.pack_weight(wb, False, wscale, tc.nseg_for(x)), tc.Mode("s1", k), bias=pb,
+                            act=activate)
             return v if wn.shape[0] == cout else v[:, :cout]
         elif activate and noise is None and bias is not None and wn.shape[0] == cout:
             return tc.conv2d_bias_act(x, wb, bias.reshape(-1), wscale=wscale)  # bias + lrelu in the epilogue
@@ -390,14 +425,17 @@ def _modconv_forward_tc(self, x, ops, bias, noise, noise_weight, activate, fused
             v = v[:, :cout]
         return _epilogue(v, bias, noise, noise_weight, activate)
     # Low resolution: shared weights, modulation / demodulation applied to the (small) activations.
+    if fused_ok and noise is None and not self.upsample:
+        pb = None if bias is None else F.pad(bias.reshape(-1), (0, wn.shape[0] - cout))
+        wp = tc.pack_weight(wn, False, wscale, tc.nseg_for(x))
+        if x.dtype == torch.float32:  # the modulation rides in the operand split
+            v = tc.conv_raw(x, wp, tc.Mode("s1", k), out_scale=d, bias=pb, act=activate, in_scale=s)
+        else:
+            v = tc.conv_raw(op.scale_bc(x, s), wp, tc.Mode("s1", k), out_scale=d, bias=pb, act=activate)
+        return v if wn.shape[0] == cout else v[:, :cout]
     u = op.scale_bc(x, s)
     if self.upsample:
         v = self.blur(tc.conv_transpose2d(u, wn, wscale=wscale))
-    elif fused_ok and noise is None:
-        pb = None if bias is None else F.pad(bias.reshape(-1), (0, wn.shape[0] - cout))
-        v = tc.conv_raw(u, tc.pack_weight(wn, False, wscale), tc.Mode("s1", k), out_scale=d, bias=pb,
-                        act=activate)
-        return v if wn.shape[0] == cout else v[:, :cout]
     else:
         v = tc.conv2d(u, wn, wscale=wscale)
     if d is not None:
@@ -482,7 +520,7 @@ class ToRGB(nn.Module):
         self.bias = nn.Parameter(torch.zeros(1, 3, 1, 1))
 
     def forward(self, input, style, skip=None):
-        if input.dtype == torch.bfloat16:
+        if _tc(input):
             # the RGB skip path stays f32 NCHW (tiny tensors): slice the padded conv output and convert
             out = self.conv(input, style).float().contiguous() + self.bias
         else:
@@ -753,8 +791,8 @@ class Generator(nn.Module):
 
         batch = spatialcode.shape[0]
         out = spatialcode.permute(0, 2, 1).reshape(batch, 512, 4, 4)
-        if _PRECISION == "bf16":
-            out = _to_bf16_cl(out)
+        if _tc_mode():
+            out = _to_cl(out)
             self._prepare_styles(latent)
         out = self.conv1(out, latent[:, 0], noise=noise[0])
         skip = self.to_rgb1(out, latent[:, 1])
@@ -798,7 +836,7 @@ class ConvLayer(nn.Sequential):
         super().__init__(*layers)
 
     def forward(self, input):
-        if input.dtype != torch.bfloat16:
+        if not _tc(input):
             return super().forward(input)
         return self.forward_tc(input)
 
@@ -877,7 +915,7 @@ class ResBlock(nn.Module):
                               bias=False, activate=False)
 
     def forward(self, input):
-        if input.dtype == torch.bfloat16:
+        if _tc(input):
             # (conv2(conv1(x)) + skip(x)) / sqrt(2) with the 1/sqrt(2) folded into conv2's activation gain and the
             # skip convolution's weight scale, and the sum taken in the skip convolution's epilogue
             # and the two gradient contributions of `input` summed in conv1's data-gradient epilogue (carry)
@@ -918,12 +956,12 @@ class Discriminator(nn.Module):
         """Not in the reference: treats `input` as `sub_batches` independent batches stacked along dim 0 —
         e.g. cat([fake, real]) — so ONE pass gives exactly the logits of separate calls: every layer is
         per-sample except the minibatch standard deviation, which is taken per sub-batch."""
-        bf16 = _PRECISION == "bf16"
-        # bf16: the whole conv stack incl. final_conv on tensor cores; statistics and linears in f32
+        bf16 = _tc_mode() and input.dtype in (torch.float32, torch.bfloat16)
+        # tensor-core modes: the whole conv stack incl. final_conv on tensor cores; statistics and linears in f32
         # RGB is zero-padded to 64 channels: a TMA box whose rows are mostly out of bounds (8 of 64 channels)
         # takes the unit's slow path (measured 4 us per tile); a dense 128-byte row costs 134 MB of extra
         # input but runs at full speed
-        out = self.convs(_to_bf16_cl(input, pad_to=64) if bf16 else input)
+        out = self.convs(_to_cl(input, pad_to=64) if bf16 else input)
         batch, channel, height, width = out.shape
         if batch % sub_batches:
             raise ValueError("batch %d is not divisible into %d sub-batches" % (batch, sub_batches))
@@ -937,7 +975,7 @@ class Discriminator(nn.Module):
         stddev = stddev.unsqueeze(1).expand(sub_batches, group, -1, self.stddev_feat, height, width)
         stddev = stddev.reshape(batch, self.stddev_feat, height, width)
         if bf16:
-            out = _to_bf16_cl(torch.cat([out, stddev.to(out.dtype)], 1))  # 513 -> 520 channels
+            out = _to_cl(torch.cat([out, stddev.to(out.dtype)], 1))  # 513 -> 520 channels
             out = self.final_conv(out).float().contiguous()
         else:
             out = self.final_conv(torch.cat([out, stddev], 1))

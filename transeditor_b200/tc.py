@@ -14,6 +14,14 @@ the master weight W [O, I, K, K].  The set is closed under differentiation:
 and the weight gradient of each mode is one te_conv_wgrad_tc call per launch of the forward geometry.
 `up` is issued as one launch per output parity class (polyphase), so no zero-inserted tensor exists.
 
+Two operand precisions, selected by the dtype of the activations:
+    bf16 activations   plain bf16 x bf16 -> f32 products (the speed mode)
+    f32 activations    SPLIT-OPERAND mode: activations, gradients and weights are stored as `split_planes()` bf16
+                       planes hi = bf16(v), mid = bf16(v - hi)(, lo) and the kernels sum the plane-pair products
+                       hi*hi + hi*mid + mid*hi (+ mid*mid + hi*lo + lo*hi) in their f32 accumulators: the reference's
+                       fp32 F.conv2d arithmetic to ~2^-16 (2^-24 with three planes) per product ON TENSOR CORES.
+                       Outputs are f32 channels-last.  `set_split_planes(2|3)` picks the plane count.
+
 Reference call sites replaced: F.conv2d / F.conv_transpose2d in model_spatial_query.py:177-183,318,327,333
 and their autograd gradients.
 """
@@ -25,6 +33,51 @@ from . import lib
 
 def _pad8(c):
     return (c + 7) // 8 * 8
+
+
+_SPLIT_PLANES = 2
+
+
+def set_split_planes(n):
+    """Planes used for f32 activations: 2 (three products, ~2^-16 per product: end-to-end image error ~2e-4 at 256^2,
+    inside the 1e-3 parity bar) or 3 (six products, f32-exact to rounding noise)."""
+    global _SPLIT_PLANES
+    if n not in (2, 3):
+        raise ValueError("split planes must be 2 or 3")
+    _SPLIT_PLANES = n
+
+
+def get_split_planes():
+    return _SPLIT_PLANES
+
+
+def nseg_for(x):
+    """Operand planes the kernels use for activations of x's dtype."""
+    return _SPLIT_PLANES if x.dtype == torch.float32 else 1
+
+
+def split_planes(x, nseg, scale=None):
+    """f32 [B, C, H, W] (any layout) -> bf16 planes [nseg, B, H, W, C] of x (* scale[b, c] when given)."""
+    lib.require_cuda(x, scale)
+    x = x.contiguous(memory_format=torch.channels_last)
+    b, c, h, w = x.shape
+    if c % 8:
+        raise RuntimeError("tensor-core conv needs channel counts that are multiples of 8 (got %d)" % c)
+    out = torch.empty((nseg, b, h, w, c), dtype=torch.bfloat16, device=x.device)
+    sf = None if scale is None else scale.to(torch.float32).contiguous()
+    lib.split_bf16(out, x, sf, b, h * w, c, nseg)
+    return out
+
+
+def _split_torch(v, nseg):
+    """f32 tensor -> stacked bf16 planes [nseg, ...] with torch ops (small per-sample weight tensors)."""
+    planes, r = [], v
+    for i in range(nseg):
+        h = r.to(torch.bfloat16)
+        planes.append(h)
+        if i + 1 < nseg:
+            r = r - h.float()
+    return torch.stack(planes)
 
 
 class Mode:
@@ -113,30 +166,32 @@ class PackCache:
             if len(shape) == 4 and shape[2] == shape[3] and shape[2] in (1, 3) and p.dtype == torch.float32:
                 self._registered[p.data_ptr()] = shape
 
-    def lookup(self, w, transposed, scale):
+    def lookup(self, w, transposed, scale, nseg=1):
         if w.dim() != 4 or self._registered.get(w.data_ptr()) != tuple(w.shape) or not w.is_contiguous():
             return None
-        key = (w.data_ptr(), float(scale))
+        key = (w.data_ptr(), float(scale), int(nseg))
         e = self._entries.get(key)
         if e is None:
             e = self._entries[key] = [w.detach(), None, None, w._version]
         slot = 2 if transposed else 1
+        stale = e[3] != w._version
         if e[slot] is None:
             o, i, k, _ = w.shape
             po, pi = _pad8(o), _pad8(i)
-            e[slot] = torch.zeros((k * k, pi, po) if transposed else (k * k, po, pi), dtype=torch.bfloat16,
-                                  device=w.device)
-            lib.pack_weights_tc([(e[0], None if transposed else e[1], e[2] if transposed else None, float(scale))])
-        elif e[3] != w._version:
-            # changed through torch (load_state_dict, copy_, a torch optimiser): those bump the version counter;
-            # the trainer's own fused Adam writes through raw pointers and calls refresh() instead
-            lib.pack_weights_tc([(e[0], e[1], e[2], float(scale))])
+            shape = (k * k, pi, po) if transposed else (k * k, po, pi)
+            e[slot] = torch.zeros(shape if nseg == 1 else (nseg,) + shape, dtype=torch.bfloat16, device=w.device)
+            stale = True
+        if stale:
+            # new slot, or the weight changed through torch (load_state_dict, copy_, a torch optimiser: those bump the
+            # version counter; the trainer's own fused Adam writes through raw pointers and calls refresh() instead):
+            # re-pack EVERY existing orientation, so that none is left behind a matching version number
+            lib.pack_weights_tc([(e[0], e[1], e[2], float(scale), int(nseg))])
         e[3] = w._version
         return e[slot]
 
     def refresh(self, lo=None, hi=None):
         """Re-pack every stored copy (of the weights whose storage lies in [lo, hi) when given): one launch per 64."""
-        tasks = [(e[0], e[1], e[2], key[1]) for key, e in self._entries.items()
+        tasks = [(e[0], e[1], e[2], key[1], key[2]) for key, e in self._entries.items()
                  if (lo is None or lo <= key[0] < hi) and (e[1] is not None or e[2] is not None)]
         lib.pack_weights_tc(tasks)
 
@@ -150,12 +205,14 @@ def set_pack_cache(cache):
     _PACK_CACHE = cache
 
 
-def pack_weight(w, transposed, scale=1.0):
+def pack_weight(w, transposed, scale=1.0, nseg=1):
     """Master weight [O, I, K, K] (f32) times `scale` -> bf16 slices [K*K, Cout, Cin] (Cin contiguous), channel
     counts padded to multiples of 8 with zeros.  A leading batch dimension ([B, O, I, K, K] ->
-    [B, K*K, Cout, Cin]) gives per-sample weights."""
+    [B, K*K, Cout, Cin]) gives per-sample weights.  nseg = 2 or 3: split-operand planes, stacked in front
+    ([nseg, K*K, Cout, Cin] / [nseg, B, K*K, Cout, Cin])."""
+    lib.require_cuda(w)
     if _PACK_CACHE is not None and w.dim() == 4:
-        hit = _PACK_CACHE.lookup(w, transposed, scale)
+        hit = _PACK_CACHE.lookup(w, transposed, scale, nseg)
         if hit is not None:
             return hit
     if w.dim() == 5:
@@ -165,8 +222,19 @@ def pack_weight(w, transposed, scale=1.0):
         if transposed:
             w = w.transpose(1, 2)
             o, i = i, o
+        if nseg > 1:
+            v = (w.detach().to(torch.float32) * scale).permute(0, 3, 4, 1, 2).reshape(b, k * k, o, i)
+            return _split_torch(v, nseg)
         out = torch.empty((b, k * k, o, i), dtype=torch.bfloat16, device=w.device)
         _scaled_copy(out.view(b, k, k, o, i), w.permute(0, 3, 4, 1, 2), scale)
+        return out
+    if nseg > 1:  # one table-driven launch writes the planes of either orientation
+        o, i, k, _ = w.shape
+        po, pi = _pad8(o), _pad8(i)
+        out = torch.zeros((nseg, k * k, pi, po) if transposed else (nseg, k * k, po, pi), dtype=torch.bfloat16,
+                          device=w.device)
+        src = w.detach().to(torch.float32).contiguous()
+        lib.pack_weights_tc([(src, None if transposed else out, out if transposed else None, float(scale), nseg)])
         return out
     o, i, k, _ = w.shape
     if transposed:
@@ -180,7 +248,7 @@ def pack_weight(w, transposed, scale=1.0):
 
 
 def _desc(x, cout, hout, wout, launch, w_slices, act=0, out_f32=0, per_sample=False, act_gain=0.0,
-          wgrad_alpha=0.0, residual=None, slope=None):
+          wgrad_alpha=0.0, residual=None, slope=None, split=1):
     taps, ist, ost, oy, ox, gh, gw = launch
     b, cin, hin, win = x.shape
     d = lib.TcConvDesc()
@@ -197,63 +265,80 @@ def _desc(x, cout, hout, wout, launch, w_slices, act=0, out_f32=0, per_sample=Fa
     d.act_gain, d.wgrad_alpha = act_gain, wgrad_alpha
     d.residual = residual.data_ptr() if residual is not None else None
     d.slope = slope.data_ptr() if slope is not None else None
+    d.split = split
     d.py_refs = (residual, slope)  # keeps the two tensors alive for the launch (and lets tests/emu.py read them)
     return d
 
 
-def _cl_bf16(x):
-    if x.dtype != torch.bfloat16:
-        raise TypeError("tensor-core conv needs bf16 activations, got %s" % x.dtype)
+def _cl_act(x):
+    """Activations for the kernels: (operand tensor, nseg).  bf16 -> the channels-last tensor itself, 1;
+    f32 -> its split-operand planes [nseg, B, H, W, C], nseg."""
+    if x.dtype not in (torch.bfloat16, torch.float32):
+        raise TypeError("tensor-core conv needs bf16 or f32 activations, got %s" % x.dtype)
     if x.shape[1] % 8:
         raise RuntimeError("tensor-core conv needs channel counts that are multiples of 8 (got %d)" % x.shape[1])
-    return x.contiguous(memory_format=torch.channels_last)
+    if x.dtype == torch.float32:
+        return split_planes(x, _SPLIT_PLANES), _SPLIT_PLANES
+    return x.contiguous(memory_format=torch.channels_last), 1
 
 
-def conv_raw(x, wp, mode, out_scale=None, bias=None, act=False, act_gain=0.0, residual=None, slope=None):
-    """x [B, Cin, H, W] bf16 channels-last, wp = pack_weight(...).  Returns bf16 channels-last:
-    act(conv * out_scale + bias) * act_gain + residual.  act: False/0, True/1 = leaky 0.2 (gain sqrt 2 by default),
-    2 = leaky 0.01 (gain 1 by default), 3 = PReLU with the f32 per-channel `slope` [Cout]."""
-    lib.require_cuda(x, wp, out_scale, bias, residual, slope)
+def conv_raw(x, wp, mode, out_scale=None, bias=None, act=False, act_gain=0.0, residual=None, slope=None,
+             in_scale=None):
+    """x [B, Cin, H, W] bf16 (or f32: split-operand mode) channels-last, wp = pack_weight(..., nseg=nseg_for(x)).
+    Returns a channels-last tensor of x's dtype: act(conv * out_scale + bias) * act_gain + residual.
+    act: False/0, True/1 = leaky 0.2 (gain sqrt 2 by default), 2 = leaky 0.01 (gain 1 by default), 3 = PReLU with the
+    f32 per-channel `slope` [Cout].  in_scale [B, Cin] (f32 activations only): x is modulated while it is split."""
+    lib.require_cuda(x, wp, out_scale, bias, residual, slope, in_scale)
     if (int(act) == 3) != (slope is not None):
         raise RuntimeError("conv_tc: act=3 (PReLU) and `slope` go together")
     if slope is not None:
         slope = slope.to(torch.float32).contiguous()
-    x = _cl_bf16(x)
     b, cin, hin, win = x.shape
-    per_sample = wp.dim() == 4
+    dtype = x.dtype
+    if in_scale is not None:
+        if dtype != torch.float32:
+            raise RuntimeError("conv_tc: in_scale is fused into the f32 operand split only")
+        xo, nseg = split_planes(x, _SPLIT_PLANES, in_scale), _SPLIT_PLANES
+    else:
+        xo, nseg = _cl_act(x)
+    per_sample = wp.dim() == (4 if nseg == 1 else 5)
+    if wp.dim() not in ((3, 4) if nseg == 1 else (4, 5)) or (nseg > 1 and wp.shape[0] != nseg):
+        raise RuntimeError("conv_tc: weight %s was not packed for %d operand plane(s)" % (tuple(wp.shape), nseg))
     cout = wp.shape[-2]
-    if wp.shape[-1] != cin or (per_sample and wp.shape[0] != b):
+    if wp.shape[-1] != cin or (per_sample and wp.shape[-4] != b):
         raise RuntimeError("conv_tc: weight %s does not match activations %s" % (tuple(wp.shape), tuple(x.shape)))
     hout, wout = mode.output_hw(hin, win)
-    y = torch.empty((b, cout, hout, wout), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+    y = torch.empty((b, cout, hout, wout), dtype=dtype, device=x.device, memory_format=torch.channels_last)
     if residual is not None:
-        if residual.shape != y.shape or residual.dtype != torch.bfloat16 or not mode.covers_output():
-            raise RuntimeError("conv_tc: residual must be bf16 of the output's shape %s" % (tuple(y.shape),))
+        if residual.shape != y.shape or residual.dtype != dtype or not mode.covers_output():
+            raise RuntimeError("conv_tc: residual must be %s of the output's shape %s" % (dtype, tuple(y.shape)))
         residual = residual.contiguous(memory_format=torch.channels_last)
     if not mode.covers_output():
         y.zero_()
     f32 = lambda t: None if t is None else t.to(torch.float32).contiguous()  # noqa: E731
     osc, bi = f32(out_scale), f32(bias)
     for launch in mode.launches(hin, win, hout, wout):
-        lib.conv_tc(y, x, wp, osc, bi, _desc(x, cout, hout, wout, launch, wp.shape[-3], int(act),
-                                             per_sample=per_sample, act_gain=act_gain, residual=residual,
-                                             slope=slope))
+        lib.conv_tc(y, xo, wp, osc, bi, _desc(x, cout, hout, wout, launch, wp.shape[-3], int(act),
+                                              out_f32=int(dtype == torch.float32), per_sample=per_sample,
+                                              act_gain=act_gain, residual=residual, slope=slope, split=nseg))
     return y
 
 
 def wgrad_raw(g, x, mode, w_shape, scale=1.0):
     """Gradient w.r.t. the master weight [O, I, K, K] (f32) of y = conv(x, W * scale; mode) given g = dL/dy."""
     lib.require_cuda(g, x)
-    g, x = _cl_bf16(g), _cl_bf16(x)
+    if g.dtype != x.dtype:
+        g = g.to(x.dtype)
     b, cin, hin, win = x.shape
     cout, hout, wout = g.shape[1], g.shape[2], g.shape[3]
+    (go, nseg), (xo, _) = _cl_act(g), _cl_act(x)
     k = mode.k
     per_sample = len(w_shape) == 5
     shape = (b, k * k, cout, cin) if per_sample else (k * k, cout, cin)
     gw = torch.zeros(shape, dtype=torch.float32, device=x.device)
     for launch in mode.launches(hin, win, hout, wout):
-        lib.conv_wgrad_tc(gw, g, x, _desc(x, cout, hout, wout, launch, k * k, per_sample=per_sample,
-                                          wgrad_alpha=scale))
+        lib.conv_wgrad_tc(gw, go, xo, _desc(x, cout, hout, wout, launch, k * k, per_sample=per_sample,
+                                            wgrad_alpha=scale, split=nseg))
     o, i = w_shape[-4], w_shape[-3]
     if per_sample:
         if mode.transposed:
@@ -272,7 +357,7 @@ class TcConv(Function):
     def forward(ctx, x, w, mode, wscale=1.0):
         ctx.save_for_backward(x, w)
         ctx.mode, ctx.wscale = mode, wscale
-        return conv_raw(x, pack_weight(w, mode.transposed, wscale), mode)
+        return conv_raw(x, pack_weight(w, mode.transposed, wscale, nseg_for(x)), mode)
 
     @staticmethod
     def backward(ctx, gy):
@@ -321,7 +406,7 @@ class TcConvBiasAct(Function):
     def forward(ctx, x, w, bias, mode, wscale=1.0, gain=2 ** 0.5):
         if not gain > 0:
             raise ValueError("TcConvBiasAct: the gain must be positive (the backward mask is the output's sign)")
-        out = conv_raw(x, pack_weight(w, mode.transposed, wscale), mode, bias=bias, act=True, act_gain=gain)
+        out = conv_raw(x, pack_weight(w, mode.transposed, wscale, nseg_for(x)), mode, bias=bias, act=True, act_gain=gain)
         ctx.save_for_backward(x, w, out)
         ctx.mode, ctx.wscale, ctx.gain = mode, wscale, gain
         ctx.bias_dtype = bias.dtype
@@ -353,7 +438,7 @@ class TcConvBiasActCarry(Function):
     def forward(ctx, x, w, bias, mode, wscale=1.0, gain=2 ** 0.5):
         if not gain > 0:
             raise ValueError("TcConvBiasActCarry: the gain must be positive")
-        out = conv_raw(x, pack_weight(w, mode.transposed, wscale), mode, bias=bias, act=True, act_gain=gain)
+        out = conv_raw(x, pack_weight(w, mode.transposed, wscale, nseg_for(x)), mode, bias=bias, act=True, act_gain=gain)
         ctx.save_for_backward(x, w, out)
         ctx.mode, ctx.wscale, ctx.gain = mode, wscale, gain
         ctx.bias_dtype = bias.dtype
@@ -371,7 +456,7 @@ class TcConvBiasActCarry(Function):
         if ctx.needs_input_grad[0]:
             adj = mode.adjoint((x.shape[2], x.shape[3]))
             fusable = (g_alias is not None and adj.covers_output() and w.shape[-3] % 8 == 0
-                       and g_alias.dtype == torch.bfloat16)
+                       and g_alias.dtype == g_y.dtype)
             if fusable:
                 gx = TcConvResidual.apply(g_y, w, g_alias, adj, wscale)
             else:
@@ -393,7 +478,7 @@ class TcConvResidual(Function):
     def forward(ctx, x, w, residual, mode, wscale=1.0):
         ctx.save_for_backward(x, w)
         ctx.mode, ctx.wscale = mode, wscale
-        return conv_raw(x, pack_weight(w, mode.transposed, wscale), mode, residual=residual)
+        return conv_raw(x, pack_weight(w, mode.transposed, wscale, nseg_for(x)), mode, residual=residual)
 
     @staticmethod
     def backward(ctx, gy):
