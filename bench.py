@@ -125,6 +125,8 @@ class KernelMeter:
             return flops, byts
         if name in ("scale_bc", "dot_bc"):
             return 0.0, 2.0 * args[1].numel() * es(args[1])
+        if name == "split_bf16":
+            return 0.0, float(args[1].numel() * 4 + args[0].numel() * 2)
         if name == "fused_bias_act":
             return 0.0, 2.0 * args[1].numel() * es(args[1])
         if name == "fused_bias_act_bwd":
@@ -145,7 +147,7 @@ class KernelMeter:
         from transeditor_b200 import lib
         for name in ("fused_bias_act", "fused_bias_act_bwd", "upfirdn2d", "conv2d_simt",
                      "conv2d_wgrad_simt", "adam_ema", "attn_core", "conv2d_tc", "conv_tc",
-                     "conv_wgrad_tc", "scale_bc", "dot_bc", "attn_stack_fwd", "attn_stack_bwd"):
+                     "conv_wgrad_tc", "scale_bc", "dot_bc", "attn_stack_fwd", "attn_stack_bwd", "split_bf16"):
             fn = getattr(lib, name)
             self._saved[name] = fn
 
@@ -380,8 +382,8 @@ def run_ours(args, rank, local_rank, world):
     if args.shapes_out and rank == 0:
         rows = sorted(meter.shapes.items(), key=lambda kv: -kv[1][1])
         with open(args.shapes_out, "w") as f:
-            for tag, (n, ms, fl) in rows:
-                f.write("%-78s n=%3d  %8.3f ms  %7.1f TFLOP/s\n" % (tag, n, ms, fl / ms / 1e9 if ms > 0 else 0))
+            for tag, (n, tag_ms, fl) in rows:
+                f.write("%-78s n=%3d  %8.3f ms  %7.1f TFLOP/s\n" % (tag, n, tag_ms, fl / tag_ms / 1e9 if tag_ms > 0 else 0))
 
     images = args.steps * cfg.batch * world
     line = {"metric": METRIC, "value": round(images / (ms * 1e-3), 3), "unit": UNIT, "n_gpus": world,

@@ -193,8 +193,9 @@ _PAIRS = {1: [(0, 0)], 2: [(0, 0), (0, 1), (1, 0)], 3: [(0, 0), (0, 1), (1, 0), 
 def _act_planes(x, nseg):
     """Activation operand -> list of f32 [B, C, H, W] planes (plain bf16 tensor, or split planes [S, B, H, W, C])."""
     if nseg == 1:
+        assert x.is_contiguous(memory_format=torch.channels_last) or x.is_contiguous(), "kernel reads dense NHWC"
         return [x.float()]
-    assert x.dim() == 5 and x.shape[0] == nseg and x.dtype == torch.bfloat16
+    assert x.dim() == 5 and x.shape[0] == nseg and x.dtype == torch.bfloat16 and x.is_contiguous()
     return [x[i].permute(0, 3, 1, 2).float() for i in range(nseg)]
 
 
@@ -215,6 +216,7 @@ def conv_tc(y, x, w, out_scale, bias, desc):
     d = desc
     nseg = d.split if d.split >= 2 else 1
     xs = _act_planes(x, nseg)
+    assert w.is_contiguous(), "the kernel addresses the packed weights as a dense array"
     per_sample = d.w_bstride != 0
     wshape = (d.batch, d.w_slices, d.cout, d.cin) if per_sample else (d.w_slices, d.cout, d.cin)
     ws = [w.float().reshape(wshape)] if nseg == 1 else [w[i].float().reshape(wshape) for i in range(nseg)]

@@ -156,9 +156,10 @@ def test_upfirdn2d_matches_oracle(dtype, case, cl):
     assert (y.double().cpu() - ref).abs().max().item() <= tol * max(1.0, ref.abs().max().item())
 
 
-@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
 @pytest.mark.parametrize("case", [
-    # (n, c, h, w, pad, fir) — large 16-bit channels-last inputs take the TMA-staged kernel (>= 2^20 outputs, c % 64 == 0)
+    # (n, c, h, w, pad, fir) — large channels-last inputs take the TMA-staged kernel (>= 2^20 outputs, c % 64 == 0;
+    # f32: 32-channel chunks, the fp32 parity mode's layout)
     (2, 128, 65, 67, (1, 1), "sep"), (1, 64, 129, 129, (2, 2), "sep"), (1, 192, 80, 96, (2, 1), "sep"),
     (2, 64, 97, 100, (-1, 2), "sep"), (1, 128, 257, 36, (1, 1), "sep"), (3, 64, 90, 70, (2, 2), "full"),
     (1, 128, 100, 90, (1, 1), "k3"), (1, 64, 300, 60, (0, 0), "sep"), (1, 64, 20, 900, (2, 2), "sep"),
@@ -177,13 +178,13 @@ def test_upfirdn2d_tma_staged_channels_last(dtype, case):
     assert y.is_contiguous(memory_format=torch.channels_last)
     ref = ops_cpu.upfirdn2d(x.double(), fir.double(), 1, 1, pad)
     assert y.shape == ref.shape and y.numel() >= 1 << 20
-    tol = {torch.float16: 2e-3, torch.bfloat16: 1.6e-2}[dtype]
+    tol = {torch.float16: 2e-3, torch.bfloat16: 1.6e-2, torch.float32: 2e-6}[dtype]
     assert (y.double().cpu() - ref).abs().max().item() <= tol * max(1.0, ref.abs().max().item())
 
 
-@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
 @pytest.mark.parametrize("case", [
-    # (n, c, h, w, up, down, pad, fir): 16-bit channels-last factor-2 resampling on the TMA-staged kernels
+    # (n, c, h, w, up, down, pad, fir): channels-last factor-2 resampling on the TMA-staged kernels
     (2, 64, 64, 64, 1, 2, (1, 1), "sep"), (1, 128, 33, 70, 1, 2, (1, 1), "sep"), (1, 64, 40, 36, 1, 2, (2, 2), "sep"),
     (2, 64, 40, 40, 1, 2, (0, 0), "full"), (1, 64, 90, 50, 1, 2, (-1, 2), "sep"), (4, 64, 16, 16, 1, 2, (1, 1), "sep"),
     (2, 64, 32, 32, 2, 1, (2, 1), "sep"), (1, 64, 31, 45, 2, 1, (2, 1), "sep"), (1, 128, 40, 40, 2, 1, (1, 1), "sep"),
@@ -203,7 +204,7 @@ def test_upfirdn2d_tma_resample_channels_last(dtype, case):
     y = upfirdn2d(x.to(DEV).contiguous(memory_format=torch.channels_last), fir.to(DEV), up=up, down=down, pad=pad)
     ref = ops_cpu.upfirdn2d(x.double(), fir.double(), up, down, pad)
     assert y.shape == ref.shape and y.is_contiguous(memory_format=torch.channels_last)
-    tol = {torch.float16: 2e-3, torch.bfloat16: 1.6e-2}[dtype]
+    tol = {torch.float16: 2e-3, torch.bfloat16: 1.6e-2, torch.float32: 2e-6}[dtype]
     assert (y.double().cpu() - ref).abs().max().item() <= tol * max(1.0, ref.abs().max().item())
 
 

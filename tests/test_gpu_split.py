@@ -2,7 +2,7 @@
 te_pack_weights_tc against an f64 torch convolution of the SAME f32 operands.
 
 Bars (stated per test): 2 planes = 3 products, each product exact to ~2^-16 -> max-abs error <= 6e-5 of the
-output's scale (K-term random sums); 3 planes = 6 products -> f32 rounding noise (<= 2e-6)."""
+output's scale (K-term random sums); 3 planes = 6 products -> the f32 accumulator's own rounding (<= 1e-5)."""
 import pytest
 import torch
 import torch.nn.functional as F
@@ -32,7 +32,7 @@ def test_split_planes_reconstruct_the_input():
     from transeditor_b200 import tc
     x = _cl(_randn(3, 24, 9, 7, seed=1) * 37.5)
     s = _randn(3, 24, seed=2)
-    for nseg, tol in ((1, 2 ** -8), (2, 2 ** -16), (3, 2 ** -23)):
+    for nseg, tol in ((1, 2 ** -8), (2, 2 ** -16), (3, 2 ** -22)):
         pl = tc.split_planes(x, nseg)
         assert pl.shape == (nseg, 3, 9, 7, 24) and pl.dtype == torch.bfloat16
         rec = pl.float().sum(0).permute(0, 3, 1, 2)
@@ -53,7 +53,7 @@ def _ref(x, w, kind, k):
     return F.conv_transpose2d(x, w.transpose(0, 1), stride=2)
 
 
-@pytest.mark.parametrize("nseg,tol", [(2, 6e-5), (3, 2e-6)])
+@pytest.mark.parametrize("nseg,tol", [(2, 6e-5), (3, 1e-5)])
 @pytest.mark.parametrize("kind,k,b,cin,cout,h", [
     ("s1", 3, 2, 64, 128, 32), ("s1", 1, 2, 72, 8, 16), ("down", 3, 2, 128, 64, 33), ("up", 3, 2, 64, 64, 16),
     ("s1", 3, 4, 128, 128, 64),      # enough tiles for the 2-CTA kernel

@@ -151,7 +151,7 @@ def test_bf16_trainer_steps_with_the_weight_repack_cache(bf16_mode):
     for cached in (True, False):
         tr = Trainer(TrainConfig(size=32, batch=4), "cpu", seed=0)
         if not cached:
-            tc.set_pack_cache(None)
+            tr._packs = tc.PackCache()  # nothing registered: every lookup misses
         for _ in range(2):
             tr.step(real)
         assert torch.isfinite(tr.g_flat.data).all() and torch.isfinite(tr.d_flat.data).all()

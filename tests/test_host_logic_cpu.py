@@ -178,3 +178,64 @@ def test_spatial_path_regulariser_matches_reference(space):
             assert np.abs(got - val).max() < 2e-3 * max(1.0, float(np.abs(val).max())), key
             seen += 1
     assert seen >= 4
+
+
+def test_path_regulariser_steps_rgb_biases_like_torch_adam(cpu_emulation):
+    """the reference adds `0 * fake_img[0,0,0,0]` to the path penalty (train_spatial_query.py:240-243), so
+    the to_rgb biases get a ZERO gradient (not None) and torch.optim.Adam steps them: step += 1, exp_avg_sq *= beta2,
+    parameter unchanged (beta1 = 0).  g_step -> g_regularize -> g_step must reproduce that bookkeeping; the noise
+    strengths (grad None in the reference) stay untouched."""
+    from transeditor_b200.train_step import TrainConfig, Trainer
+    tr = Trainer(TrainConfig(size=32, batch=4), "cpu", seed=0)
+    flat, opt = tr.g_flat, tr.g_optim
+    lo, hi = flat.group_end[0], flat.group_end[1]          # group 1 = the to_rgb biases
+    assert hi - lo >= 4 * 3 and flat.group_end[2] > hi     # 4-aligned slots of 3 values; group 2 = noise strengths
+    tr.g_step()
+    assert int(opt.steps[0]) == 1 and int(opt.steps[1]) == 1 and int(opt.steps[2]) == 0
+    p1, v1 = flat.data[lo:hi].clone(), opt.v[lo:hi].clone()
+    assert v1.abs().sum() > 0
+    tr.g_regularize()
+    assert int(opt.steps[0]) == 2 and int(opt.steps[1]) == 2 and int(opt.steps[2]) == 0
+    assert torch.equal(flat.data[lo:hi], p1)                              # zero gradient, beta1 = 0: no move
+    assert torch.allclose(opt.v[lo:hi], v1 * opt.betas[1], rtol=1e-6)     # second moment decays
+    # reference run of the same three updates on one bias with torch.optim.Adam
+    name = next(n for n, _ in flat.params if n == "to_rgb1.bias")
+    o = flat.offsets[name]
+    g1 = None
+    ref_p = torch.nn.Parameter(torch.zeros(3))
+    ref_opt = torch.optim.Adam([ref_p], lr=opt.lr, betas=opt.betas, eps=opt.eps)
+    v_after_1 = opt.v[o:o + 3].clone() / opt.betas[1]   # undo the decay of the regulariser step
+    g1 = (v_after_1 / (1 - opt.betas[1])).sqrt()          # |g| of the first step (first moment of g^2)
+    ref_p.grad = g1.clone()
+    ref_opt.step()
+    ref_p.grad = torch.zeros(3)
+    ref_opt.step()
+    st = ref_opt.state[ref_p]
+    assert int(st["step"]) == 2
+    assert torch.allclose(st["exp_avg_sq"], opt.v[o:o + 3], rtol=1e-5, atol=1e-20)
+    tr.g_step()
+    assert int(opt.steps[1]) == 3 and int(opt.steps[2]) == 0
+
+
+def test_ema_rides_in_the_last_generator_update(cpu_emulation):
+    """step() fuses accumulate(g_ema, g, decay) (train_spatial_query.py:56-61,294) into the optimiser launch of the
+    iteration's LAST generator phase: same numbers as the stand-alone pass."""
+    from transeditor_b200.train_step import TrainConfig, Trainer
+    real = torch.rand(4, 3, 32, 32, generator=torch.Generator().manual_seed(1)) * 2 - 1
+    a = Trainer(TrainConfig(size=32, batch=4), "cpu", seed=0)
+    b = Trainer(TrainConfig(size=32, batch=4), "cpu", seed=0)
+    for it in range(2):   # iteration 0 ends with the path regulariser, iteration 1 with the plain G step
+        torch.manual_seed(77 + it)
+        a.step(real)
+        torch.manual_seed(77 + it)
+        b.d_step(real)
+        if it % 16 == 0:
+            b.d_regularize(real)
+        b.g_step()
+        if it % 4 == 0:
+            b.g_regularize()
+        b.ema_update()
+        b.iteration += 1
+    assert torch.equal(a.g_flat.data, b.g_flat.data)
+    assert torch.allclose(a.ema_flat.data, b.ema_flat.data, rtol=1e-6, atol=1e-7)
+    assert not torch.equal(a.ema_flat.data, a.g_flat.data)

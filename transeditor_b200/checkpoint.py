@@ -86,11 +86,34 @@ def save_checkpoint(trainer, path):
     torch.save(checkpoint_dict(trainer), path)
 
 
-def load_checkpoint(trainer, path_or_dict, strict=True):
+def iteration_from_name(path):
+    """The reference derives the start iteration from the file name (`790000.pt` -> 790000,
+    train_spatial_query.py:478-483); None when the name is not a number."""
+    import os
+    stem = os.path.splitext(os.path.basename(str(path)))[0]
+    try:
+        return int(stem)
+    except ValueError:
+        return None
+
+
+def load_checkpoint(trainer, path_or_dict, strict=True, iteration=None):
     """Resume from a reference-format checkpoint (ours or the authors').  Parameters are copied IN PLACE into the
     flat buffers (captured CUDA graphs stay valid).  Files without optimiser state (the released inference
-    checkpoints hold only 'g_ema') load the networks and leave the optimisers untouched."""
-    ckpt = path_or_dict if isinstance(path_or_dict, dict) else torch.load(path_or_dict, map_location="cpu")
+    checkpoints hold only 'g_ema') load the networks and leave the optimisers untouched.
+
+    The file is read with `weights_only=True` (tensors, dicts and numbers only: a third-party checkpoint cannot run
+    pickle code).  `trainer.iteration` — which drives the d_reg / g_reg cadence — is set from `iteration`, else from
+    the file name like the reference does, else left alone.  `mean_path_length` is not part of the reference's
+    checkpoint and restarts at zero there too."""
+    if isinstance(path_or_dict, dict):
+        ckpt = path_or_dict
+    else:
+        ckpt = torch.load(path_or_dict, map_location="cpu", weights_only=True)
+        if iteration is None:
+            iteration = iteration_from_name(path_or_dict)
+    if iteration is not None:
+        trainer.iteration = int(iteration)
     if "g" in ckpt:
         trainer.generator.load_state_dict(ckpt["g"], strict=strict)
     if "d" in ckpt:

@@ -178,9 +178,9 @@ inline int encode_map_bf16(CUtensorMap* map, const void* base, int rank, const u
   return TE_OK;
 }
 
-// 16-bit elements moved as raw words, NO swizzle (rows of the box land back to back in shared memory), zero fill
-inline int encode_map_u16_linear(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
-                                 const uint64_t* strides_bytes, const uint32_t* box) {
+// 16-bit / 32-bit elements moved as raw words, NO swizzle (rows of the box land back to back in shared memory), zero fill
+inline int encode_map_linear(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                             const uint64_t* strides_bytes, const uint32_t* box, int elem_bytes) {
   auto fn = get_encode_fn();
   if (!fn) {
     set_error("TMA path: cuTensorMapEncodeTiled entry point unavailable");
@@ -188,7 +188,8 @@ inline int encode_map_u16_linear(CUtensorMap* map, const void* base, int rank, c
   }
   bind_primary_context();
   uint32_t ones[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, rank, const_cast<void*>(base), dims, strides_bytes, box, ones,
+  CUresult r = fn(map, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16, rank,
+                  const_cast<void*>(base), dims, strides_bytes, box, ones,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

@@ -560,6 +560,33 @@ template <> struct Unpack2<__half> {
   }
 };
 
+// One 16-byte vector of T as NQ packed float2 values: the TMA-staged kernels below are written over this view, so
+// that f32 tensors (a 128-byte channel chunk = 32 floats, 4 per thread) share the code of the 16-bit ones (64, 8).
+template <typename T> struct Pack16 {
+  static constexpr int NQ = 4;            // float2 per 16 bytes
+  static constexpr int ELEMS = 8;         // elements per 16 bytes
+  static constexpr int CHUNK = 64;        // elements per 128-byte channel chunk
+  static __device__ __forceinline__ float2 get(const uint4& r, int q) { return Unpack2<T>::get((&r.x)[q]); }
+  static __device__ __forceinline__ uint4 put(const float2* a) {
+    return make_uint4(Unpack2<T>::put(a[0]), Unpack2<T>::put(a[1]), Unpack2<T>::put(a[2]), Unpack2<T>::put(a[3]));
+  }
+};
+template <> struct Pack16<float> {
+  static constexpr int NQ = 2;
+  static constexpr int ELEMS = 4;
+  static constexpr int CHUNK = 32;
+  static __device__ __forceinline__ float2 get(const uint4& r, int q) {
+    return make_float2(__uint_as_float((&r.x)[2 * q]), __uint_as_float((&r.x)[2 * q + 1]));
+  }
+  static __device__ __forceinline__ uint4 put(const float2* a) {
+    return make_uint4(__float_as_uint(a[0].x), __float_as_uint(a[0].y), __float_as_uint(a[1].x), __float_as_uint(a[1].y));
+  }
+};
+template <typename T> struct IsTmaFir { static constexpr bool value = false; };
+template <> struct IsTmaFir<__nv_bfloat16> { static constexpr bool value = true; };
+template <> struct IsTmaFir<__half> { static constexpr bool value = true; };
+template <> struct IsTmaFir<float> { static constexpr bool value = true; };
+
 constexpr int F2_TY = 4;   // output rows per thread
 constexpr int F2_XW = 2;   // output columns per thread
 
@@ -761,7 +788,7 @@ fir_nhwc_tma_kernel(T* __restrict__ out, const __grid_constant__ CUtensorMap in_
     const int tx = int(r % t.tiles_x); r /= t.tiles_x;
     const int ty = int(r % t.tiles_y); r /= t.tiles_y;
     mbar_expect_tx(&full[s], stage_bytes);
-    tma_load_4d(stage0 + size_t(s) * stage_bytes, &in_map, &full[s], chunk * 64, tx * t.tw - p.pad_x0,
+    tma_load_4d(stage0 + size_t(s) * stage_bytes, &in_map, &full[s], chunk * Pack16<T>::CHUNK, tx * t.tw - p.pad_x0,
                 ty * t.th - p.pad_y0, int(r));
   };
   if (tid == 32) {
@@ -806,15 +833,15 @@ fir_nhwc_tma_kernel(T* __restrict__ out, const __grid_constant__ CUtensorMap in_
       const int ox0 = tx * t.tw + xp * F2_XW, oy0 = ty * t.th + strip * F2_TY;
       const uint8_t* src = stage0 + size_t(s) * stage_bytes +
                            (size_t(strip * F2_TY) * t.box_w + xp * F2_XW) * 128 + q8 * 16;
-      T* dst = out + ((r * p.out_h + oy0) * int64_t(p.out_w) + ox0) * p.minor + chunk * 64 + q8 * 8;
+      T* dst = out + ((r * p.out_h + oy0) * int64_t(p.out_w) + ox0) * p.minor + chunk * Pack16<T>::CHUNK + q8 * Pack16<T>::ELEMS;
       if (ox0 < p.out_w && oy0 < p.out_h) {
-        float2 acc[F2_TY][F2_XW][4];
+        float2 acc[F2_TY][F2_XW][Pack16<T>::NQ];
 #pragma unroll
         for (int a = 0; a < F2_TY; ++a)
 #pragma unroll
           for (int w = 0; w < F2_XW; ++w)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) acc[a][w][q] = make_float2(0.f, 0.f);
+            for (int q = 0; q < Pack16<T>::NQ; ++q) acc[a][w][q] = make_float2(0.f, 0.f);
         if (sep) {
 #pragma unroll
           for (int ry = 0; ry < F2_TY + 3; ++ry) {
@@ -822,12 +849,12 @@ fir_nhwc_tma_kernel(T* __restrict__ out, const __grid_constant__ CUtensorMap in_
 #pragma unroll
             for (int kx = 0; kx < 5; ++kx)
               raw[kx] = *reinterpret_cast<const uint4*>(src + (size_t(ry) * t.box_w + kx) * 128);
-            float2 h[F2_XW][4];
+            float2 h[F2_XW][Pack16<T>::NQ];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < Pack16<T>::NQ; ++q) {
               float2 v[5];
 #pragma unroll
-              for (int kx = 0; kx < 5; ++kx) v[kx] = Unpack2<T>::get((&raw[kx].x)[q]);
+              for (int kx = 0; kx < 5; ++kx) v[kx] = Pack16<T>::get(raw[kx], q);
 #pragma unroll
               for (int w = 0; w < F2_XW; ++w) {
                 float2 u = __fmul2_rn(v[w], r0);
@@ -845,7 +872,7 @@ fir_nhwc_tma_kernel(T* __restrict__ out, const __grid_constant__ CUtensorMap in_
 #pragma unroll
                 for (int w = 0; w < F2_XW; ++w)
 #pragma unroll
-                  for (int q = 0; q < 4; ++q) acc[a][w][q] = __ffma2_rn(h[w][q], ck, acc[a][w][q]);
+                  for (int q = 0; q < Pack16<T>::NQ; ++q) acc[a][w][q] = __ffma2_rn(h[w][q], ck, acc[a][w][q]);
               }
             }
           }
@@ -862,8 +889,8 @@ fir_nhwc_tma_kernel(T* __restrict__ out, const __grid_constant__ CUtensorMap in_
                   if (ky >= 0 && ky < 4 && kk >= 0 && kk < 4) {
                     const float2 tp = make_float2(sk[ky][kk], sk[ky][kk]);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                      acc[a][w][q] = __ffma2_rn(Unpack2<T>::get((&raw.x)[q]), tp, acc[a][w][q]);
+                    for (int q = 0; q < Pack16<T>::NQ; ++q)
+                      acc[a][w][q] = __ffma2_rn(Pack16<T>::get(raw, q), tp, acc[a][w][q]);
                   }
                 }
             }
@@ -874,12 +901,7 @@ fir_nhwc_tma_kernel(T* __restrict__ out, const __grid_constant__ CUtensorMap in_
 #pragma unroll
           for (int w = 0; w < F2_XW; ++w) {
             if (ox0 + w >= p.out_w) continue;
-            uint4 o;
-            o.x = Unpack2<T>::put(acc[a][w][0]);
-            o.y = Unpack2<T>::put(acc[a][w][1]);
-            o.z = Unpack2<T>::put(acc[a][w][2]);
-            o.w = Unpack2<T>::put(acc[a][w][3]);
-            *reinterpret_cast<uint4*>(dst + (int64_t(a) * p.out_w + w) * p.minor) = o;
+            *reinterpret_cast<uint4*>(dst + (int64_t(a) * p.out_w + w) * p.minor) = Pack16<T>::put(acc[a][w]);
           }
         }
       }
@@ -894,7 +916,7 @@ template <typename T>
 static int launch_fir_nhwc_tma(T* out, const T* in, const float* fir, const UpfirdnParams& p, cudaStream_t st,
                                int* status) {
   *status = TE_OK;
-  if constexpr (Is16<T>::value) {
+  if constexpr (IsTmaFir<T>::value) {
     FirTmaTiling t;
     const int nx = (p.out_w + 31) / 32;
     t.tw = (((p.out_w + nx - 1) / nx) + 1) & ~1;
@@ -909,17 +931,17 @@ static int launch_fir_nhwc_tma(T* out, const T* in, const float* fir, const Upfi
     t.box_h = t.th + 3;
     t.tiles_x = (p.out_w + t.tw - 1) / t.tw;
     t.tiles_y = (p.out_h + t.th - 1) / t.th;
-    t.chunks = p.minor / 64;
+    t.chunks = p.minor / Pack16<T>::CHUNK;
     t.jobs = int64_t(p.major) * t.tiles_y * t.tiles_x * t.chunks;
     const int threads = ((t.strips * t.xpairs * 8) + 31) / 32 * 32;
     const size_t smem = size_t(FIR_TMA_STAGES) * t.box_h * t.box_w * 128 + 128;
     if (threads < 64 || threads > FIR_TMA_MAX_THREADS || smem > 110 * 1024) return 0;
     CUtensorMap map;
     const uint64_t dims[4] = {uint64_t(p.minor), uint64_t(p.in_w), uint64_t(p.in_h), uint64_t(p.major)};
-    const uint64_t strides[3] = {uint64_t(p.minor) * 2, uint64_t(p.in_w) * p.minor * 2,
-                                 uint64_t(p.in_h) * p.in_w * p.minor * 2};
-    const uint32_t box[4] = {64, uint32_t(t.box_w), uint32_t(t.box_h), 1};
-    *status = encode_map_u16_linear(&map, in, 4, dims, strides, box);
+    const uint64_t strides[3] = {uint64_t(p.minor) * sizeof(T), uint64_t(p.in_w) * p.minor * sizeof(T),
+                                 uint64_t(p.in_h) * p.in_w * p.minor * sizeof(T)};
+    const uint32_t box[4] = {Pack16<T>::CHUNK, uint32_t(t.box_w), uint32_t(t.box_h), 1};
+    *status = encode_map_linear(&map, in, 4, dims, strides, box, int(sizeof(T)));
     if (*status != TE_OK) return 1;
     static bool attr_done = false;
     if (!attr_done) {
@@ -977,7 +999,7 @@ fir_nhwc_resample_tma_kernel(T* __restrict__ out, const __grid_constant__ CUtens
     const int tx = int(r % t.tiles_x); r /= t.tiles_x;
     const int ty = int(r % t.tiles_y); r /= t.tiles_y;
     mbar_expect_tx(&full[s], stage_bytes);
-    tma_load_4d(stage0 + size_t(s) * stage_bytes, &in_map, &full[s], chunk * 64,
+    tma_load_4d(stage0 + size_t(s) * stage_bytes, &in_map, &full[s], chunk * Pack16<T>::CHUNK,
                 t.org_x + tx * t.tw * IN_PER_OUT_NUM / IN_PER_OUT_DEN,
                 t.org_y + ty * t.th * IN_PER_OUT_NUM / IN_PER_OUT_DEN, int(r));
   };
@@ -1009,11 +1031,11 @@ fir_nhwc_resample_tma_kernel(T* __restrict__ out, const __grid_constant__ CUtens
         // thread: output column gx, output rows 2*gy, 2*gy+1 of the tile; window rows 4*gy .. 4*gy+5, cols 2*gx .. +3
         const int ox = tx * t.tw + gx, oy0 = ty * t.th + 2 * gy;
         if (ox < p.out_w && oy0 < p.out_h) {
-          float2 acc[2][4];
+          float2 acc[2][Pack16<T>::NQ];
 #pragma unroll
           for (int a = 0; a < 2; ++a)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) acc[a][q] = make_float2(0.f, 0.f);
+            for (int q = 0; q < Pack16<T>::NQ; ++q) acc[a][q] = make_float2(0.f, 0.f);
 #pragma unroll
           for (int rr = 0; rr < 6; ++rr) {
 #pragma unroll
@@ -1024,20 +1046,17 @@ fir_nhwc_resample_tma_kernel(T* __restrict__ out, const __grid_constant__ CUtens
                 const int ky = rr - 2 * a;
                 if (ky >= 0 && ky < 4) {
 #pragma unroll
-                  for (int q = 0; q < 4; ++q)
-                    acc[a][q] = __ffma2_rn(Unpack2<T>::get((&raw.x)[q]), wt[ky][kx], acc[a][q]);
+                  for (int q = 0; q < Pack16<T>::NQ; ++q)
+                    acc[a][q] = __ffma2_rn(Pack16<T>::get(raw, q), wt[ky][kx], acc[a][q]);
                 }
               }
             }
           }
-          T* dst = out + ((r * p.out_h + oy0) * int64_t(p.out_w) + ox) * p.minor + chunk * 64 + q8 * 8;
+          T* dst = out + ((r * p.out_h + oy0) * int64_t(p.out_w) + ox) * p.minor + chunk * Pack16<T>::CHUNK + q8 * Pack16<T>::ELEMS;
 #pragma unroll
           for (int a = 0; a < 2; ++a) {
             if (oy0 + a >= p.out_h) break;
-            uint4 o;
-            o.x = Unpack2<T>::put(acc[a][0]); o.y = Unpack2<T>::put(acc[a][1]);
-            o.z = Unpack2<T>::put(acc[a][2]); o.w = Unpack2<T>::put(acc[a][3]);
-            *reinterpret_cast<uint4*>(dst + int64_t(a) * p.out_w * p.minor) = o;
+            *reinterpret_cast<uint4*>(dst + int64_t(a) * p.out_w * p.minor) = Pack16<T>::put(acc[a]);
           }
         }
       } else {
@@ -1047,22 +1066,22 @@ fir_nhwc_resample_tma_kernel(T* __restrict__ out, const __grid_constant__ CUtens
         constexpr int E = MODE == 1 ? 0 : 1;
         const int ox0 = tx * t.tw + 2 * gx, oy0 = ty * t.th + 4 * gy;
         if (ox0 < p.out_w && oy0 < p.out_h) {
-          float2 acc[4][2][4];
+          float2 acc[4][2][Pack16<T>::NQ];
 #pragma unroll
           for (int a = 0; a < 4; ++a)
 #pragma unroll
             for (int w = 0; w < 2; ++w)
 #pragma unroll
-              for (int q = 0; q < 4; ++q) acc[a][w][q] = make_float2(0.f, 0.f);
+              for (int q = 0; q < Pack16<T>::NQ; ++q) acc[a][w][q] = make_float2(0.f, 0.f);
 #pragma unroll
           for (int rr = 0; rr < 4; ++rr) {
 #pragma unroll
             for (int cc = 0; cc < 3; ++cc) {
               if (E == 1 && cc == 2) continue;
               const uint4 raw = *reinterpret_cast<const uint4*>(tile + (size_t(2 * gy + rr) * t.box_w + gx + cc) * 128);
-              float2 v[4];
+              float2 v[Pack16<T>::NQ];
 #pragma unroll
-              for (int q = 0; q < 4; ++q) v[q] = Unpack2<T>::get((&raw.x)[q]);
+              for (int q = 0; q < Pack16<T>::NQ; ++q) v[q] = Pack16<T>::get(raw, q);
 #pragma unroll
               for (int a = 0; a < 4; ++a) {
                 const int pa = a & 1, h = a >> 1;
@@ -1075,22 +1094,19 @@ fir_nhwc_resample_tma_kernel(T* __restrict__ out, const __grid_constant__ CUtens
                   if (jx < 0 || jx > 1) continue;
                   const int kx = (E ^ w) + 2 * jx;
 #pragma unroll
-                  for (int q = 0; q < 4; ++q) acc[a][w][q] = __ffma2_rn(v[q], wt[ky][kx], acc[a][w][q]);
+                  for (int q = 0; q < Pack16<T>::NQ; ++q) acc[a][w][q] = __ffma2_rn(v[q], wt[ky][kx], acc[a][w][q]);
                 }
               }
             }
           }
-          T* dst = out + ((r * p.out_h + oy0) * int64_t(p.out_w) + ox0) * p.minor + chunk * 64 + q8 * 8;
+          T* dst = out + ((r * p.out_h + oy0) * int64_t(p.out_w) + ox0) * p.minor + chunk * Pack16<T>::CHUNK + q8 * Pack16<T>::ELEMS;
 #pragma unroll
           for (int a = 0; a < 4; ++a) {
             if (oy0 + a >= p.out_h) break;
 #pragma unroll
             for (int w = 0; w < 2; ++w) {
               if (ox0 + w >= p.out_w) continue;
-              uint4 o;
-              o.x = Unpack2<T>::put(acc[a][w][0]); o.y = Unpack2<T>::put(acc[a][w][1]);
-              o.z = Unpack2<T>::put(acc[a][w][2]); o.w = Unpack2<T>::put(acc[a][w][3]);
-              *reinterpret_cast<uint4*>(dst + (int64_t(a) * p.out_w + w) * p.minor) = o;
+              *reinterpret_cast<uint4*>(dst + (int64_t(a) * p.out_w + w) * p.minor) = Pack16<T>::put(acc[a][w]);
             }
           }
         }
@@ -1121,10 +1137,10 @@ template <typename T>
 static int launch_fir_nhwc_resample(T* out, const T* in, const float* fir, const UpfirdnParams& p, cudaStream_t st,
                                     int* status) {
   *status = TE_OK;
-  if constexpr (Is16<T>::value) {
+  if constexpr (IsTmaFir<T>::value) {
     const bool down2 = p.up_x == 1 && p.up_y == 1 && p.down_x == 2 && p.down_y == 2;
     const bool up2 = p.up_x == 2 && p.up_y == 2 && p.down_x == 1 && p.down_y == 1;
-    if (!(down2 || up2) || p.pad_x0 != p.pad_y0 || p.kh > 4 || p.kw > 4 || p.minor % 64 != 0) return 0;
+    if (!(down2 || up2) || p.pad_x0 != p.pad_y0 || p.kh > 4 || p.kw > 4 || p.minor % Pack16<T>::CHUNK != 0) return 0;
     FirResampleTiling t;
     int mode;
     if (down2) {
@@ -1147,15 +1163,15 @@ static int launch_fir_nhwc_resample(T* out, const T* in, const float* fir, const
     if (threads > 256 || t.tw < 2) return 0;
     t.tiles_x = (p.out_w + t.tw - 1) / t.tw;
     t.tiles_y = (p.out_h + t.th - 1) / t.th;
-    t.chunks = p.minor / 64;
+    t.chunks = p.minor / Pack16<T>::CHUNK;
     t.jobs = int64_t(p.major) * t.tiles_y * t.tiles_x * t.chunks;
     const size_t smem = size_t(FIR_TMA_STAGES) * t.box_h * t.box_w * 128 + 128;
     CUtensorMap map;
     const uint64_t dims[4] = {uint64_t(p.minor), uint64_t(p.in_w), uint64_t(p.in_h), uint64_t(p.major)};
-    const uint64_t strides[3] = {uint64_t(p.minor) * 2, uint64_t(p.in_w) * p.minor * 2,
-                                 uint64_t(p.in_h) * p.in_w * p.minor * 2};
-    const uint32_t box[4] = {64, uint32_t(t.box_w), uint32_t(t.box_h), 1};
-    *status = encode_map_u16_linear(&map, in, 4, dims, strides, box);
+    const uint64_t strides[3] = {uint64_t(p.minor) * sizeof(T), uint64_t(p.in_w) * p.minor * sizeof(T),
+                                 uint64_t(p.in_h) * p.in_w * p.minor * sizeof(T)};
+    const uint32_t box[4] = {Pack16<T>::CHUNK, uint32_t(t.box_w), uint32_t(t.box_h), 1};
+    *status = encode_map_linear(&map, in, 4, dims, strides, box, int(sizeof(T)));
     if (*status != TE_OK) return 1;
     if (mode == 0) return launch_resample_mode<T, 0>(out, map, fir, p, t, threads, smem, st);
     if (mode == 1) return launch_resample_mode<T, 1>(out, map, fir, p, t, threads, smem, st);
@@ -1185,7 +1201,7 @@ static int upfirdn2d_typed(void* out_, const void* in_, const float* fir, const 
       launch_fir_nhwc_resample<T>(out, in, fir, p, st, &tma_status)) {
     // 16-bit channels-last factor-2 resampling: TMA-staged kernel launched
     if (tma_status != TE_OK) return tma_status;
-  } else if (hot_cl && use_tma && p.minor % 64 == 0 && total >= (int64_t(1) << 20) &&
+  } else if (hot_cl && use_tma && p.minor % (128 / int(sizeof(T))) == 0 && total >= (int64_t(1) << 20) &&
       launch_fir_nhwc_tma<T>(out, in, fir, p, st, &tma_status)) {
     // 16-bit channels-last, large: TMA-staged kernel launched (or the tensor map could not be encoded)
     if (tma_status != TE_OK) return tma_status;

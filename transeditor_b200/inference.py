@@ -53,7 +53,10 @@ class GraphedGenerator:
     The first call runs three eager warm-up forwards (lazy initialisation), captures the graph and replays it;
     every later call costs two small copies into the static input buffers plus one graph launch.  Outputs are
     static buffers owned by the graph: `.clone()` what must outlive the next call.  Weights are read at replay
-    time, so in-place updates of the generator (EMA, load_state_dict) are picked up without re-capturing."""
+    time (the captured graph contains the f32 -> bf16 weight repack kernels), so in-place updates of the generator
+    (EMA, load_state_dict) are picked up without re-capturing — provided no tc.PackCache is installed while the
+    graph is captured (cached weight copies would be frozen into it; a Trainer's cache is only active inside the
+    trainer's own phases, see tc.use_pack_cache)."""
 
     def __init__(self, generator, batch, **flags):
         self.generator = generator

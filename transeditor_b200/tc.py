@@ -71,13 +71,13 @@ def split_planes(x, nseg, scale=None):
 
 def _split_torch(v, nseg):
     """f32 tensor -> stacked bf16 planes [nseg, ...] with torch ops (small per-sample weight tensors)."""
-    planes, r = [], v
+    planes, r = [], v.contiguous()
     for i in range(nseg):
         h = r.to(torch.bfloat16)
         planes.append(h)
         if i + 1 < nseg:
             r = r - h.float()
-    return torch.stack(planes)
+    return torch.stack(planes).contiguous()
 
 
 class Mode:
@@ -158,13 +158,16 @@ class PackCache:
 
     def __init__(self):
         self._registered = {}   # data_ptr -> (O, I, K, K)
-        self._entries = {}      # (data_ptr, scale) -> [src, dst_n, dst_t, version of src when last packed]
+        self._entries = {}      # (data_ptr, scale, nseg) -> [src, dst_n, dst_t, version of src when last packed]
+        self._keepalive = []    # storages of the registered parameters: their addresses cannot be recycled while
+                                # this cache lives, so a data_ptr match is a match of the parameter itself
 
     def register(self, params):
         for p in params:
             shape = tuple(p.shape[1:]) if (p.dim() == 5 and p.shape[0] == 1) else tuple(p.shape)
             if len(shape) == 4 and shape[2] == shape[3] and shape[2] in (1, 3) and p.dtype == torch.float32:
                 self._registered[p.data_ptr()] = shape
+                self._keepalive.append(p.untyped_storage())
 
     def lookup(self, w, transposed, scale, nseg=1):
         if w.dim() != 4 or self._registered.get(w.data_ptr()) != tuple(w.shape) or not w.is_contiguous():
@@ -200,9 +203,28 @@ _PACK_CACHE = None
 
 
 def set_pack_cache(cache):
-    """Install (or with None remove) the process-wide PackCache consulted by `pack_weight`."""
+    """Install (or with None remove) the PackCache consulted by `pack_weight`."""
     global _PACK_CACHE
     _PACK_CACHE = cache
+
+
+class use_pack_cache:
+    """Context manager: `pack_weight` consults `cache` inside the block and whatever was installed before after it.
+    A Trainer wraps its own phases in this, so two trainers (or a trainer and free-standing modules) in one process
+    never see each other's cached copies."""
+
+    def __init__(self, cache):
+        self.cache = cache
+
+    def __enter__(self):
+        global _PACK_CACHE
+        self.prev, _PACK_CACHE = _PACK_CACHE, self.cache
+        return self.cache
+
+    def __exit__(self, *exc):
+        global _PACK_CACHE
+        _PACK_CACHE = self.prev
+        return False
 
 
 def pack_weight(w, transposed, scale=1.0, nseg=1):

@@ -133,16 +133,20 @@ class FlatAdam:
         self.steps = [torch.zeros(1, dtype=torch.int32, device=flat.data.device)
                       for _ in flat.group_end]
 
-    def step(self, n_groups, grad_scale=1.0):
-        """Update parameter groups [0, n_groups) (the main group is group 0)."""
+    def step(self, n_groups, grad_scale=1.0, ema=None, ema_decay=0.0):
+        """Update parameter groups [0, n_groups) (the main group is group 0).  `ema` (a flat buffer laid out like
+        the parameters) receives ema = ema_decay * ema + (1 - ema_decay) * p_new in the same launch: the reference's
+        `accumulate` loop (train_spatial_query.py:56-61) without a pass of its own.  Groups that are not stepped
+        keep p == const, so their EMA entries are left alone."""
         lo = 0
         for gi in range(n_groups):
             hi = self.flat.group_end[gi]
             if hi > lo:
                 self.steps[gi].add_(1)
                 sl = slice(lo, hi)
-                lib.adam_ema_devstep(self.flat.data[sl], self.flat.grad[sl], self.m[sl], self.v[sl], None,
-                                     self.lr, self.betas[0], self.betas[1], self.eps, self.steps[gi], 0.0,
+                lib.adam_ema_devstep(self.flat.data[sl], self.flat.grad[sl], self.m[sl], self.v[sl],
+                                     None if ema is None else ema[sl],
+                                     self.lr, self.betas[0], self.betas[1], self.eps, self.steps[gi], ema_decay,
                                      grad_scale)
             lo = hi
 
@@ -216,9 +220,10 @@ class Trainer:
         self._graphs = {}
         self._real = None  # static input buffer (graph replays read from it)
         # bf16 route: tap-major bf16 copies of the shared conv weights, re-packed once per optimiser step
+        # (consulted only inside this trainer's own phases: tc.use_pack_cache)
         self._packs = tc.PackCache()
         self._packs.register(p for _, p in self.g_flat.params + self.d_flat.params)
-        tc.set_pack_cache(self._packs)
+        self._ema_in_step = False  # set per phase by step(): the LAST generator update of an iteration carries the EMA
 
     def weights_changed(self):
         """Call after modifying generator / discriminator weights outside this trainer's optimiser steps
@@ -226,8 +231,11 @@ class Trainer:
         without consulting version counters."""
         self._packs.refresh()
 
-    def _step_optim(self, flat, optim, n_groups):
-        optim.step(n_groups, grad_scale=1.0 / self.world)
+    def _step_optim(self, flat, optim, n_groups, with_ema=False):
+        if with_ema:
+            optim.step(n_groups, grad_scale=1.0 / self.world, ema=self.ema_flat.data, ema_decay=self.cfg.ema_decay)
+        else:
+            optim.step(n_groups, grad_scale=1.0 / self.world)
         lo = flat.data.data_ptr()
         self._packs.refresh(lo, lo + flat.data.numel() * flat.data.element_size())
 
@@ -239,9 +247,14 @@ class Trainer:
         self.use_graphs = flag
 
     def _phase(self, name, fwdbwd, flat, optim, n_groups):
+        with tc.use_pack_cache(self._packs):
+            self._phase_inner(name, fwdbwd, flat, optim, n_groups)
+
+    def _phase_inner(self, name, fwdbwd, flat, optim, n_groups):
+        with_ema = self._ema_in_step and flat is self.g_flat
         if not self.use_graphs:
             fwdbwd()
-            self._reduce_and_step(flat, optim, n_groups)
+            self._reduce_and_step(flat, optim, n_groups, with_ema)
             return
         entry = self._graphs.get(name)
         if entry is None:
@@ -250,17 +263,23 @@ class Trainer:
             ga = torch.cuda.CUDAGraph()
             with torch.cuda.graph(ga):
                 fwdbwd()
+            entry = self._graphs[name] = [ga, {}, lib.launch_count - n0]
+        ga, steps, launches = entry
+        if with_ema not in steps:  # the optimiser graph exists in two flavours: with and without the fused EMA
+            torch.cuda.synchronize()
+            n0 = lib.launch_count
             gb = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gb):
-                self._step_optim(flat, optim, n_groups)
-            entry = (ga, gb, lib.launch_count - n0)
-            self._graphs[name] = entry
-        ga, gb, launches = entry
+                self._step_optim(flat, optim, n_groups, with_ema)
+            steps[with_ema] = (gb, lib.launch_count - n0)
+            # capturing does not execute: undo the step counters' host-side bookkeeping is not needed (device
+            # counters are only incremented by the captured add_ when the graph runs)
+        gb, step_launches = steps[with_ema]
         ga.replay()
         if self.world > 1:
             dist.all_reduce(flat.grad, op=dist.ReduceOp.SUM)
         gb.replay()
-        lib.launch_count += launches
+        lib.launch_count += launches + step_launches
 
     # ------------------------------------------------------------------ pieces of one iteration
     def _latents(self, n):
@@ -269,10 +288,10 @@ class Trainer:
         p = torch.randn(n, c.latent, c.para_num, device=self.device)  # utils/sample.py:10
         return z, p
 
-    def _reduce_and_step(self, flat, optim, n_groups):
+    def _reduce_and_step(self, flat, optim, n_groups, with_ema=False):
         if self.world > 1:
             dist.all_reduce(flat.grad, op=dist.ReduceOp.SUM)
-        self._step_optim(flat, optim, n_groups)
+        self._step_optim(flat, optim, n_groups, with_ema)
 
     def _d_fwdbwd(self):
         _set_requires_grad(self.g_flat, False)
@@ -359,6 +378,12 @@ class Trainer:
         if real_img is self._real:
             return
         if self._real is None or self._real.shape != real_img.shape:
+            if self._graphs:
+                # captured graphs read the OLD static buffer at the OLD batch size: refuse instead of silently
+                # training on stale data (a partial last batch must be dropped or padded by the caller)
+                raise RuntimeError("Trainer: the image batch changed shape from %s to %s after CUDA graphs were "
+                                   "captured; call enable_graphs(False) or keep the batch shape fixed"
+                                   % (tuple(self._real.shape), tuple(real_img.shape)))
             self._real = torch.empty(real_img.shape, dtype=torch.float32, device=self.device)
         self._real.copy_(real_img, non_blocking=True)
 
@@ -375,14 +400,18 @@ class Trainer:
         self._phase("g", self._g_fwdbwd, self.g_flat, self.g_optim, 2)
 
     def g_regularize(self):
-        # to_rgb biases get no gradient from the path penalty -> skipped like Adam skips grad=None
-        self._phase("greg", self._greg_fwdbwd, self.g_flat, self.g_optim, 1)
+        # The reference adds `0 * fake_img[0,0,0,0]` to the path penalty (train_spatial_query.py:240-243), so the
+        # to_rgb biases receive a ZERO gradient tensor (not None) and torch's Adam steps them: step += 1 and
+        # exp_avg_sq *= beta2 with no parameter change (beta1 = 0).  The gathered flat gradient is zero there, so
+        # stepping group 1 reproduces exactly that; only the noise strengths (grad None) stay skipped.
+        self._phase("greg", self._greg_fwdbwd, self.g_flat, self.g_optim, 2)
 
     def g_spatial_regularize(self):
-        self._phase("gsreg", self._gsreg_fwdbwd, self.g_flat, self.g_optim, 1)
+        self._phase("gsreg", self._gsreg_fwdbwd, self.g_flat, self.g_optim, 2)
 
     def ema_update(self):
-        """accumulate(g_ema, g_module, 0.5 ** (32 / 10000)), train_spatial_query.py:56-61,294"""
+        """accumulate(g_ema, g_module, 0.5 ** (32 / 10000)), train_spatial_query.py:56-61,294 as a stand-alone
+        pass (step() fuses it into the last generator update instead)."""
         self.ema_flat.data.lerp_(self.g_flat.data, 1.0 - self.cfg.ema_decay)
 
     # ------------------------------------------------------------------ one iteration
@@ -392,12 +421,20 @@ class Trainer:
         self.d_step(real_img)
         if i % self.cfg.d_reg_every == 0:
             self.d_regularize(real_img)
-        self.g_step()
-        if i % self.cfg.g_reg_every == 0:
-            self.g_regularize()
-            if self.cfg.spatial_regu:
-                self.g_spatial_regularize()
-        self.ema_update()
+        # the EMA (accumulate(g_ema, g, decay) after the iteration's generator updates, :294) rides in the optimiser
+        # kernel of the LAST generator phase of this iteration
+        greg = i % self.cfg.g_reg_every == 0
+        try:
+            self._ema_in_step = not greg
+            self.g_step()
+            if greg:
+                self._ema_in_step = not self.cfg.spatial_regu
+                self.g_regularize()
+                if self.cfg.spatial_regu:
+                    self._ema_in_step = True
+                    self.g_spatial_regularize()
+        finally:
+            self._ema_in_step = False
         self.iteration += 1
         return self.losses
 
