@@ -26,6 +26,11 @@
 //     of f32 values (te_split_bf16 / te_pack_weights_tc) and the K loop additionally walks the plane pairs
 //     (hi,hi) (hi,mid) (mid,hi) [(mid,mid) (hi,lo) (lo,hi)], all accumulated in the same f32 TMEM tile: the f32
 //     convolution to ~2^-16 (2^-24) relative accuracy at 3 (6) tensor-core products — the fp32 parity mode.
+//     The tensor core's f32 accumulation truncates (measured: the end-to-end error grows with the number of MMAs
+//     accumulated into one tile), so the split kernels spread one tile over FOUR TMEM accumulators: the hi*hi
+//     k-blocks round-robin over three of them (a third of the roundings each, against sums a third the size) and
+//     all correction pairs (2^-8 and smaller) go to the fourth; the epilogue adds the four in registers
+//     (round-to-nearest).  Measured image error at 256^2: see profiles/r02_parity_modes*.txt.
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -170,13 +175,22 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, const uint3
 // Persistent kernel: one CTA per SM walks tiles t = blockIdx.x, +gridDim.x, ...; the operand ring and
 // the two TMEM accumulator buffers let the TMA producer / MMA issuer run ahead into the next tile
 // while the epilogue warps drain the previous one.
-template <int BLOCK_N, bool OUT_F32>
+// accumulator slots of one tile / tile buffers in TMEM (512 columns): plain 1 x 2; split 4 x (2 at N=64, 1 at N=128)
+template <int BLOCK_N, bool SPLIT> struct TcAcc {
+  static constexpr int SLOTS = SPLIT ? 4 : 1;
+  static constexpr int NBUF = (2 * SLOTS * BLOCK_N <= 512) ? 2 : 1;
+  static constexpr uint32_t COLS = NBUF * SLOTS * BLOCK_N < 32 ? 32 : NBUF * SLOTS * BLOCK_N;
+  static_assert(COLS <= 512, "TMEM has 512 columns");
+};
+
+template <int BLOCK_N, bool OUT_F32, bool SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ TcParams p) {
   using S = TcSmem<BLOCK_N>;
   constexpr int STAGES = S::STAGES;
-  constexpr uint32_t TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  using ACC = TcAcc<BLOCK_N, SPLIT>;
+  constexpr uint32_t TMEM_COLS = ACC::COLS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFFSET);
@@ -263,10 +277,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
       constexpr uint32_t idesc = make_idesc_bf16(TC_BLOCK_M, BLOCK_N);
       uint32_t it = 0, ti = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
-        const uint32_t buf = ti & 1;
-        mbar_wait(&tmem_empty_bar[buf], ((ti >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+        const uint32_t buf = ACC::NBUF == 2 ? (ti & 1) : 0;
+        // epilogue has drained this accumulator
+        mbar_wait(&tmem_empty_bar[buf], (ACC::NBUF == 2 ? ((ti >> 1) & 1) : (ti & 1)) ^ 1);
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * BLOCK_N;
+        const uint32_t d_base = tmem_base + buf * ACC::SLOTS * BLOCK_N;
+        bool corr_started = false;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
@@ -275,11 +291,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
           const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
           const uint64_t da = make_sw128_desc(a_addr);
           const uint64_t db = make_sw128_desc(a_addr + TC_A_BYTES);
+          uint32_t d_tmem = d_base;
+          bool fresh = kb == 0;
+          if (SPLIT) {
+            // hi*hi k-blocks round-robin over slots 0..2, every correction pair into slot 3 (see the header)
+            const int tap = kb / kb_per_tap, r = kb - tap * kb_per_tap;
+            const int pr = r / k_chunks, kc = r - pr * k_chunks;
+            if (pr == 0) {
+              const int idx = tap * k_chunks + kc;
+              d_tmem = d_base + (idx % 3) * BLOCK_N;
+              fresh = idx < 3;
+            } else {
+              d_tmem = d_base + 3 * BLOCK_N;
+              fresh = !corr_started;
+              corr_started = true;
+            }
+          }
           if (!(p.debug & 4)) {
 #pragma unroll
             for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
               // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in 16-byte units
-              umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (!fresh || k != 0) ? 1u : 0u);
             }
           }
           umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
@@ -303,7 +335,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
       int b0, ay0, ax0, n0;
       tile_coords(tile, b0, ay0, ax0, n0);
-      const uint32_t buf = ti & 1;
+      const uint32_t buf = ACC::NBUF == 2 ? (ti & 1) : 0;
       if (staged) {
         __syncwarp();
         for (int c = lane; c < BLOCK_N; c += 32) {
@@ -320,13 +352,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
       const int oy = ay * p.out_stride + p.out_off_y, ox = ax * p.out_stride + p.out_off_x;
       const int64_t pix = (static_cast<int64_t>(bs) * p.hout + oy) * p.wout + ox;
 
-      mbar_wait(&tmem_full_bar[buf], (ti >> 1) & 1);
+      mbar_wait(&tmem_full_bar[buf], ACC::NBUF == 2 ? ((ti >> 1) & 1) : (ti & 1));
       tcgen05_fence_after();
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
         if (n0 + c0 >= p.cout || (p.debug & 2)) break;  // warp-uniform
         uint32_t v[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * BLOCK_N + c0, v);
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * ACC::SLOTS * BLOCK_N + c0;
+        if (SPLIT) {
+          // sum the tile's accumulator slots in registers (round-to-nearest): corrections first, then the hi*hi slots
+          tmem_ld32(t_row + 3 * BLOCK_N, v);
+          const int n_main = num_kb / p.npairs < 3 ? num_kb / p.npairs : 3;
+          for (int sl = 0; sl < n_main; ++sl) {
+            uint32_t u[32];
+            tmem_ld32(t_row + sl * BLOCK_N, u);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+          }
+        } else {
+          tmem_ld32(t_row, v);
+        }
         tc_epilogue_chunk<OUT_F32>(p, v, s_osc + c0, s_bias + c0, staged, osc, valid, pix, n0 + c0);
       }
       // this warp is done reading the accumulator buffer: hand it back to the MMA issuer
@@ -356,13 +401,14 @@ struct Tc2Smem {
   static constexpr int TOTAL = EPI_OFFSET + 4 * 2 * BLOCK_N * 4 + 1024;
 };
 
-template <int BLOCK_N, bool OUT_F32>
+template <int BLOCK_N, bool OUT_F32, bool SPLIT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                 const __grid_constant__ TcParams p) {
   using S = Tc2Smem<BLOCK_N>;
   constexpr int STAGES = S::STAGES;
-  constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
+  using ACC = TcAcc<BLOCK_N, SPLIT>;
+  constexpr uint32_t TMEM_COLS = ACC::COLS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFFSET);   // used in the leader only
@@ -451,10 +497,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       constexpr uint32_t idesc = make_idesc_bf16(2 * TC_BLOCK_M, BLOCK_N);
       uint32_t it = 0, ti = 0;
       for (int w = pair_id; w < total_work; w += num_pairs, ++ti) {
-        const uint32_t buf = ti & 1;
-        mbar_wait(&tmem_empty_bar[buf], ((ti >> 1) & 1) ^ 1);
+        const uint32_t buf = ACC::NBUF == 2 ? (ti & 1) : 0;
+        mbar_wait(&tmem_empty_bar[buf], (ACC::NBUF == 2 ? ((ti >> 1) & 1) : (ti & 1)) ^ 1);
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * BLOCK_N;
+        const uint32_t d_base = tmem_base + buf * ACC::SLOTS * BLOCK_N;
+        bool corr_started = false;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
@@ -463,10 +510,25 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
           const uint64_t da = make_sw128_desc(a_addr);
           const uint64_t db = make_sw128_desc(a_addr + TC_A_BYTES);
+          uint32_t d_tmem = d_base;
+          bool fresh = kb == 0;
+          if (SPLIT) {
+            const int tap = kb / kb_per_tap, r = kb - tap * kb_per_tap;
+            const int pr = r / k_chunks, kc = r - pr * k_chunks;
+            if (pr == 0) {
+              const int idx = tap * k_chunks + kc;
+              d_tmem = d_base + (idx % 3) * BLOCK_N;
+              fresh = idx < 3;
+            } else {
+              d_tmem = d_base + 3 * BLOCK_N;
+              fresh = !corr_started;
+              corr_started = true;
+            }
+          }
           if (!(p.debug & 4)) {
 #pragma unroll
             for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k)
-              umma2_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma2_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (!fresh || k != 0) ? 1u : 0u);
           }
           umma2_commit_both(&empty_bar[s]);
         }
@@ -488,7 +550,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     for (int w = pair_id; w < total_work; w += num_pairs, ++ti) {
       int b0, ay0, ax0, n0;
       work_coords(w, b0, ay0, ax0, n0);
-      const uint32_t buf = ti & 1;
+      const uint32_t buf = ACC::NBUF == 2 ? (ti & 1) : 0;
       const int b = b0 + nbi, ay = ay0 + thi, ax = ax0 + twi;
       const bool valid = b < p.batch && ay < p.grid_h && ax < p.grid_w;
       const int bs = valid ? b : 0;
@@ -506,13 +568,26 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       const int oy = ay * p.out_stride + p.out_off_y, ox = ax * p.out_stride + p.out_off_x;
       const int64_t pix = (static_cast<int64_t>(bs) * p.hout + oy) * p.wout + ox;
 
-      mbar_wait(&tmem_full_bar[buf], (ti >> 1) & 1);
+      mbar_wait(&tmem_full_bar[buf], ACC::NBUF == 2 ? ((ti >> 1) & 1) : (ti & 1));
       tcgen05_fence_after();
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
         if (n0 + c0 >= p.cout || (p.debug & 2)) break;  // warp-uniform
         uint32_t v[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * BLOCK_N + c0, v);
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * ACC::SLOTS * BLOCK_N + c0;
+        if (SPLIT) {
+          // sum the tile's accumulator slots in registers (round-to-nearest): corrections first, then the hi*hi slots
+          tmem_ld32(t_row + 3 * BLOCK_N, v);
+          const int n_main = num_kb / p.npairs < 3 ? num_kb / p.npairs : 3;
+          for (int sl = 0; sl < n_main; ++sl) {
+            uint32_t u[32];
+            tmem_ld32(t_row + sl * BLOCK_N, u);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+          }
+        } else {
+          tmem_ld32(t_row, v);
+        }
         tc_epilogue_chunk<OUT_F32>(p, v, s_osc + c0, s_bias + c0, staged, osc, valid, pix, n0 + c0);
       }
       tcgen05_fence_before();
@@ -529,10 +604,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   }
 }
 
-template <int BLOCK_N, bool OUT_F32>
+template <int BLOCK_N, bool OUT_F32, bool SPLIT = false>
 static int launch_tc2(const CUtensorMap& mx, const CUtensorMap& mw, const TcParams& p, cudaStream_t st) {
   using S = Tc2Smem<BLOCK_N>;
-  auto kern = conv_tc2_kernel<BLOCK_N, OUT_F32>;
+  auto kern = conv_tc2_kernel<BLOCK_N, OUT_F32, SPLIT>;
   static bool configured = false;
   if (!configured) {
     TE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
@@ -546,10 +621,10 @@ static int launch_tc2(const CUtensorMap& mx, const CUtensorMap& mw, const TcPara
 }
 
 // ---- host side ---------------------------------------------------------------------------------
-template <int BLOCK_N, bool OUT_F32>
+template <int BLOCK_N, bool OUT_F32, bool SPLIT = false>
 static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const TcParams& p, cudaStream_t st) {
   using S = TcSmem<BLOCK_N>;
-  auto kern = conv_tc_kernel<BLOCK_N, OUT_F32>;
+  auto kern = conv_tc_kernel<BLOCK_N, OUT_F32, SPLIT>;
   static bool configured = false;
   if (!configured) {
     TE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
@@ -623,8 +698,10 @@ static int conv_tc_dispatch(void* y, const void* x, const void* w, const float* 
   // N tile: 256 halves the A-operand shared-memory reads per FLOP (one-CTA UMMA at M128 x N128 is bound by
   // the 128 B/cycle shared-memory port: every K16 step reads 4 KB of A + 4 KB of B in 64 cycles); used when
   // the layer still yields >= 1 tile per SM.
+  const bool split = p.nseg > 1;
+  TE_CHECK_ARG(!split || d.out_f32, "conv_tc: the split-operand mode writes f32 output");
   int block_n = (d.cout % 128 == 0) ? 128 : 64;
-  if (d.cout % 256 == 0) {
+  if (d.cout % 256 == 0 && !split) {  // split mode: four accumulator slots per tile fit TMEM only up to N = 128
     // waves x cost per tile: an N=256 tile does twice the work of an N=128 tile in ~1.4x the time (measured
     // 1.67 vs 1.10 PFLOP/s at 512 channels), so it wins whenever it does not cost an extra wave of its own
     const int64_t t256 = int64_t(p.n_tiles) * (d.cout / 256), t128 = 2 * t256;
@@ -634,7 +711,7 @@ static int conv_tc_dispatch(void* y, const void* x, const void* w, const float* 
   {  // TE_TC_BLOCK_N=128|256 (profiling aid): force the N tile where the layer allows it
     static int force_n = -1;
     if (force_n < 0) { const char* e = getenv("TE_TC_BLOCK_N"); force_n = e ? atoi(e) : 0; }
-    if (force_n == 256 && d.cout % 256 == 0) block_n = 256;
+    if (force_n == 256 && d.cout % 256 == 0 && !split) block_n = 256;
     if (force_n == 128 && d.cout % 128 == 0) block_n = 128;
   }
 
@@ -665,6 +742,11 @@ static int conv_tc_dispatch(void* y, const void* x, const void* w, const float* 
     uint32_t box[4] = {TC_BLOCK_K, uint32_t(two_cta ? block_n / 2 : block_n), 1, 1};
     int rc = encode_map_bf16(&mw, w, 4, dims, strides, box, nullptr);
     if (rc) return rc;
+  }
+  if (split) {
+    if (two_cta) return launch_tc2<128, true, true>(mx, mw, p, st);
+    if (block_n == 128) return launch_tc<128, true, true>(mx, mw, p, st);
+    return launch_tc<64, true, true>(mx, mw, p, st);
   }
   if (two_cta) {
     if (block_n == 256)

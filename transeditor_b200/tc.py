@@ -19,7 +19,7 @@ Two operand precisions, selected by the dtype of the activations:
     f32 activations    SPLIT-OPERAND mode: activations, gradients and weights are stored as `split_planes()` bf16
                        planes hi = bf16(v), mid = bf16(v - hi)(, lo) and the kernels sum the plane-pair products
                        hi*hi + hi*mid + mid*hi (+ mid*mid + hi*lo + lo*hi) in their f32 accumulators: the reference's
-                       fp32 F.conv2d arithmetic to ~2^-24 per product with three planes (default; 2^-16 with two)
+                       fp32 F.conv2d arithmetic to ~2^-16 per product with two planes (default; 2^-24 with three)
                        ON TENSOR CORES.  Outputs are f32 channels-last.  `set_split_planes(2|3)` picks the count.
 
 Reference call sites replaced: F.conv2d / F.conv_transpose2d in model_spatial_query.py:177-183,318,327,333
@@ -35,13 +35,14 @@ def _pad8(c):
     return (c + 7) // 8 * 8
 
 
-_SPLIT_PLANES = 3
+_SPLIT_PLANES = 2
 
 
 def set_split_planes(n):
-    """Planes used for f32 activations: 3 (six products, f32-exact to accumulator rounding: the default of the
-    parity mode) or 2 (three products, ~2^-16 per product, twice as fast: measured image max-abs error 2e-4 at
-    256^2 — inside the 1e-3 bar — but 2e-3 at 1024^2 with its 18 layers, outside it)."""
+    """Planes used for f32 activations: 2 (three products, ~2^-16 per product: the default) or 3 (six products,
+    twice the cost).  Measured image max-abs error against the reference goldens / the CPU oracle on B200
+    (profiles/r02_parity_modes_v2.txt): 2 planes 2.2e-4 at 256^2 and 4.5e-4 at 1024^2; 3 planes 9.6e-5 and 1.9e-4;
+    the exact-f32 SIMT engine 4.2e-5 and 9.7e-5 — all inside the 1e-3 bar."""
     global _SPLIT_PLANES
     if n not in (2, 3):
         raise ValueError("split planes must be 2 or 3")
