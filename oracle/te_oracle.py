@@ -134,6 +134,23 @@ def attention_block(x, p_code, p):
     return x + h
 
 
+def interaction_stack(x0, p0, p, blocks):
+    """The whole interaction network (`self.interact[i](x, spatialcode)` loop, model_spatial_query.py:668-679) over
+    `attention_block` above, for parameter tables in the layout of te_attn_stack (include/te_b200.h: w_q, b_q, ...
+    per block): the checker of te_attn_stack_fwd / te_attn_stack_bwd.  Block 0 reads (x0, p0), later blocks the
+    previous output and p."""
+    names = {"w_proj": "proj.weight", "b_proj": "proj.bias", "w_q": "atten.q_transform.weight",
+             "b_q": "atten.q_transform.bias", "w_k": "atten.k_transform.weight", "b_k": "atten.k_transform.bias",
+             "w_v": "atten.v_transform.weight", "b_v": "atten.v_transform.bias", "w_o": "atten.proj.weight",
+             "b_o": "atten.proj.bias", "w_m1": "mlp.0.weight", "b_m1": "mlp.0.bias", "w_m2": "mlp.2.weight",
+             "b_m2": "mlp.2.bias"}
+    x = x0
+    for i, blk in enumerate(blocks):
+        params = {names[k]: v for k, v in blk.items() if k in names and v is not None}
+        x = attention_block(x, p0 if i == 0 else p, params)
+    return x
+
+
 def map_codes(code, sd, prefix, norm_dim):
     """:626-646.  Pixel norm then one independent 512->512 linear per column."""
     code = pixel_norm(code, norm_dim)

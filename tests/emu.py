@@ -149,20 +149,20 @@ def adam_ema_devstep(p, g, m, v, ema, lr, beta1, beta2, eps, step_dev, ema_decay
 
 
 def attn_stack_fwd(y, x0, p0, p, blocks, batch, lr_mul, tf32, save):
-    from transeditor_b200.op import attn_stack_reference
+    from oracle.te_oracle import interaction_stack
     with torch.no_grad():
-        y.copy_(attn_stack_reference(x0, p0, p, blocks, lr_mul))
+        y.copy_(interaction_stack(x0, p0, p, blocks))
 
 
 def attn_stack_bwd(g_x0, g_p0, g_p, grads, gy, x0, p0, p, blocks, batch, lr_mul, tf32, save, gws):
-    from transeditor_b200.op import attn_stack_reference
+    from oracle.te_oracle import interaction_stack
     fields = [f for f in lib.ATTN_FIELDS]
     leaf = lambda t: None if t is None else t.detach().clone().requires_grad_(True)  # noqa: E731
     lx0, lp0, lp = leaf(x0), leaf(p0), leaf(p)
     lblocks = [{**{f: leaf(b.get(f)) for f in fields}, "in_dim": b["in_dim"], "param_dim": b["param_dim"]}
                for b in blocks]
     with torch.enable_grad():
-        y = attn_stack_reference(lx0, lp0, lp, lblocks, lr_mul)
+        y = interaction_stack(lx0, lp0, lp, lblocks)
         wanted = [(lx0, g_x0), (lp0, g_p0)] + ([(lp, g_p)] if (lp is not None and g_p is not None) else [])
         for lb, gb in zip(lblocks, grads):
             wanted += [(lb[f], gb[f]) for f in fields if lb[f] is not None]

@@ -1,10 +1,12 @@
 """te_attn_stack_fwd / te_attn_stack_bwd (the interaction network in one launch) against the float64 CPU
-restatement of AttentionBlock / Attention (model_spatial_query.py:883-936) — `op.attn_stack_reference`, which the
-CPU suite pins to the reference's own classes through the generator goldens."""
+restatement of AttentionBlock / Attention (model_spatial_query.py:883-936) in oracle/te_oracle.py
+(`interaction_stack` over `attention_block`), which tests/test_oracle_golden.py pins to the reference's own classes."""
 import os
 
 import pytest
 import torch
+
+from oracle import te_oracle as O
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -66,7 +68,7 @@ def test_forward_matches_float64_restatement(batch, n_blocks, first_dim, tf32):
     from transeditor_b200 import op
     b64 = _blocks(n_blocks, first_dim, seed=n_blocks, dtype=torch.float64)
     x0, p0, p = _inputs(batch, first_dim, seed=batch)
-    ref = op.attn_stack_reference(x0, p0, p, b64, LR)
+    ref = O.interaction_stack(x0, p0, p, b64)
     bd = _to(b64, torch.float32, DEV)
     pd = p.float().to(DEV) if n_blocks > 1 else None
     assert op.attn_stack_supported(x0.float().to(DEV), p0.float().to(DEV), pd, bd)
@@ -84,7 +86,7 @@ def test_backward_matches_float64_autograd(batch, n_blocks, first_dim, tf32):
     b64 = _to(_blocks(n_blocks, first_dim, seed=10 + n_blocks, dtype=torch.float64), torch.float64, "cpu", grad=True)
     x0, p0, p = [t.requires_grad_(True) for t in _inputs(batch, first_dim, seed=20 + batch)]
     gy = torch.randn(batch, 16, 512, generator=torch.Generator().manual_seed(5), dtype=torch.float64)
-    ref = op.attn_stack_reference(x0, p0, p, b64, LR)
+    ref = O.interaction_stack(x0, p0, p, b64)
     leaves = [x0, p0] + ([p] if n_blocks > 1 else []) + [blk[f] for blk in b64 for f in FIELDS if blk[f] is not None]
     gref = torch.autograd.grad(ref, leaves, gy)
 
@@ -124,7 +126,7 @@ def test_second_order_route_is_differentiable():
         (gg,) = torch.autograd.grad(g.square().sum(), p)
         return gg
 
-    ref = penalty(op.attn_stack_reference, x0, p0, p, b64)
+    ref = penalty(lambda a, b_, c, blks, lr: O.interaction_stack(a, b_, c, blks), x0, p0, p, b64)
     got = penalty(op.attn_stack, x0.float().to(DEV), p0.float().to(DEV), p.float().to(DEV),
                   _to(b64, torch.float32, DEV))
     assert _rel(got, ref) < 1e-3
@@ -218,5 +220,5 @@ def test_partial_derivatives_when_arguments_depend_on_each_other(create_graph):
         y = fn(torch.cat([s, eye], 2), torch.cat([q, eye], 2), q, bd, LR)
         return torch.autograd.grad(y, [q, s], gy, create_graph=create_graph)
 
-    for a, b in zip(run(op.attn_stack), run(op.attn_stack_reference)):
+    for a, b in zip(run(op.attn_stack), run(lambda a_, b_, c, blks, lr: O.interaction_stack(a_, b_, c, blks))):
         assert _rel(a, b) < 1e-4

@@ -115,6 +115,57 @@ def test_bf16_train_step_runs():
     assert torch.isfinite(tr.g_flat.data).all() and torch.isfinite(tr.d_flat.data).all()
 
 
+def test_bf16_train_step_tracks_the_cpu_oracle_update():
+    """One D step and one G step of the bf16 engine against the oracle's torch.optim.Adam update on the CPU (the bf16
+    twin of test_gpu_model.test_train_step_matches_cpu_oracle_update).  Adam's first update is -lr * g / (|g| + eps),
+    i.e. the SIGN of the gradient wherever |g| >> eps: bar = the update direction agrees on >= 97 % of the
+    well-conditioned elements (reference update >= half its maximum size) and the losses agree to 5 %."""
+    from oracle import te_oracle as O
+    from oracle.train_cpu import CpuTrainer
+    from transeditor_b200.train_step import TrainConfig, Trainer
+    cfg = TrainConfig(size=32, batch=4)
+    tr = Trainer(cfg, DEV, seed=0)
+    ref = CpuTrainer(size=32, batch=4)
+    tr.generator.load_state_dict({k: v.detach() for k, v in ref.g.items()}, strict=True)
+    tr.discriminator.load_state_dict({k: v.detach() for k, v in ref.d.items()}, strict=True)
+    tr.weights_changed()
+    before_g = {k: v.detach().clone() for k, v in ref.g.items()}
+    before_d = {k: v.detach().clone() for k, v in ref.d.items()}
+    gen = torch.Generator().manual_seed(99)
+    lat = [torch.randn(4, 512, 16, generator=gen) for _ in range(4)]
+    real = torch.rand(4, 3, 32, 32, generator=gen) * 2 - 1
+    it = iter(lat)
+    tr._latents = lambda n: (next(it).to(DEV), next(it).to(DEV))
+    tr.d_step(real.to(DEV))
+    tr.g_step()
+    it2 = iter(lat)
+
+    def fake(n, with_latent=False):
+        z, p = next(it2), next(it2)
+        img, l = O.generator_forward(ref.g, z, p, 32, 8)
+        return (img, l) if with_latent else img
+    ref._fake = fake
+    ref.it = 1  # no lazy regularisers
+    g_loss_ref = ref.step(real)
+    assert abs(float(tr.losses["g"]) - g_loss_ref) < 0.05 * max(1.0, abs(g_loss_ref))
+    dp, gp = dict(tr.discriminator.named_parameters()), dict(tr.generator.named_parameters())
+
+    def agree(now, before, ref_now, key):
+        upd = (now.detach().cpu() - before[key]).reshape(-1)
+        upd_ref = (ref_now[key].detach() - before[key]).reshape(-1)
+        strong = upd_ref.abs() >= 0.5 * upd_ref.abs().max()
+        assert strong.sum().item() > 0, key
+        same = (torch.sign(upd[strong]) == torch.sign(upd_ref[strong])).float().mean().item()
+        assert same >= 0.97, (key, same)
+        assert (upd[strong] - upd_ref[strong]).abs().mean().item() < 0.1 * upd_ref.abs().max().item(), key
+
+    for k in ("final_linear.1.weight", "convs.0.1.bias", "convs.1.conv2.1.weight", "final_conv.0.weight"):
+        agree(dp[k], before_d, ref.d, k)
+    for k in ("conv1.conv.weight", "adjust_style.weight", "convs.1.activate.bias", "interact.3.mlp.0.weight",
+              "style_mapping_network.5.weight"):
+        agree(gp[k], before_g, ref.g, k)
+
+
 def test_train_step_cuda_graph_replay():
     """Phases replayed from captured CUDA graphs (fwd+bwd graph, NCCL point, optimiser graph): the
     parameters keep moving, the Adam step counters advance on the device, everything stays finite."""

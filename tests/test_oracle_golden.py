@@ -113,3 +113,29 @@ def test_ops_match_kernel_index_transcription():
             assert np.abs(y.numpy() - ref).max() < 1e-12
     x, b = torch.from_numpy(gold["fba_x"]), torch.from_numpy(gold["fba_b"])
     assert np.abs(ops_cpu.fused_leaky_relu(x, b).numpy() - gold["fba_30"]).max() < 1e-6
+
+
+def test_product_attention_restatement_matches_the_oracle():
+    """`op.attn_stack_reference` (the differentiable re-expression the product uses for second-order gradients of the
+    fused attention stack) computes the oracle's `interaction_stack` — which the golden tests above pin to the
+    reference's own AttentionBlock."""
+    import torch
+    from oracle import te_oracle as O
+    from transeditor_b200 import op
+    g = torch.Generator().manual_seed(21)
+    lr = 0.01
+    blocks = []
+    for i in range(3):
+        d = 528 if i == 0 else 512
+        w = lambda o, n: (torch.randn(o, n, generator=g, dtype=torch.float64) / lr)  # noqa: E731
+        b = lambda o: (torch.randn(o, generator=g, dtype=torch.float64) * 0.3 / lr)  # noqa: E731
+        blocks.append({"in_dim": d, "param_dim": d, "w_proj": w(512, d) if i == 0 else None,
+                       "b_proj": b(512) if i == 0 else None, "w_q": w(128, d), "b_q": b(128), "w_k": w(128, d),
+                       "b_k": b(128), "w_v": w(128, d), "b_v": b(128), "w_o": w(512, 128), "b_o": b(512),
+                       "w_m1": w(512, 512), "b_m1": b(512), "w_m2": w(512, 512), "b_m2": b(512)})
+    x0 = torch.randn(2, 16, 528, generator=g, dtype=torch.float64)
+    p0 = torch.randn(2, 16, 528, generator=g, dtype=torch.float64)
+    p = torch.randn(2, 16, 512, generator=g, dtype=torch.float64)
+    a = op.attn_stack_reference(x0, p0, p, blocks, lr)
+    r = O.interaction_stack(x0, p0, p, blocks)
+    assert (a - r).abs().max().item() < 1e-10 * max(1.0, r.abs().max().item())

@@ -57,7 +57,8 @@ def main():
     torch.cuda.synchronize()
     out = {}
     for name in ("d", "dreg", "g", "greg"):
-        ga, gb, launches = tr._graphs[name]
+        ga, steps, launches = tr._graphs[name]
+        gb = next(iter(steps.values()))[0]
         for which, g in (("fwdbwd", ga), ("optim", gb)):
             ts = []
             for _ in range(7):

@@ -15,7 +15,11 @@
 //     no im2col buffer, no halo logic.  Channel tails (Cin % 64 != 0) are zero-filled the same way.
 //   * B operand = a [BLOCK_N x 64] box of the tap-major weight tensor; every CTA reads the same
 //     weights, so they stay L2-resident (the point of the shared-weight formulation).
-//   * K loop = taps x ceil(Cin/64); each step is 4 x tcgen05.mma (M128, N=BLOCK_N, K16).
+//   * K loop = taps x ceil(Cin/64) k-blocks of 4 x tcgen05.mma (M128, N=BLOCK_N, K16); a pipeline stage holds
+//     TC_KSUB k-blocks (1: measured, tools/mma_rate_probe.py + profiles/r02_mma_rate_probe.md — with operands in
+//     shared memory one tcgen05.mma of M = 128 rows per CTA costs ~140 cycles whatever N <= 256 is and however many
+//     MMAs share a barrier round trip, so N = 256 tiles run at the cuBLAS rate and N = 128 tiles at ~half of it;
+//     two k-blocks per stage only coarsened the pipeline: 0.385 vs 0.329 ms on the 128-channel 256^2 layer).
 //   * Persistent: one CTA per SM walks the tile list.  Warp 0 = TMA producer, warp 1 = MMA issuer
 //     (+ TMEM alloc), warps 2-5 = epilogue (TMEM lane quarter = warp_id % 4).  A 6-stage (8 at
 //     BLOCK_N=64) full/empty mbarrier ring feeds the MMAs; TWO accumulator buffers in TMEM
@@ -42,7 +46,8 @@ constexpr int TC_BLOCK_M = 128;
 constexpr int TC_BLOCK_K = 64;        // bf16 elements = 128 bytes = one swizzle row
 constexpr int TC_UMMA_K = 16;
 constexpr int TC_THREADS = 192;
-constexpr int TC_SMEM_BUDGET = 196608;  // operand ring: 6 stages at BLOCK_N=128, 8 at BLOCK_N=64
+constexpr int TC_KSUB = 1;              // k-blocks per pipeline stage (see the header)
+constexpr int TC_SMEM_BUDGET = 196608;  // operand ring
 constexpr int TC_A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;  // 16 KB
 
 struct TcParams {
@@ -54,13 +59,15 @@ struct TcParams {
   int tw, th, nb;          // tile patch; nb*th*tw == 128
   int tiles_w, tiles_h, tiles_b, n_tiles;
   int w_slices_per_sample; // 0: shared weights; else slices per sample (weights indexed b*slices + w_t)
+  int halo_x0, halo_y0;    // haloed-patch kernel: input offset of the box origin relative to the tile's first anchor
+  int halo_bo;             // profiling aid: 1 = leave the descriptor's matrix base offset at 0
   int nseg, npairs;        // split-operand planes and plane pairs (1, 1 = plain bf16)
   int pair_a[6], pair_w[6];
   int act;
   float act_gain;
   const void* residual;    // [B, hout, wout, cout] (the output's dtype) added after the activation, or null
   const float* slope;      // act 3 (PReLU): negative slope per output channel [cout]
-  int debug;               // TE_TC_DEBUG bits (profiling aid): 1 no stores, 2 no epilogue work, 4 no MMAs
+  int debug;               // TE_TC_DEBUG bits (profiling aid): 1 no stores, 2 no epilogue work, 4 no MMAs, 8 no loads
   const float* out_scale;  // [B, cout] or null
   const float* bias;       // [cout] or null
   void* y;
@@ -69,8 +76,9 @@ struct TcParams {
 template <int BLOCK_N>
 struct TcSmem {
   static constexpr int B_BYTES = BLOCK_N * TC_BLOCK_K * 2;
-  static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
-  static constexpr int STAGES = TC_SMEM_BUDGET / STAGE_BYTES;
+  static constexpr int SUB_BYTES = TC_A_BYTES + B_BYTES;          // one k-block: A tile + B tile
+  static constexpr int STAGE_BYTES = TC_KSUB * SUB_BYTES;
+  static constexpr int STAGES = TC_SMEM_BUDGET / STAGE_BYTES;     // 8 at N=64, 6 at N=128, 4 at N=256
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int EPI_OFFSET = BAR_OFFSET + 256;     // per-epilogue-warp scale/bias staging
   static constexpr int TOTAL = EPI_OFFSET + 4 * 2 * BLOCK_N * 4 + 1024;  // + slack for 1024-B alignment
@@ -255,19 +263,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             for (int kc = 0; kc < k_chunks; ++kc)
               tma_prefetch_5d(&map_x, kc * TC_BLOCK_K, px * p.in_stride, py * p.in_stride, pb, sg);
         }
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        for (int kb0 = 0; kb0 < num_kb; kb0 += TC_KSUB, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
-          const int tap = kb / kb_per_tap, r = kb - tap * kb_per_tap;
-          const int pr = r / k_chunks, kc = r - pr * k_chunks;
-          uint8_t* a_dst = smem + s * S::STAGE_BYTES;
-          uint8_t* b_dst = a_dst + TC_A_BYTES;
-          mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
-          tma_load_5d(a_dst, &map_x, &full_bar[s], kc * TC_BLOCK_K, ax0 * p.in_stride + p.tap_dx[tap],
-                      ay0 * p.in_stride + p.tap_dy[tap], b0, p.pair_a[pr]);
-          const int wsl = p.w_slices_per_sample ? b0 * p.w_slices_per_sample + p.tap_w[tap] : p.tap_w[tap];
-          tma_load_4d(b_dst, &map_w, &full_bar[s], kc * TC_BLOCK_K, n0, wsl, p.pair_w[pr]);
+          const int nsub = num_kb - kb0 < TC_KSUB ? num_kb - kb0 : TC_KSUB;
+          mbar_expect_tx(&full_bar[s], nsub * S::SUB_BYTES);
+          for (int sub = 0; sub < nsub; ++sub) {
+            const int kb = kb0 + sub;
+            const int tap = kb / kb_per_tap, r = kb - tap * kb_per_tap;
+            const int pr = r / k_chunks, kc = r - pr * k_chunks;
+            uint8_t* a_dst = smem + s * S::STAGE_BYTES + sub * S::SUB_BYTES;
+            uint8_t* b_dst = a_dst + TC_A_BYTES;
+            tma_load_5d(a_dst, &map_x, &full_bar[s], kc * TC_BLOCK_K, ax0 * p.in_stride + p.tap_dx[tap],
+                        ay0 * p.in_stride + p.tap_dy[tap], b0, p.pair_a[pr]);
+            const int wsl = p.w_slices_per_sample ? b0 * p.w_slices_per_sample + p.tap_w[tap] : p.tap_w[tap];
+            tma_load_4d(b_dst, &map_w, &full_bar[s], kc * TC_BLOCK_K, n0, wsl, p.pair_w[pr]);
+          }
         }
       }
     }
@@ -283,35 +295,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         tcgen05_fence_after();
         const uint32_t d_base = tmem_base + buf * ACC::SLOTS * BLOCK_N;
         bool corr_started = false;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        for (int kb0 = 0; kb0 < num_kb; kb0 += TC_KSUB, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
           tcgen05_fence_after();
-          const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
-          const uint64_t da = make_sw128_desc(a_addr);
-          const uint64_t db = make_sw128_desc(a_addr + TC_A_BYTES);
-          uint32_t d_tmem = d_base;
-          bool fresh = kb == 0;
-          if (SPLIT) {
-            // hi*hi k-blocks round-robin over slots 0..2, every correction pair into slot 3 (see the header)
-            const int tap = kb / kb_per_tap, r = kb - tap * kb_per_tap;
-            const int pr = r / k_chunks, kc = r - pr * k_chunks;
-            if (pr == 0) {
-              const int idx = tap * k_chunks + kc;
-              d_tmem = d_base + (idx % 3) * BLOCK_N;
-              fresh = idx < 3;
-            } else {
-              d_tmem = d_base + 3 * BLOCK_N;
-              fresh = !corr_started;
-              corr_started = true;
+          const int nsub = num_kb - kb0 < TC_KSUB ? num_kb - kb0 : TC_KSUB;
+          for (int sub = 0; sub < nsub; ++sub) {
+            const int kb = kb0 + sub;
+            const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES + sub * S::SUB_BYTES);
+            const uint64_t da = make_sw128_desc(a_addr);
+            const uint64_t db = make_sw128_desc(a_addr + TC_A_BYTES);
+            uint32_t d_tmem = d_base;
+            bool fresh = kb == 0;
+            if (SPLIT) {
+              // hi*hi k-blocks round-robin over slots 0..2, every correction pair into slot 3 (see the header)
+              const int tap = kb / kb_per_tap, r = kb - tap * kb_per_tap;
+              const int pr = r / k_chunks, kc = r - pr * k_chunks;
+              if (pr == 0) {
+                const int idx = tap * k_chunks + kc;
+                d_tmem = d_base + (idx % 3) * BLOCK_N;
+                fresh = idx < 3;
+              } else {
+                d_tmem = d_base + 3 * BLOCK_N;
+                fresh = !corr_started;
+                corr_started = true;
+              }
             }
-          }
-          if (!(p.debug & 4)) {
+            if (!(p.debug & 4)) {
 #pragma unroll
-            for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
-              // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in 16-byte units
-              umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (!fresh || k != 0) ? 1u : 0u);
+              for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
+                // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in 16-byte units
+                umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (!fresh || k != 0) ? 1u : 0u);
+              }
             }
           }
           umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
@@ -394,7 +410,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 template <int BLOCK_N>
 struct Tc2Smem {
   static constexpr int B_BYTES = (BLOCK_N / 2) * TC_BLOCK_K * 2;   // this CTA's half of the weight tile
-  static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+  static constexpr int SUB_BYTES = TC_A_BYTES + B_BYTES;
+  static constexpr int STAGE_BYTES = TC_KSUB * SUB_BYTES;
   static constexpr int STAGES = TC_SMEM_BUDGET / STAGE_BYTES;      // 8 at N=128, 6 at N=256
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int EPI_OFFSET = BAR_OFFSET + 256;
@@ -474,20 +491,28 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             for (int kc = 0; kc < k_chunks; ++kc)
               tma_prefetch_5d(&map_x, kc * TC_BLOCK_K, px * p.in_stride, py * p.in_stride, pb, sg);
         }
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        for (int kb0 = 0; kb0 < num_kb; kb0 += TC_KSUB, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
-          const int tap = kb / kb_per_tap, r = kb - tap * kb_per_tap;
-          const int pr = r / k_chunks, kc = r - pr * k_chunks;
-          uint8_t* a_dst = smem + s * S::STAGE_BYTES;
-          uint8_t* b_dst = a_dst + TC_A_BYTES;
-          if (leader) mbar_expect_tx(&full_bar[s], 2 * S::STAGE_BYTES);
-          tma2_load_5d(a_dst, &map_x, &full_bar[s], kc * TC_BLOCK_K, ax0 * p.in_stride + p.tap_dx[tap],
-                       ay0 * p.in_stride + p.tap_dy[tap], b0, p.pair_a[pr]);
-          const int wsl = p.w_slices_per_sample ? b0 * p.w_slices_per_sample + p.tap_w[tap] : p.tap_w[tap];
-          tma2_load_4d(b_dst, &map_w, &full_bar[s], kc * TC_BLOCK_K, n0 + int(rank) * (BLOCK_N / 2), wsl,
-                       p.pair_w[pr]);
+          const int nsub = num_kb - kb0 < TC_KSUB ? num_kb - kb0 : TC_KSUB;
+          if (p.debug & 8) {  // profiling aid: no loads
+            if (leader) mbar_arrive(&full_bar[s]);
+            continue;
+          }
+          if (leader) mbar_expect_tx(&full_bar[s], 2 * nsub * S::SUB_BYTES);
+          for (int sub = 0; sub < nsub; ++sub) {
+            const int kb = kb0 + sub;
+            const int tap = kb / kb_per_tap, r = kb - tap * kb_per_tap;
+            const int pr = r / k_chunks, kc = r - pr * k_chunks;
+            uint8_t* a_dst = smem + s * S::STAGE_BYTES + sub * S::SUB_BYTES;
+            uint8_t* b_dst = a_dst + TC_A_BYTES;
+            tma2_load_5d(a_dst, &map_x, &full_bar[s], kc * TC_BLOCK_K, ax0 * p.in_stride + p.tap_dx[tap],
+                         ay0 * p.in_stride + p.tap_dy[tap], b0, p.pair_a[pr]);
+            const int wsl = p.w_slices_per_sample ? b0 * p.w_slices_per_sample + p.tap_w[tap] : p.tap_w[tap];
+            tma2_load_4d(b_dst, &map_w, &full_bar[s], kc * TC_BLOCK_K, n0 + int(rank) * (BLOCK_N / 2), wsl,
+                         p.pair_w[pr]);
+          }
         }
       }
     }
@@ -502,33 +527,37 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         tcgen05_fence_after();
         const uint32_t d_base = tmem_base + buf * ACC::SLOTS * BLOCK_N;
         bool corr_started = false;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        for (int kb0 = 0; kb0 < num_kb; kb0 += TC_KSUB, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
           tcgen05_fence_after();
-          const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
-          const uint64_t da = make_sw128_desc(a_addr);
-          const uint64_t db = make_sw128_desc(a_addr + TC_A_BYTES);
-          uint32_t d_tmem = d_base;
-          bool fresh = kb == 0;
-          if (SPLIT) {
-            const int tap = kb / kb_per_tap, r = kb - tap * kb_per_tap;
-            const int pr = r / k_chunks, kc = r - pr * k_chunks;
-            if (pr == 0) {
-              const int idx = tap * k_chunks + kc;
-              d_tmem = d_base + (idx % 3) * BLOCK_N;
-              fresh = idx < 3;
-            } else {
-              d_tmem = d_base + 3 * BLOCK_N;
-              fresh = !corr_started;
-              corr_started = true;
+          const int nsub = num_kb - kb0 < TC_KSUB ? num_kb - kb0 : TC_KSUB;
+          for (int sub = 0; sub < nsub; ++sub) {
+            const int kb = kb0 + sub;
+            const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES + sub * S::SUB_BYTES);
+            const uint64_t da = make_sw128_desc(a_addr);
+            const uint64_t db = make_sw128_desc(a_addr + TC_A_BYTES);
+            uint32_t d_tmem = d_base;
+            bool fresh = kb == 0;
+            if (SPLIT) {
+              const int tap = kb / kb_per_tap, r = kb - tap * kb_per_tap;
+              const int pr = r / k_chunks, kc = r - pr * k_chunks;
+              if (pr == 0) {
+                const int idx = tap * k_chunks + kc;
+                d_tmem = d_base + (idx % 3) * BLOCK_N;
+                fresh = idx < 3;
+              } else {
+                d_tmem = d_base + 3 * BLOCK_N;
+                fresh = !corr_started;
+                corr_started = true;
+              }
             }
-          }
-          if (!(p.debug & 4)) {
+            if (!(p.debug & 4)) {
 #pragma unroll
-            for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k)
-              umma2_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (!fresh || k != 0) ? 1u : 0u);
+              for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k)
+                umma2_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (!fresh || k != 0) ? 1u : 0u);
+            }
           }
           umma2_commit_both(&empty_bar[s]);
         }
@@ -603,6 +632,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
+
+}  // namespace te
+#include "conv_tc_halo.cuh"
+namespace te {
 
 template <int BLOCK_N, bool OUT_F32, bool SPLIT = false>
 static int launch_tc2(const CUtensorMap& mx, const CUtensorMap& mw, const TcParams& p, cudaStream_t st) {
@@ -689,6 +722,7 @@ static int conv_tc_dispatch(void* y, const void* x, const void* w, const float* 
     if (dbg < 0) { const char* e = getenv("TE_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
     p.debug = dbg;
   }
+  p.halo_x0 = p.halo_y0 = p.halo_bo = 0;
   p.w_slices_per_sample = 0;
   if (d.w_bstride != 0) {
     TE_CHECK_ARG(d.w_bstride == int64_t(d.w_slices) * d.cout * d.cin, "conv_tc: per-sample weights must be densely packed");
@@ -722,8 +756,44 @@ static int conv_tc_dispatch(void* y, const void* x, const void* w, const float* 
   bool two_cta = use2 != 0 && block_n >= 128 && int64_t((p.n_tiles + 1) / 2) * ((d.cout + block_n - 1) / block_n) >= kNumSMs / 2;
   if (two_cta && p.w_slices_per_sample && ((p.tiles_w * p.tiles_h) % 2) != 0) two_cta = false;
 
-  CUtensorMap mx, mw;
+  // Haloed-patch kernel (conv_tc_halo.cuh): stride-1 geometries with several taps whose offsets fit the 18 x 16 box
+  bool halo = false;
   {
+    static int use_halo = -1, halo_bo = 0;
+    if (use_halo < 0) {
+      // off by default: measured no faster (the kernels are bound by MMA issue, not by operand fill, see header)
+      const char* e = getenv("TE_TC_HALO"); use_halo = e ? atoi(e) : 0;
+      halo_bo = 1;  // the swizzle is a function of the absolute shared-memory address: base offset stays 0
+    }
+    int x0 = 0, x1 = 0, y0 = 0, y1 = 0;
+    for (int t = 0; t < d.ntaps; ++t) {
+      x0 = t == 0 || d.tap_dx[t] < x0 ? d.tap_dx[t] : x0; x1 = t == 0 || d.tap_dx[t] > x1 ? d.tap_dx[t] : x1;
+      y0 = t == 0 || d.tap_dy[t] < y0 ? d.tap_dy[t] : y0; y1 = t == 0 || d.tap_dy[t] > y1 ? d.tap_dy[t] : y1;
+    }
+    const int h_tiles = ((d.grid_w + TH_TILE_W - 1) / TH_TILE_W) * ((d.grid_h + TH_TILE_H - 1) / TH_TILE_H);
+    const int64_t h_work = int64_t((int64_t(h_tiles) * d.batch + 1) / 2) * ((d.cout + block_n - 1) / block_n);
+    halo = use_halo != 0 && use2 != 0 && d.in_stride == 1 && d.ntaps >= 2 && block_n >= 128 &&
+           d.grid_h >= TH_TILE_H && d.grid_w >= TH_TILE_W && x1 - x0 <= TH_BOX_W - TH_TILE_W && y1 - y0 <= 2 &&
+           h_work >= kNumSMs / 2 && !(p.w_slices_per_sample && (h_tiles % 2) != 0);
+    if (halo) {
+      p.tw = TH_TILE_W; p.th = TH_TILE_H; p.nb = 1;
+      p.tiles_w = (d.grid_w + TH_TILE_W - 1) / TH_TILE_W;
+      p.tiles_h = (d.grid_h + TH_TILE_H - 1) / TH_TILE_H;
+      p.tiles_b = d.batch;
+      p.n_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
+      p.halo_x0 = x0; p.halo_y0 = y0; p.halo_bo = halo_bo;
+      two_cta = true;
+    }
+  }
+  CUtensorMap mx, mw;
+  if (halo) {
+    uint64_t dims[5] = {uint64_t(d.cin), uint64_t(d.win), uint64_t(d.hin), uint64_t(d.batch), uint64_t(p.nseg)};
+    uint64_t strides[4] = {uint64_t(d.cin) * 2, uint64_t(d.win) * d.cin * 2, uint64_t(d.hin) * d.win * d.cin * 2,
+                           uint64_t(d.batch) * d.hin * d.win * d.cin * 2};
+    uint32_t box[5] = {TC_BLOCK_K, TH_BOX_W, TH_BOX_H, 1, 1};
+    int rc = encode_map_bf16(&mx, x, 5, dims, strides, box, nullptr);
+    if (rc) return rc;
+  } else {
     const uint32_t is = uint32_t(d.in_stride);
     // [planes][B][H][W][C]: the split-operand planes are the outermost dimension (1 plane for plain bf16)
     uint64_t dims[5] = {uint64_t(d.cin), uint64_t(d.win), uint64_t(d.hin), uint64_t(d.batch), uint64_t(p.nseg)};
@@ -742,6 +812,12 @@ static int conv_tc_dispatch(void* y, const void* x, const void* w, const float* 
     uint32_t box[4] = {TC_BLOCK_K, uint32_t(two_cta ? block_n / 2 : block_n), 1, 1};
     int rc = encode_map_bf16(&mw, w, 4, dims, strides, box, nullptr);
     if (rc) return rc;
+  }
+  if (halo) {
+    if (split) return launch_tc2h<128, true, true>(mx, mw, p, st);
+    if (block_n == 256)
+      return d.out_f32 ? launch_tc2h<256, true>(mx, mw, p, st) : launch_tc2h<256, false>(mx, mw, p, st);
+    return d.out_f32 ? launch_tc2h<128, true>(mx, mw, p, st) : launch_tc2h<128, false>(mx, mw, p, st);
   }
   if (split) {
     if (two_cta) return launch_tc2<128, true, true>(mx, mw, p, st);
