@@ -1,0 +1,116 @@
+"""te_upfirdn2d / te_fused_bias_act against the REFERENCE'S OWN CUDA kernels (utils/op/upfirdn2d_kernel.cu,
+fused_bias_act_kernel.cu, JIT-built for sm_100a the way utils/op/fused_act.py:9-15 and upfirdn2d.py:8-14 build them),
+and the Generator / Discriminator against the reference's classes on the same GPU.  Needs the unmodified reference
+tree on the box (baseline/_ref, installed by tools/install_reference.py and shipped by gpurun); skipped without it.
+Bar: f32, max-abs <= 1e-5 of the output scale per op (both sides are f32 kernels with different summation orders);
+model outputs < 1e-3 (BASELINE.json)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_gpu, te_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def ref_ops():
+    if ref_gpu.reference_root() is None:
+        pytest.skip("no reference tree on this machine (baseline/_ref)")
+    try:
+        return ref_gpu.load_reference_ops()
+    except Exception as e:  # toolchain trouble must not fail the product's suite
+        pytest.skip("reference CUDA extensions did not build: %s" % str(e)[:200])
+
+
+def _rand(*shape, seed=0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed)).to(DEV)
+
+
+@pytest.mark.parametrize("case", [
+    # (n, c, h, w, up, down, pad): the live parameter sets of the path and their gradients
+    (2, 8, 33, 33, 1, 1, (1, 1)), (2, 8, 32, 32, 1, 1, (2, 2)), (2, 3, 16, 16, 2, 1, (2, 1)), (2, 8, 32, 32, 1, 2, (1, 1)),
+    (1, 4, 64, 48, 1, 1, (2, 1)), (4, 16, 65, 65, 1, 1, (1, 1)),
+])
+def test_upfirdn2d_matches_the_reference_kernel(ref_ops, case):
+    from utils.op import upfirdn2d
+    _, ref_up = ref_ops
+    n, c, h, w, up, down, pad = case
+    fir = torch.outer(torch.tensor([1., 3., 3., 1.]), torch.tensor([1., 3., 3., 1.]))
+    fir = (fir / fir.sum() * up * up).to(DEV)
+    outs = []
+    for fn in (upfirdn2d, ref_up.upfirdn2d):
+        x = _rand(n, c, h, w, seed=1).requires_grad_(True)
+        y = fn(x, fir, up=up, down=down, pad=pad)
+        gy = _rand(*y.shape, seed=2).requires_grad_(True)
+        (gx,) = torch.autograd.grad(y, x, gy, create_graph=True)
+        (gg,) = torch.autograd.grad(gx, gy, _rand(*gx.shape, seed=3))
+        outs.append((y.detach(), gx.detach(), gg.detach()))
+    for a, r in zip(*outs):
+        assert a.shape == r.shape
+        assert (a - r).abs().max().item() <= 1e-5 * max(1.0, r.abs().max().item())
+
+
+def test_fused_leaky_relu_matches_the_reference_kernel(ref_ops):
+    from utils.op import fused_leaky_relu
+    ref_fa, _ = ref_ops
+    outs = []
+    for fn in (fused_leaky_relu, ref_fa.fused_leaky_relu):
+        x = _rand(4, 16, 32, 32, seed=4).requires_grad_(True)
+        b = _rand(16, seed=5).requires_grad_(True)
+        y = fn(x, b)
+        gy = _rand(*y.shape, seed=6).requires_grad_(True)
+        gx, gb = torch.autograd.grad(y, (x, b), gy, create_graph=True)
+        (gg,) = torch.autograd.grad((gx * _rand(*gx.shape, seed=7)).sum() + (gb * _rand(16, seed=8)).sum(), gy)
+        outs.append((y.detach(), gx.detach(), gb.detach(), gg.detach()))
+    for a, r in zip(*outs):
+        assert (a - r).abs().max().item() <= 1e-5 * max(1.0, r.abs().max().item())
+
+
+def test_flagship_blur_equals_the_reference_kernel_and_is_faster(ref_ops):
+    """[16, 128, 257, 257] -> 256^2 (BASELINE's upfirdn2d flagship) in the reference's own layout and dtype."""
+    from utils.op import upfirdn2d
+    _, ref_up = ref_ops
+    fir = torch.outer(torch.tensor([1., 3., 3., 1.]), torch.tensor([1., 3., 3., 1.]))
+    fir = (fir / fir.sum()).to(DEV)
+    x = _rand(16, 128, 257, 257, seed=9)
+    a, r = upfirdn2d(x, fir, pad=(1, 1)), ref_up.upfirdn2d(x, fir, pad=(1, 1))
+    assert (a - r).abs().max().item() <= 1e-5 * max(1.0, r.abs().max().item())
+
+    def ms(fn):
+        for _ in range(2):
+            fn(x, fir, pad=(1, 1))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            fn(x, fir, pad=(1, 1))
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 5
+    ours, theirs = ms(upfirdn2d), ms(ref_up.upfirdn2d)
+    print("upfirdn2d flagship f32 NCHW: ours %.3f ms, reference kernel %.3f ms" % (ours, theirs))
+    assert ours < theirs
+
+
+@pytest.mark.parametrize("size,batch", [(64, 2), (256, 1)])
+def test_models_match_the_reference_classes_on_the_gpu(ref_ops, size, batch):
+    import model_spatial_query as M
+    ref = ref_gpu.load_reference_model()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    t = 2 * int(np.log2(size)) - 2
+    sdg = O.synthetic_state(O.generator_shapes(size, 2))
+    sdd = O.synthetic_state(O.discriminator_shapes(size, 2))
+    outs = []
+    for mod in (M, ref):
+        g = mod.Generator(size, 512, 512, t, channel_multiplier=2, n_trans=8, pixel_norm_op_dim=1).to(DEV).eval()
+        d = mod.Discriminator(size, channel_multiplier=2).to(DEV).eval()
+        g.load_state_dict(sdg, strict=True)
+        d.load_state_dict(sdd, strict=True)
+        z, p = _rand(batch, 512, 16, seed=11), _rand(batch, 512, 16, seed=12)
+        with torch.no_grad():
+            img, lat, _ = g(z, p, return_latents=True)
+            outs.append((img, lat, d(img)))
+    for a, r in zip(*outs):
+        assert (a - r).abs().max().item() < 1e-3
