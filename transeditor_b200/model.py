@@ -83,6 +83,21 @@ def _to_bf16_cl(x, pad_to=8):
     return _to_cl(x, torch.bfloat16, pad_to)
 
 
+class _DenseGrad(torch.autograd.Function):
+    """Identity whose gradient comes back dense in the INPUT's layout.  The tensor-core routes run channels-last
+    inside, so d(out)/d(image) would reach the caller as a permuted view; the reference's R1 penalty calls
+    `.view(batch, -1)` on it (train_spatial_query.py:81), which needs the NCHW-contiguous gradient cuDNN returns."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.channels_last = x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous()
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.contiguous(memory_format=torch.channels_last) if ctx.channels_last else g.contiguous()
+
+
 _SIDE_STREAMS = {}
 
 
@@ -957,6 +972,8 @@ class Discriminator(nn.Module):
         e.g. cat([fake, real]) — so ONE pass gives exactly the logits of separate calls: every layer is
         per-sample except the minibatch standard deviation, which is taken per sub-batch."""
         bf16 = _tc_mode() and input.dtype in (torch.float32, torch.bfloat16)
+        if bf16 and input.requires_grad and torch.is_grad_enabled():
+            input = _DenseGrad.apply(input)
         # tensor-core modes: the whole conv stack incl. final_conv on tensor cores; statistics and linears in f32
         # RGB is zero-padded to 64 channels: a TMA box whose rows are mostly out of bounds (8 of 64 channels)
         # takes the unit's slow path (measured 4 us per tile); a dense 128-byte row costs 134 MB of extra
