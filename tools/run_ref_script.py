@@ -13,7 +13,12 @@ baseline/_ref, or /root/reference); only the PROCESS ENVIRONMENT is adapted (SUR
     in-memory store of synthetic PNG images behind lmdb's API, so the reference's own `MultiResolutionDataset`
     (utils/dataset.py) runs as written, PIL decode included;
   * `torchvision.utils.save_image(range=...)` (renamed `value_range` since torchvision 0.13);
-  * `--local_rank` from $LOCAL_RANK when launched by torchrun (the script predates it).
+  * `--local_rank` from $LOCAL_RANK when launched by torchrun (the script predates it);
+  * under torchrun: torch >= 1.10's DistributedDataParallel(find_unused_parameters=True) hands the module's outputs
+    through an autograd sink that returns NEW tensor objects; the script's path regulariser differentiates one output
+    (the image) with respect to another (the latents, train_spatial_query.py:96-98), which only works on the original
+    tensors, as torch 1.7 (the authors' version) returned them.  The sink is a pass-through when static_graph is off,
+    so it is replaced by the identity — torch 1.7's behaviour; the reducer is prepared in forward either way.
 """
 import argparse
 import io
@@ -107,6 +112,12 @@ def _patch_save_image():
     tvu.save_image = save_image
 
 
+def _patch_ddp_sink():
+    import torch.nn.parallel.distributed as ddp
+    if hasattr(ddp, "_DDPSink"):
+        ddp._DDPSink.apply = lambda ddp_weakref, *inputs: tuple(inputs)
+
+
 def main():
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     ap.add_argument("--ref", default=None, help="reference tree (default: $TE_REFERENCE_ROOT, baseline/_ref, /root/reference)")
@@ -146,6 +157,8 @@ def main():
             and os.path.basename(script).startswith("train"):
         argv.append("--local_rank=%s" % os.environ["LOCAL_RANK"])
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        _patch_ddp_sink()
     if a.workdir:
         os.makedirs(a.workdir, exist_ok=True)
         os.chdir(a.workdir)
