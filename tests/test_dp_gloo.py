@@ -83,3 +83,57 @@ def test_two_rank_flat_allreduce_adam_matches_single_process():
         o = ref.offsets[n]
         got = out[0][o:o + p.numel()].view(p.shape)
         assert torch.allclose(got, p.detach(), atol=1e-6), n
+
+
+def _bucket_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from transeditor_b200.train_step import FlatParams, GradBuckets
+    torch.manual_seed(5)
+    m = torch.nn.Sequential(torch.nn.Linear(9, 16), torch.nn.Tanh(), torch.nn.Linear(16, 16), torch.nn.Tanh(),
+                            torch.nn.Linear(16, 4))
+    unused = torch.nn.Parameter(torch.ones(5))           # never receives a gradient (the noise strengths' case)
+    m.register_parameter("unused", unused)
+    flat = FlatParams(m, [lambda n: n == "unused"])
+    buckets = GradBuckets(flat, world, bucket_mb=100 * 4 / (1 << 20))   # ~100 floats per bucket -> several buckets
+    assert len(buckets.buckets) >= 3
+    assert buckets.buckets[0][0] == 0 and buckets.buckets[-1][1] == flat.numel
+    for step in range(2):
+        x = torch.randn(6, 9, generator=torch.Generator().manual_seed(10 * step + rank))
+        buckets.begin()
+        m(x).square().sum().backward()
+        buckets.finish()
+        assert all(p.grad is None for _, p in flat.params)
+    out[rank] = flat.grad.clone()
+    dist.destroy_process_group()
+
+
+def test_bucketed_overlapped_allreduce_sums_the_ranks_gradients():
+    """GradBuckets (hooks + per-bucket all-reduce during backward) == the plain sum of the ranks' gradients, zeros
+    for parameters without a gradient."""
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_bucket_worker, args=(world, port, out), nprocs=world, join=True)
+    assert torch.equal(out[0], out[1])
+    torch.manual_seed(5)
+    m = torch.nn.Sequential(torch.nn.Linear(9, 16), torch.nn.Tanh(), torch.nn.Linear(16, 16), torch.nn.Tanh(),
+                            torch.nn.Linear(16, 4))
+    m.register_parameter("unused", torch.nn.Parameter(torch.ones(5)))
+    from transeditor_b200.train_step import FlatParams
+    ref = FlatParams(m, [lambda n: n == "unused"])
+    want = torch.zeros_like(ref.grad)
+    for rank in range(world):
+        x = torch.randn(6, 9, generator=torch.Generator().manual_seed(10 + rank))
+        for _, p in ref.params:
+            p.grad = None
+        m(x).square().sum().backward()
+        for n, p in ref.params:
+            if p.grad is not None:
+                o = ref.offsets[n]
+                want[o:o + p.numel()] += p.grad.reshape(-1)
+    assert torch.allclose(out[0], want, atol=1e-6)
+    o = ref.offsets["unused"]
+    assert out[0][o:o + 5].abs().sum().item() == 0

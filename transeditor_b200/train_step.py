@@ -120,6 +120,112 @@ class FlatParams:
             p.grad = None
 
 
+class GradBuckets:
+    """DDP-style overlapped gradient exchange for a FlatParams (what torch's DistributedDataParallel does for the
+    reference, train_spatial_query.py:495-509): the flat buffer is cut into contiguous buckets of ~`bucket_mb`; a
+    post-accumulate-grad hook on every parameter counts arrivals, and as soon as a bucket's parameters all have their
+    gradients these are copied into the bucket's slice of the flat buffer and ONE all-reduce of that slice is issued
+    on a side stream — while the backward pass keeps running on the computing stream.  Backward produces the LAST
+    layers' gradients first, so by the time it reaches the first layers most of the buffer is already reduced; only
+    the final bucket's all-reduce is exposed.  `finish()` flushes what is left (parameters that received no gradient
+    stay zero, like the flat gather they replace) and joins the side stream.  Everything is stream-ordered (events,
+    no host synchronisation), so the whole exchange is captured inside the phase's CUDA graph."""
+
+    def __init__(self, flat, world, bucket_mb=25.0):
+        self.flat, self.world = flat, world
+        self.buckets = []   # [lo, hi, [(name, param)]]
+        cur, lo = [], 0
+        limit = int(bucket_mb * (1 << 20) / 4)
+        for name, p in flat.params:
+            cur.append((name, p))
+            hi = flat.offsets[name] + (p.numel() + 3) // 4 * 4
+            if hi - lo >= limit:
+                self.buckets.append([lo, hi, cur])
+                cur, lo = [], hi
+        if cur:
+            self.buckets.append([lo, flat.numel, cur])
+        self._of = {}
+        for bi, (_, _, ps) in enumerate(self.buckets):
+            for _, p in ps:
+                self._of[id(p)] = bi
+        self._pending = [0] * len(self.buckets)
+        self._flushed = [True] * len(self.buckets)
+        self._arrived = [[] for _ in self.buckets]
+        self._held = []
+        self._active = False
+        self._side = None
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for _, p in flat.params]
+
+    def begin(self):
+        """Call right before backward(): zero the flat buffer, drop stale .grad tensors, arm the buckets."""
+        self.flat.grad.zero_()
+        for _, p in self.flat.params:
+            p.grad = None
+        for bi, (_, _, ps) in enumerate(self.buckets):
+            self._pending[bi] = sum(1 for _, p in ps if p.requires_grad)
+            self._flushed[bi] = False
+            self._arrived[bi] = []
+        self._held = []
+        self._active = True
+        if self.flat.grad.is_cuda:
+            if self._side is None:
+                self._side = torch.cuda.Stream(self.flat.grad.device)
+            # the zeroing above precedes every bucket's copy on the side stream
+            self._side.wait_stream(torch.cuda.current_stream(self.flat.grad.device))
+
+    def _on_grad(self, p):
+        if not self._active:
+            return
+        bi = self._of[id(p)]
+        if p.grad is not None and p.grad.is_cuda:
+            # autograd runs AccumulateGrad on the stream the parameter was first used on (the generator's style work
+            # lives on a side stream): remember where this gradient became final
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(p.grad.device))
+            self._arrived[bi].append(ev)
+        self._pending[bi] -= 1
+        if self._pending[bi] == 0 and not self._flushed[bi]:
+            self._flush(bi)
+
+    def _flush(self, bi):
+        lo, hi, ps = self.buckets[bi]
+        self._flushed[bi] = True
+        views, grads = [], []
+        for name, p in ps:
+            if p.grad is not None:
+                o = self.flat.offsets[name]
+                views.append(self.flat.grad[o:o + p.numel()].view(p.shape))
+                grads.append(p.grad)
+            p.grad = None
+        chunk = self.flat.grad[lo:hi]
+        if chunk.is_cuda:
+            # copy + all-reduce on the side stream, after every gradient of the bucket is final; the gradient tensors
+            # stay referenced until finish() so that their memory is not handed out again while the side stream reads it
+            self._held.append(grads)
+            for ev in self._arrived[bi]:
+                self._side.wait_event(ev)
+            with torch.cuda.stream(self._side):
+                if grads:
+                    torch._foreach_copy_(views, grads)
+                if self.world > 1:
+                    dist.all_reduce(chunk, op=dist.ReduceOp.SUM)
+        else:
+            if grads:
+                torch._foreach_copy_(views, grads)
+            if self.world > 1:
+                dist.all_reduce(chunk, op=dist.ReduceOp.SUM)
+
+    def finish(self):
+        """Call after backward(): flush the buckets that never filled, wait for the exchanges."""
+        for bi in range(len(self.buckets) - 1, -1, -1):
+            if not self._flushed[bi]:
+                self._flush(bi)
+        self._active = False
+        if self._side is not None:
+            torch.cuda.current_stream(self.flat.grad.device).wait_stream(self._side)
+        self._held = []
+
+
 class FlatAdam:
     """torch.optim.Adam semantics on a FlatParams through te_adam_ema."""
 
@@ -224,6 +330,9 @@ class Trainer:
         self._packs = tc.PackCache()
         self._packs.register(p for _, p in self.g_flat.params + self.d_flat.params)
         self._ema_in_step = False  # set per phase by step(): the LAST generator update of an iteration carries the EMA
+        # gradient exchange overlapped with backward (N > 1): bucketed all-reduces issued from autograd hooks
+        self.g_buckets = GradBuckets(self.g_flat, self.world) if self.world > 1 else None
+        self.d_buckets = GradBuckets(self.d_flat, self.world) if self.world > 1 else None
 
     def weights_changed(self):
         """Call after modifying generator / discriminator weights outside this trainer's optimiser steps
@@ -275,9 +384,7 @@ class Trainer:
             # capturing does not execute: undo the step counters' host-side bookkeeping is not needed (device
             # counters are only incremented by the captured add_ when the graph runs)
         gb, step_launches = steps[with_ema]
-        ga.replay()
-        if self.world > 1:
-            dist.all_reduce(flat.grad, op=dist.ReduceOp.SUM)
+        ga.replay()   # N > 1: the bucketed NCCL all-reduces are part of the captured graph
         gb.replay()
         lib.launch_count += launches + step_launches
 
@@ -288,9 +395,19 @@ class Trainer:
         p = torch.randn(n, c.latent, c.para_num, device=self.device)  # utils/sample.py:10
         return z, p
 
+    def _backward(self, loss, flat, buckets):
+        """loss.backward() with the gradients landing in `flat.grad` — summed over ranks when N > 1 (bucketed
+        all-reduces overlapped with the backward pass, GradBuckets); N = 1: one flat gather at the end."""
+        if buckets is None:
+            flat.clear_grads()
+            loss.backward()
+            flat.gather_grads()
+            return
+        buckets.begin()
+        loss.backward()
+        buckets.finish()
+
     def _reduce_and_step(self, flat, optim, n_groups, with_ema=False):
-        if self.world > 1:
-            dist.all_reduce(flat.grad, op=dist.ReduceOp.SUM)
         self._step_optim(flat, optim, n_groups, with_ema)
 
     def _d_fwdbwd(self):
@@ -302,9 +419,7 @@ class Trainer:
         # (train_spatial_query.py:199-201), half the launches and weight repacks
         fake_pred, real_pred = self.discriminator.forward_stacked(torch.cat([fake_img, self._real]), 2).chunk(2)
         d_loss = d_logistic_loss(real_pred, fake_pred)
-        self.d_flat.clear_grads()
-        d_loss.backward()
-        self.d_flat.gather_grads()
+        self._backward(d_loss, self.d_flat, self.d_buckets)
         self.losses.update(d=d_loss.detach(), real_score=real_pred.mean().detach(),
                            fake_score=fake_pred.mean().detach())
 
@@ -314,9 +429,7 @@ class Trainer:
         real_img = self._real.detach().requires_grad_(True)
         real_pred = self.discriminator(real_img)
         r1_loss = d_r1_loss(real_pred, real_img)
-        self.d_flat.clear_grads()
-        (self.cfg.r1 / 2 * r1_loss * self.cfg.d_reg_every + 0 * real_pred[0]).backward()
-        self.d_flat.gather_grads()
+        self._backward(self.cfg.r1 / 2 * r1_loss * self.cfg.d_reg_every + 0 * real_pred[0], self.d_flat, self.d_buckets)
         self.losses["r1"] = r1_loss.detach()
 
     def _g_fwdbwd(self):
@@ -325,9 +438,7 @@ class Trainer:
         z, p = self._latents(self.cfg.batch)
         fake_img, _, _ = self.generator(z, p)
         g_loss = g_nonsaturating_loss(self.discriminator(fake_img))
-        self.g_flat.clear_grads()
-        g_loss.backward()
-        self.g_flat.gather_grads()
+        self._backward(g_loss, self.g_flat, self.g_buckets)
         self.losses["g"] = g_loss.detach()
 
     def _greg_fwdbwd(self):
@@ -338,12 +449,10 @@ class Trainer:
         z, p = self._latents(n)
         fake_img, latents, _ = self.generator(z, p, return_latents=True)
         path_loss, path_mean, path_lengths = g_path_regularize(fake_img, latents, self.mean_path_length)
-        self.g_flat.clear_grads()
         weighted = c.path_regularize * c.g_reg_every * path_loss
         if c.path_batch_shrink:
             weighted = weighted + 0 * fake_img[0, 0, 0, 0]
-        weighted.backward()
-        self.g_flat.gather_grads()
+        self._backward(weighted, self.g_flat, self.g_buckets)
         self.mean_path_length.copy_(path_mean)  # in place: a static buffer for graph replays
         self.losses.update(path=path_loss.detach(), path_length=path_lengths.mean().detach())
 
@@ -365,12 +474,10 @@ class Trainer:
             target.requires_grad_()
             fake_img, _, _ = self.generator(z, target, use_spatial_mapping=False)
         path_loss, path_mean, path_lengths = g_path_regularize(fake_img, target, self.mean_spatial_path_length)
-        self.g_flat.clear_grads()
         weighted = c.spatial_path_regularize * c.g_reg_every * path_loss
         if c.path_batch_shrink:
             weighted = weighted + 0 * fake_img[0, 0, 0, 0]
-        weighted.backward()
-        self.g_flat.gather_grads()
+        self._backward(weighted, self.g_flat, self.g_buckets)
         self.mean_spatial_path_length.copy_(path_mean)
         self.losses.update(spatial_path=path_loss.detach(), spatial_path_length=path_lengths.mean().detach())
 
@@ -438,10 +545,30 @@ class Trainer:
         self.iteration += 1
         return self.losses
 
+    def reduced_losses(self):
+        """The loss dictionary averaged over ranks on rank 0 — `reduce_loss_dict` (utils/distributed.py:102-124, called
+        at train_spatial_query.py:296): one stacked [n] vector, dist.reduce(dst=0), divided by the world size there;
+        the other ranks keep their local values, like the reference.  Returns (keys, stacked device tensor)."""
+        keys = sorted(self.losses)
+        vec = torch.stack([self.losses[k].float() for k in keys])
+        if self.world > 1:
+            dist.reduce(vec, dst=0)
+            if self.rank == 0:
+                vec = vec / self.world
+        return keys, vec
+
+    def mean_path_length_avg(self):
+        """`reduce_sum(mean_path_length).item() / world_size` (train_spatial_query.py:248-250): the logged average of
+        the ranks' running path-length means (each rank keeps its own running mean, as in the reference)."""
+        v = self.mean_path_length.detach().clone()
+        if self.world > 1:
+            dist.all_reduce(v, op=dist.ReduceOp.SUM)
+        return v / self.world
+
     def step_from_host(self, real_pinned):
-        """End-to-end form: host (pinned) images in, host loss scalars out."""
+        """End-to-end form: host (pinned) images in, host loss scalars out (rank-averaged on rank 0)."""
         self._set_real(real_pinned)  # H2D straight into the static input buffer
-        losses = self.step(self._real)
-        keys = sorted(losses)
-        host = torch.stack([losses[k].float() for k in keys]).cpu()  # D2H + sync, like the .item()s at :298-306
+        self.step(self._real)
+        keys, vec = self.reduced_losses()
+        host = vec.cpu()  # D2H + sync, like the .item()s at :298-306
         return dict(zip(keys, host.tolist()))
