@@ -10,8 +10,9 @@ EMA.  Per-rank batch 16, synthetic images / latents, random-init weights (same s
 weak scaling.  Prints ONE JSON line on rank 0.
 
   value     device-resident inputs, CUDA-event timed, max over ranks
-  e2e       the same steps through Trainer.step_from_host: pinned host images copied H2D and the
-            loss scalars read back D2H inside the timed region
+  e2e       the same steps through Trainer.step_from_host_uint8: decoded uint8 pixels + flip coins copied H2D from
+            pinned memory, the loader transform's tail on the device (te_image_prep), the loss scalars read back D2H
+            — all inside the timed region
   roofline  dominant kernel of the step, measured live with CUDA events in one instrumented step
   cpu_baseline  the oracle's CPU train iteration on a bounded sample (rank 0, N=1)
 
@@ -283,13 +284,18 @@ def _cpu_threads():
     return max(1, min(os.cpu_count() or 1, 32))
 
 
+_KIND_TEXT = {"reference": "the reference's own classes (unmodified model_spatial_query.py from baseline/_ref, pure-torch "
+                           "utils.op stub, torch.optim.Adam) looped like train_spatial_query.py:166-306 on the host cores",
+              "port": "oracle CPU port of the train loop (oracle/train_cpu.py)"}
+
+
 def cpu_train_rate(steps, warmup, batch=1, seconds_cap=None, lazy=True):
     """images/sec of the oracle's CPU train iteration on a bounded sample (batch `batch` per step).
     lazy=False leaves out the R1 / path-length regularisers (plain D step + G step)."""
-    from oracle.train_cpu import CpuTrainer
+    from oracle.train_cpu import make_trainer
     cores = _cpu_threads()
     torch.set_num_threads(cores)
-    tr = CpuTrainer(size=256, batch=batch)
+    tr, kind = make_trainer(size=256, batch=batch)
     real = torch.rand(batch, 3, 256, 256) * 2 - 1
     for _ in range(warmup):
         tr.it = 1  # warm-up steps without the lazy regularisers
@@ -305,22 +311,22 @@ def cpu_train_rate(steps, warmup, batch=1, seconds_cap=None, lazy=True):
         if seconds_cap and time.perf_counter() - t0 > seconds_cap:
             break
     dt = time.perf_counter() - t0
-    return done * batch / dt, cores, done, dt
+    return done * batch / dt, cores, done, dt, kind
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
     # bounded: a CPU iteration takes seconds, so the timed region stops after ~2.5 minutes whatever --steps says
-    rate, cores, done, dt = cpu_train_rate(args.steps, min(args.warmup, 1), batch=1, seconds_cap=150)
-    sample = ("oracle CPU port of the train loop (oracle/train_cpu.py), 256^2, batch 1 per step, "
-              "%d timed steps incl. lazy R1 (i%%16==0) and path (i%%4==0), fp32, %d torch threads" % (done, cores))
+    rate, cores, done, dt, kind = cpu_train_rate(args.steps, min(args.warmup, 1), batch=1, seconds_cap=150)
+    sample = ("%s, 256^2, batch 1 per step, %d timed steps incl. lazy R1 (i%%16==0) and path (i%%4==0), fp32, "
+              "%d torch threads" % (_KIND_TEXT[kind], done, cores))
     line = {"impl": "reference", "metric": METRIC, "value": round(rate, 4), "unit": UNIT,
             "n_gpus": args.gpus, "steps": done, "warmup": min(args.warmup, 1),
             "ms_per_step": round(dt / done * 1e3, 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "sample": "batch 1 per step on host cores"},
-            "cpu_baseline": {"value": round(rate, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": round(rate, 4), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": round(rate, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -346,8 +352,12 @@ def run_ours(args, rank, local_rank, world):
     trainer = Trainer(cfg, dev, seed=0)
 
     gen = torch.Generator().manual_seed(4321 + rank)
-    real_host = (torch.rand(cfg.batch, 3, cfg.size, cfg.size, generator=gen) * 2 - 1).pin_memory()
-    real_dev = real_host.to(dev)
+    # synthetic DECODED images: uint8 HWC pixels + RandomHorizontalFlip coins, what the loader's decode step yields
+    # (utils/dataset.py:38-39); the transform's tail runs on the device (transeditor_b200/data.py)
+    from transeditor_b200 import data as te_data
+    u8_host = torch.randint(0, 256, (cfg.batch, cfg.size, cfg.size, 3), generator=gen, dtype=torch.uint8).pin_memory()
+    flip_host = torch.randint(0, 2, (cfg.batch,), generator=gen, dtype=torch.uint8).pin_memory()
+    real_dev = te_data.image_prep(u8_host.to(dev), flip_host.to(dev))
 
     def barrier():
         if world > 1:
@@ -405,7 +415,7 @@ def run_ours(args, rank, local_rank, world):
     ms, launches = timed(trainer.step, real_dev, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     trainer.iteration = 0
-    ms_e2e, _ = timed(trainer.step_from_host, real_host, args.steps)
+    ms_e2e, _ = timed(lambda u8: trainer.step_from_host_uint8(u8, flip_host), u8_host, args.steps)
 
     # one instrumented step (plain D+G, plus the lazy regularisers) for the per-kernel roofline
     meter = KernelMeter()
@@ -442,7 +452,9 @@ def run_ours(args, rank, local_rank, world):
                                             "for the timed region",
                        "l2": "no explicit flush: each step streams several GB of activations, far above the 126 MB L2"},
             "e2e": {"value": round(images / (ms_e2e * 1e-3), 3), "unit": UNIT,
-                    "h2d_bytes_per_step": real_host.numel() * 4, "d2h_bytes_per_step": 4 * len(trainer.losses),
+                    "h2d_bytes_per_step": u8_host.numel() + flip_host.numel(),
+                    "d2h_bytes_per_step": 4 * len(trainer.losses),
+                    "input": "uint8 HWC pixels + flip coins from pinned host memory; te_image_prep on the device",
                     "ms_per_step": round(ms_e2e / args.steps, 3)},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": table,
             "timing_check": timing_checks}
@@ -477,10 +489,10 @@ def run_ours(args, rank, local_rank, world):
         del tr32
         te_model.set_precision(args.precision)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, cores, done, dt = cpu_train_rate(2, 0, batch=1, seconds_cap=20, lazy=False)
-        line["cpu_baseline"] = {"value": round(rate, 4), "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": "oracle CPU port (oracle/train_cpu.py), 256^2, batch 1 per step, %d plain "
-                                          "iterations (D step + G step, no lazy regularisers), %.1f s" % (done, dt)}
+        rate, cores, done, dt, kind = cpu_train_rate(2, 0, batch=1, seconds_cap=20, lazy=False)
+        line["cpu_baseline"] = {"value": round(rate, 4), "unit": UNIT, "cores": cores, "kind": kind,
+                                "sample": "%s, 256^2, batch 1 per step, %d plain iterations (D step + G step, no lazy "
+                                          "regularisers), %.1f s" % (_KIND_TEXT[kind], done, dt)}
     if rank == 0:
         print(json.dumps(line), flush=True)
 

@@ -299,6 +299,32 @@ int te_attn_stack_bwd(float* g_x0, float* g_p0, float* g_p, const te_attn_block*
                       int n_blocks, int batch, float lr_mul, int precision, const float* save, float* gws,
                       void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Data formats either side of the path.
+ *
+ * te_image_prep — the device-side tail of the reference's input pipeline: `self.transform(img)` in
+ * utils/dataset.py:38-41 with the transform built at train_spatial_query.py:511-517
+ * (RandomHorizontalFlip, ToTensor, Normalize(0.5, 0.5, inplace)).  The host keeps the entropy decode
+ * (PIL, as in the reference) and the coin flips; the H2D copy carries uint8 pixels (1/4 of the f32 bytes).
+ *   src_hwc  uint8 [B, H, W, 3]   decoded RGB pixels (np.asarray(PIL image))
+ *   flip     uint8 [B] or NULL    1 = mirror that image horizontally
+ *   dst_nchw f32 [B, 3, H, W] or NULL   ((x / 255) - 0.5) / 0.5, bit-identical to the torch ops
+ *   dst_nhwc8 [B, H, W, 8] of nhwc_dtype (TE_F32 / TE_BF16) or NULL: the same values channels-last with
+ *            the three channels zero-padded to 8 (the tensor-core from-RGB convolution's operand)
+ *
+ * te_image_quantize — network output to pixels: torchvision.utils.save_image(normalize=True,
+ * range=(low, high)) per element (test_spatial_query.py:82-88, train_spatial_query.py:345-351):
+ * clamp(x, low, high); (x - low) / max(high - low, 1e-5); * 255; + 0.5; clamp(0, 255); truncate.
+ *   src   [B, 3, H, W] elements of `dtype` (TE_F32 / TE_BF16) addressed through the four element strides
+ *         (NCHW or channels-last storage)
+ *   dst_hwc uint8 [B, H, W, 3]
+ */
+int te_image_prep(float* dst_nchw, void* dst_nhwc8, const uint8_t* src_hwc, const uint8_t* flip, int batch,
+                  int h, int w, int nhwc_dtype, void* stream);
+int te_image_quantize(uint8_t* dst_hwc, const void* src, int batch, int h, int w, int64_t stride_b,
+                      int64_t stride_c, int64_t stride_y, int64_t stride_x, float low, float high, int dtype,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

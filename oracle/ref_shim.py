@@ -19,7 +19,17 @@ import types
 
 import torch
 
-REFERENCE_ROOT = os.environ.get("TE_REFERENCE_ROOT", "/root/reference")
+def _default_root():
+    """TE_REFERENCE_ROOT, else /root/reference (the build container), else the unmodified copy that
+    tools/install_reference.py placed under baseline/_ref (git-ignored; it travels to the GPU box)."""
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for cand in (os.environ.get("TE_REFERENCE_ROOT"), "/root/reference", os.path.join(here, "baseline", "_ref")):
+        if cand and os.path.isfile(os.path.join(cand, "model_spatial_query.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _default_root()
 
 
 def available():

@@ -277,9 +277,27 @@ def pack_weights_tc(tasks):
             v = v - h.float()
 
 
+def image_prep(dst_nchw, dst_nhwc8, src_hwc, flip, batch, h, w):
+    x = src_hwc
+    if flip is not None:
+        x = torch.stack([img.flip(1) if int(f) else img for img, f in zip(x, flip)])
+    t = x.to(torch.float32).div(255).sub(0.5).div(0.5)
+    if dst_nchw is not None:
+        dst_nchw.copy_(t.permute(0, 3, 1, 2))
+    if dst_nhwc8 is not None:
+        dst_nhwc8.zero_()
+        dst_nhwc8[..., :3] = t.to(dst_nhwc8.dtype)
+
+
+def image_quantize(dst_hwc, src, low, high):
+    t = src.float().clamp(low, high).sub(low).div(max(high - low, 1e-5))
+    dst_hwc.copy_(t.mul(255).add_(0.5).clamp_(0, 255).permute(0, 2, 3, 1).to(torch.uint8))
+
+
 def install(monkeypatch):
     monkeypatch.setattr(lib, "require_cuda", lambda *a: None)
     for name in ("fused_bias_act", "fused_bias_act_bwd", "upfirdn2d", "conv2d_simt",
                  "conv2d_wgrad_simt", "attn_core", "adam_ema", "adam_ema_devstep", "scale_bc", "dot_bc",
-                 "attn_stack_fwd", "attn_stack_bwd", "pack_weights_tc", "conv_tc", "conv_wgrad_tc", "split_bf16"):
+                 "attn_stack_fwd", "attn_stack_bwd", "pack_weights_tc", "conv_tc", "conv_wgrad_tc", "split_bf16",
+                 "image_prep", "image_quantize"):
         monkeypatch.setattr(lib, name, globals()[name])

@@ -79,6 +79,8 @@ _SIGNATURES = {
     "te_gemm_tc_selftest": ([_P, _P, _P, _I, _I, _I, _P], _I),
     "te_attn_core": ([_P, _P, _P, _P, _P, _I, _I, _P], _I),
     "te_pack_weights_tc": ([ctypes.POINTER(PackTask), _I, _P], _I),
+    "te_image_prep": ([_P, _P, _P, _P, _I, _I, _I, _I, _P], _I),
+    "te_image_quantize": ([_P, _P, _I, _I, _I, _L, _L, _L, _L, _F, _F, _I, _P], _I),
     "te_attn_stack_workspace": ([ctypes.POINTER(AttnBlock), _I, _I, ctypes.POINTER(_L), ctypes.POINTER(_L)], _I),
     "te_attn_stack_occupancy": ([ctypes.POINTER(_I), ctypes.POINTER(_I)], _I),
     "te_attn_stack_fwd": ([_P, _P, _P, _P, ctypes.POINTER(AttnBlock), _I, _I, _F, _I, _P, _P], _I),
@@ -304,4 +306,19 @@ def dot_bc(out, a, b, batch, pixels, channels):
 
 def gemm_tc_selftest(d, a, b, m, n, k):
     _check(load().te_gemm_tc_selftest(ptr(d), ptr(a), ptr(b), m, n, k, stream()), "gemm_tc_selftest")
+    _count()
+
+
+def image_prep(dst_nchw, dst_nhwc8, src_hwc, flip, batch, h, w):
+    code = TE_F32 if dst_nhwc8 is None else dtype_code(dst_nhwc8)
+    _check(load().te_image_prep(ptr(dst_nchw), ptr(dst_nhwc8), ptr(src_hwc), ptr(flip), batch, h, w, code, stream()),
+           "image_prep")
+    _count()
+
+
+def image_quantize(dst_hwc, src, low, high):
+    b, _, h, w = src.shape
+    sb, sc, sy, sx = src.stride()
+    _check(load().te_image_quantize(ptr(dst_hwc), ptr(src), b, h, w, sb, sc, sy, sx, low, high, dtype_code(src),
+                                    stream()), "image_quantize")
     _count()

@@ -40,7 +40,7 @@ _SPLIT_PLANES = 2
 
 def set_split_planes(n):
     """Planes used for f32 activations: 2 (three products, ~2^-16 per product: the default) or 3 (six products,
-    twice the cost).  Measured image max-abs error against the reference goldens / the CPU oracle on B200
+    twice the cost).  Measured image max-abs error against the reference goldens / the CPU restatement on B200
     (profiles/r02_parity_modes_v2.txt): 2 planes 2.2e-4 at 256^2 and 4.5e-4 at 1024^2; 3 planes 9.6e-5 and 1.9e-4;
     the exact-f32 SIMT engine 4.2e-5 and 9.7e-5 — all inside the 1e-3 bar."""
     global _SPLIT_PLANES

@@ -14,6 +14,7 @@ groups match DDP semantics, model_spatial_query.py:845-852).  The only data-path
 the gradient sum (averaged by world size like DDP).
 """
 import math
+import os
 
 import torch
 import torch.distributed as dist
@@ -331,8 +332,11 @@ class Trainer:
         self._packs.register(p for _, p in self.g_flat.params + self.d_flat.params)
         self._ema_in_step = False  # set per phase by step(): the LAST generator update of an iteration carries the EMA
         # gradient exchange overlapped with backward (N > 1): bucketed all-reduces issued from autograd hooks
-        self.g_buckets = GradBuckets(self.g_flat, self.world) if self.world > 1 else None
-        self.d_buckets = GradBuckets(self.d_flat, self.world) if self.world > 1 else None
+        # (TE_GRAD_BUCKETS=0: one flat all-reduce after the backward pass instead; TE_GRAD_BUCKET_MB sizes the buckets)
+        overlap = self.world > 1 and os.environ.get("TE_GRAD_BUCKETS", "1") != "0"
+        mb = float(os.environ.get("TE_GRAD_BUCKET_MB", "25"))
+        self.g_buckets = GradBuckets(self.g_flat, self.world, mb) if overlap else None
+        self.d_buckets = GradBuckets(self.d_flat, self.world, mb) if overlap else None
 
     def weights_changed(self):
         """Call after modifying generator / discriminator weights outside this trainer's optimiser steps
@@ -402,6 +406,8 @@ class Trainer:
             flat.clear_grads()
             loss.backward()
             flat.gather_grads()
+            if self.world > 1:
+                dist.all_reduce(flat.grad, op=dist.ReduceOp.SUM)
             return
         buckets.begin()
         loss.backward()
@@ -564,6 +570,22 @@ class Trainer:
         if self.world > 1:
             dist.all_reduce(v, op=dist.ReduceOp.SUM)
         return v / self.world
+
+    def step_from_host_uint8(self, u8_pinned, flip_pinned=None):
+        """End-to-end form on the data path's own format: decoded uint8 [B, H, W, 3] pixels (pinned) and the
+        RandomHorizontalFlip coins in, host loss scalars out.  The H2D copy carries a quarter of the float32 bytes;
+        mirror / ToTensor / Normalize (train_spatial_query.py:511-517) run on the device in one kernel that writes
+        straight into the static input buffer the captured graphs read."""
+        from .data import DeviceImagePipeline
+        b, h, w, _ = u8_pinned.shape
+        if getattr(self, "_pipe", None) is None or self._pipe.u8.shape != u8_pinned.shape:
+            self._pipe = DeviceImagePipeline(b, h, self.device)
+        if self._real is None or self._real.shape != (b, 3, h, w):
+            self._set_real(torch.empty((b, 3, h, w), dtype=torch.float32, device=self.device))
+        self._pipe.load(u8_pinned, flip_pinned, out=self._real)
+        self.step(self._real)
+        keys, vec = self.reduced_losses()
+        return dict(zip(keys, vec.cpu().tolist()))
 
     def step_from_host(self, real_pinned):
         """End-to-end form: host (pinned) images in, host loss scalars out (rank-averaged on rank 0)."""
