@@ -635,6 +635,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 
 }  // namespace te
 #include "conv_tc_halo.cuh"
+#include "conv_tct.cuh"
 namespace te {
 
 template <int BLOCK_N, bool OUT_F32, bool SPLIT = false>
@@ -705,6 +706,7 @@ static int conv_tc_dispatch(void* y, const void* x, const void* w, const float* 
   p.n_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
   p.act = d.act; p.out_scale = out_scale; p.bias = bias; p.y = y;
   TE_CHECK_ARG(d.act >= 0 && d.act <= 3, "conv_tc: act must be 0, 1, 2 or 3");
+  TE_CHECK_ARG(d.act == 0 || d.act == 3 || !(d.act_gain < 0.f), "conv_tc: the activation gain must be positive");
   TE_CHECK_ARG(d.act != 3 || d.slope != nullptr, "conv_tc: act 3 (PReLU) needs the per-channel slopes");
   p.slope = static_cast<const float*>(d.slope);
   p.act_gain = d.act_gain != 0.f ? d.act_gain : (d.act == 2 ? 1.f : 1.4142135623730951f);
@@ -785,6 +787,30 @@ static int conv_tc_dispatch(void* y, const void* x, const void* w, const float* 
       two_cta = true;
     }
   }
+  // Operand-swapped kernel (conv_tct.cuh): channel tile of 128 only (Cout = 128 layers), 256-pixel tiles, enough of
+  // them to fill the chip.  TE_TC_SWAP=0 keeps those layers on the kernels above.
+  bool swapped = false;
+  if (!halo && !split && block_n == 128) {
+    static int use_swap = -1;
+    if (use_swap < 0) { const char* e = getenv("TE_TC_SWAP"); use_swap = e ? atoi(e) : 1; }
+    const int tw = next_pow2(d.grid_w) < 16 ? next_pow2(d.grid_w) : 16;
+    const int th_max = TT_BLOCK_N / tw;
+    const int th = next_pow2(d.grid_h) < th_max ? next_pow2(d.grid_h) : th_max;
+    const int nb = TT_BLOCK_N / (tw * th);
+    const int64_t tiles = int64_t((d.grid_w + tw - 1) / tw) * ((d.grid_h + th - 1) / th) * ((d.batch + nb - 1) / nb);
+    const int num_kb = d.ntaps * ((d.cin + TC_BLOCK_K - 1) / TC_BLOCK_K);   // light tiles (1x1 layers) are epilogue-bound:
+    swapped = use_swap != 0 && tw * th >= 32 && nb <= 256 && (use_swap == 2 || num_kb >= 8) &&   // they stay on the 4-chunk tiles
+              (use_swap == 2 || tiles * (d.cout / TT_BLOCK_M) >= kNumSMs) &&   // 2 = force (tests)
+              !(p.w_slices_per_sample && nb != 1);
+    if (swapped) {
+      p.tw = tw; p.th = th; p.nb = nb;
+      p.tiles_w = (d.grid_w + tw - 1) / tw;
+      p.tiles_h = (d.grid_h + th - 1) / th;
+      p.tiles_b = (d.batch + nb - 1) / nb;
+      p.n_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
+      two_cta = false;
+    }
+  }
   CUtensorMap mx, mw;
   if (halo) {
     uint64_t dims[5] = {uint64_t(d.cin), uint64_t(d.win), uint64_t(d.hin), uint64_t(d.batch), uint64_t(p.nseg)};
@@ -813,6 +839,7 @@ static int conv_tc_dispatch(void* y, const void* x, const void* w, const float* 
     int rc = encode_map_bf16(&mw, w, 4, dims, strides, box, nullptr);
     if (rc) return rc;
   }
+  if (swapped) return d.out_f32 ? launch_tct<true>(mx, mw, p, st) : launch_tct<false>(mx, mw, p, st);
   if (halo) {
     if (split) return launch_tc2h<128, true, true>(mx, mw, p, st);
     if (block_n == 256)
