@@ -325,6 +325,45 @@ int te_image_quantize(uint8_t* dst_hwc, const void* src, int batch, int h, int w
                       int64_t stride_c, int64_t stride_y, int64_t stride_x, float low, float high, int dtype,
                       void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Grouped EqualLinear (model_spatial_query.py:194-221) for the small-M linears of the path, many layers per
+ * launch: the 2 x 16 per-column mapping linears incl. their PixelNorm (:75-81, :626-646), the style modulations
+ * (ModulatedConv2d.modulation, :283), adjust_style (:686), the discriminator's final linears (:838-841), and —
+ * with w_trans — their data gradients.  f32 in and out; products on TF32 tensor cores: precision 0 = 3 x TF32
+ * (~1e-6 relative, the fp32 parity mode), 1 = single-pass TF32.
+ *   y[m, n] = act( alpha * r[m] * SUM_k x[m*x_rs + k*x_cs] * B(k, n) + bias[n] * bias_mul )
+ *   B(k, n) = w[n*w_ld + k] (w_trans 0) or w[k*w_ld + n] (w_trans 1);  y element (m, n) at y[m*y_rs + n*y_cs]
+ *   r[m] = rsqrt(mean_k x[m, k]^2 + 1e-8) when pixel_norm (K <= 512), else 1; written to rnorm_out[m] if not NULL
+ *   act 0: none; 1: leaky_relu(0.2) * sqrt(2) (fused_leaky_relu)
+ *   k_splits > 1: the reduction is cut into that many CTAs which atomically ADD into y (caller zeroes y; no act).
+ * `tasks` is a HOST array; all pointers in it are device pointers.
+ */
+typedef struct te_linear_task {
+  const float* x; int64_t x_rs, x_cs;
+  const float* w; int64_t w_ld; int w_trans;
+  const float* bias; float bias_mul;
+  float* y; int64_t y_rs, y_cs;
+  int m, n, k;
+  float alpha;
+  int act, pixel_norm, k_splits;
+  float* rnorm_out;
+} te_linear_task;
+int te_linear_grouped(const te_linear_task* tasks, int n_tasks, int precision, void* stream);
+
+/* Weight / bias gradients of the same layers, many per launch (exact f32 FMA; output-bound):
+ *   gw[n*k_dim + k] = alpha * SUM_m g[m*g_rs + n*g_cs] * x_scale[m] * x[m*x_rs + k*x_cs]
+ *   gbias[n] = bias_mul * SUM_m g[m, n]     (gbias may be NULL; x_scale may be NULL = 1)
+ * Writes, never accumulates. */
+typedef struct te_linear_wgrad_task {
+  const float* g; int64_t g_rs, g_cs;
+  const float* x; int64_t x_rs, x_cs;
+  const float* x_scale;
+  float* gw; float* gbias;
+  int m, n, k;
+  float alpha, bias_mul;
+} te_linear_wgrad_task;
+int te_linear_wgrad_grouped(const te_linear_wgrad_task* tasks, int n_tasks, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -277,6 +277,36 @@ def pack_weights_tc(tasks):
             v = v - h.float()
 
 
+def linear_grouped(tasks, tf32=False):
+    for t in tasks:
+        x, w = t["x"].double(), t["w"].double()
+        if t.get("pixel_norm"):
+            r = torch.rsqrt((x * x).mean(1, keepdim=True) + 1e-8)
+            if t.get("rnorm_out") is not None:
+                t["rnorm_out"].copy_(r[:, 0].float())
+            x = x * r
+        y = (x @ (w if t.get("w_trans") else w.t())) * t.get("alpha", 1.0)
+        if t.get("bias") is not None:
+            y = y + t["bias"].double() * t.get("bias_mul", 1.0)
+        if t.get("act"):
+            y = F.leaky_relu(y, 0.2) * 2 ** 0.5
+        if t.get("k_splits", 1) > 1:
+            t["y"].add_(y.float())
+        else:
+            t["y"].copy_(y.float())
+
+
+def linear_wgrad_grouped(tasks):
+    for t in tasks:
+        x = t["x"].double()
+        if t.get("x_scale") is not None:
+            x = x * t["x_scale"].double().unsqueeze(1)
+        g = t["g"].double()
+        t["gw"].copy_(((g.t() @ x) * t.get("alpha", 1.0)).float())
+        if t.get("gbias") is not None:
+            t["gbias"].copy_((g.sum(0) * t.get("bias_mul", 1.0)).float())
+
+
 def image_prep(dst_nchw, dst_nhwc8, src_hwc, flip, batch, h, w):
     x = src_hwc
     if flip is not None:
@@ -299,5 +329,5 @@ def install(monkeypatch):
     for name in ("fused_bias_act", "fused_bias_act_bwd", "upfirdn2d", "conv2d_simt",
                  "conv2d_wgrad_simt", "attn_core", "adam_ema", "adam_ema_devstep", "scale_bc", "dot_bc",
                  "attn_stack_fwd", "attn_stack_bwd", "pack_weights_tc", "conv_tc", "conv_wgrad_tc", "split_bf16",
-                 "image_prep", "image_quantize"):
+                 "image_prep", "image_quantize", "linear_grouped", "linear_wgrad_grouped"):
         monkeypatch.setattr(lib, name, globals()[name])

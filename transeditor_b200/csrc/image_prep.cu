@@ -146,12 +146,12 @@ image_quantize_kernel(uint8_t* __restrict__ dst, const T* __restrict__ src, int 
 extern "C" int te_image_prep(float* dst_nchw, void* dst_nhwc8, const uint8_t* src_hwc, const uint8_t* flip,
                              int batch, int h, int w, int nhwc_dtype, void* stream) {
   using namespace te;
-  TE_CHECK_ARG(src_hwc != nullptr, "te_image_prep: src is NULL");
-  TE_CHECK_ARG(dst_nchw != nullptr || dst_nhwc8 != nullptr, "te_image_prep: no destination");
   TE_CHECK_ARG(batch >= 0 && h >= 0 && w >= 0, "te_image_prep: negative size");
   TE_CHECK_ARG(nhwc_dtype == TE_F32 || nhwc_dtype == TE_BF16, "te_image_prep: nhwc dtype must be f32 or bf16");
   const int64_t n = int64_t(batch) * h * w;
-  if (n == 0) return TE_OK;
+  if (n == 0) return TE_OK;   // empty batch: nothing to do (the pointers of empty tensors are NULL)
+  TE_CHECK_ARG(src_hwc != nullptr, "te_image_prep: src is NULL");
+  TE_CHECK_ARG(dst_nchw != nullptr || dst_nhwc8 != nullptr, "te_image_prep: no destination");
   const int64_t items = (w & 3) == 0 ? n / 4 : n;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int grid = grid_for(items, 256, 8);
@@ -169,11 +169,11 @@ extern "C" int te_image_quantize(uint8_t* dst_hwc, const void* src, int batch, i
                                  int64_t stride_c, int64_t stride_y, int64_t stride_x, float low, float high,
                                  int dtype, void* stream) {
   using namespace te;
-  TE_CHECK_ARG(dst_hwc != nullptr && src != nullptr, "te_image_quantize: NULL pointer");
   TE_CHECK_ARG(batch >= 0 && h >= 0 && w >= 0, "te_image_quantize: negative size");
   TE_CHECK_ARG(dtype == TE_F32 || dtype == TE_BF16, "te_image_quantize: dtype must be f32 or bf16");
   const int64_t n = int64_t(batch) * h * w;
   if (n == 0) return TE_OK;
+  TE_CHECK_ARG(dst_hwc != nullptr && src != nullptr, "te_image_quantize: NULL pointer");
   const bool vec = (w & 3) == 0 && stride_x == 1;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int grid = grid_for(vec ? n / 4 : n, 256, 8);

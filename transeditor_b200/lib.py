@@ -59,6 +59,26 @@ class PackTask(ctypes.Structure):
                 ("split", ctypes.c_int)]
 
 
+class LinearTask(ctypes.Structure):
+    """Mirror of te_linear_task."""
+    _fields_ = [("x", ctypes.c_void_p), ("x_rs", ctypes.c_int64), ("x_cs", ctypes.c_int64),
+                ("w", ctypes.c_void_p), ("w_ld", ctypes.c_int64), ("w_trans", ctypes.c_int),
+                ("bias", ctypes.c_void_p), ("bias_mul", ctypes.c_float),
+                ("y", ctypes.c_void_p), ("y_rs", ctypes.c_int64), ("y_cs", ctypes.c_int64),
+                ("m", ctypes.c_int), ("n", ctypes.c_int), ("k", ctypes.c_int), ("alpha", ctypes.c_float),
+                ("act", ctypes.c_int), ("pixel_norm", ctypes.c_int), ("k_splits", ctypes.c_int),
+                ("rnorm_out", ctypes.c_void_p)]
+
+
+class LinearWgradTask(ctypes.Structure):
+    """Mirror of te_linear_wgrad_task."""
+    _fields_ = [("g", ctypes.c_void_p), ("g_rs", ctypes.c_int64), ("g_cs", ctypes.c_int64),
+                ("x", ctypes.c_void_p), ("x_rs", ctypes.c_int64), ("x_cs", ctypes.c_int64),
+                ("x_scale", ctypes.c_void_p), ("gw", ctypes.c_void_p), ("gbias", ctypes.c_void_p),
+                ("m", ctypes.c_int), ("n", ctypes.c_int), ("k", ctypes.c_int),
+                ("alpha", ctypes.c_float), ("bias_mul", ctypes.c_float)]
+
+
 _P, _I, _L, _F = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
 _SIGNATURES = {
     "te_version": ([], _I),
@@ -79,6 +99,8 @@ _SIGNATURES = {
     "te_gemm_tc_selftest": ([_P, _P, _P, _I, _I, _I, _P], _I),
     "te_attn_core": ([_P, _P, _P, _P, _P, _I, _I, _P], _I),
     "te_pack_weights_tc": ([ctypes.POINTER(PackTask), _I, _P], _I),
+    "te_linear_grouped": ([ctypes.POINTER(LinearTask), _I, _I, _P], _I),
+    "te_linear_wgrad_grouped": ([ctypes.POINTER(LinearWgradTask), _I, _P], _I),
     "te_image_prep": ([_P, _P, _P, _P, _I, _I, _I, _I, _P], _I),
     "te_image_quantize": ([_P, _P, _I, _I, _I, _L, _L, _L, _L, _F, _F, _I, _P], _I),
     "te_attn_stack_workspace": ([ctypes.POINTER(AttnBlock), _I, _I, ctypes.POINTER(_L), ctypes.POINTER(_L)], _I),
@@ -322,3 +344,66 @@ def image_quantize(dst_hwc, src, low, high):
     _check(load().te_image_quantize(ptr(dst_hwc), ptr(src), b, h, w, sb, sc, sy, sx, low, high, dtype_code(src),
                                     stream()), "image_quantize")
     _count()
+
+
+def _f32_2d(t, what):
+    if t.dtype != torch.float32 or t.dim() != 2:
+        raise TypeError("grouped linear: %s must be a 2-D float32 tensor, got %s %s" % (what, t.dtype, tuple(t.shape)))
+
+
+def linear_grouped(tasks, tf32=False):
+    """tasks: list of dicts {x [M,K] (any strides), w ([N,K] contiguous; or [K,N] contiguous with w_trans=True),
+    y [M,N] (any strides), bias [N] or None, bias_mul, alpha, act (0/1), pixel_norm (bool), rnorm_out [M] or None,
+    k_splits}.  One launch per 32 tasks (te_linear_grouped)."""
+    if not tasks:
+        return
+    table = (LinearTask * len(tasks))()
+    for e, t in zip(table, tasks):
+        x, w, y, bias = t["x"], t["w"], t["y"], t.get("bias")
+        require_cuda(x, w, y, bias, t.get("rnorm_out"))
+        _f32_2d(x, "x"), _f32_2d(w, "w"), _f32_2d(y, "y")
+        if not w.is_contiguous() or (bias is not None and (bias.dtype != torch.float32 or not bias.is_contiguous())):
+            raise TypeError("grouped linear: weights and biases must be contiguous float32 tensors")
+        trans = bool(t.get("w_trans", False))
+        m, k = x.shape
+        n = w.shape[1] if trans else w.shape[0]
+        if (w.shape[0] if trans else w.shape[1]) != k or tuple(y.shape) != (m, n) or (bias is not None and bias.numel() != n):
+            raise RuntimeError("grouped linear: shapes x %s, w %s (trans=%s), y %s do not agree"
+                               % (tuple(x.shape), tuple(w.shape), trans, tuple(y.shape)))
+        e.x, e.x_rs, e.x_cs = x.data_ptr(), x.stride(0), x.stride(1)
+        e.w, e.w_ld, e.w_trans = w.data_ptr(), w.shape[1], int(trans)
+        e.bias = None if bias is None else bias.data_ptr()
+        e.bias_mul = float(t.get("bias_mul", 1.0))
+        e.y, e.y_rs, e.y_cs = y.data_ptr(), y.stride(0), y.stride(1)
+        e.m, e.n, e.k, e.alpha = m, n, k, float(t.get("alpha", 1.0))
+        e.act, e.pixel_norm, e.k_splits = int(t.get("act", 0)), int(bool(t.get("pixel_norm", False))), int(t.get("k_splits", 1))
+        rn = t.get("rnorm_out")
+        e.rnorm_out = None if rn is None else rn.data_ptr()
+    _check(load().te_linear_grouped(table, len(tasks), 1 if tf32 else 0, stream()), "linear_grouped")
+    _count((len(tasks) + 31) // 32)
+
+
+def linear_wgrad_grouped(tasks):
+    """tasks: list of dicts {g [M,N], x [M,K] (any strides), gw [N,K] contiguous, gbias [N] or None, x_scale [M] or
+    None, alpha, bias_mul}.  One launch per 32 tasks (te_linear_wgrad_grouped)."""
+    if not tasks:
+        return
+    table = (LinearWgradTask * len(tasks))()
+    for e, t in zip(table, tasks):
+        g, x, gw, gb, xs = t["g"], t["x"], t["gw"], t.get("gbias"), t.get("x_scale")
+        require_cuda(g, x, gw, gb, xs)
+        _f32_2d(g, "g"), _f32_2d(x, "x"), _f32_2d(gw, "gw")
+        m, n = g.shape
+        k = x.shape[1]
+        if x.shape[0] != m or tuple(gw.shape) != (n, k) or not gw.is_contiguous():
+            raise RuntimeError("grouped linear wgrad: shapes g %s, x %s, gw %s do not agree"
+                               % (tuple(g.shape), tuple(x.shape), tuple(gw.shape)))
+        e.g, e.g_rs, e.g_cs = g.data_ptr(), g.stride(0), g.stride(1)
+        e.x, e.x_rs, e.x_cs = x.data_ptr(), x.stride(0), x.stride(1)
+        e.x_scale = None if xs is None else xs.data_ptr()
+        e.gw = gw.data_ptr()
+        e.gbias = None if gb is None else gb.data_ptr()
+        e.m, e.n, e.k = m, n, k
+        e.alpha, e.bias_mul = float(t.get("alpha", 1.0)), float(t.get("bias_mul", 1.0))
+    _check(load().te_linear_wgrad_grouped(table, len(tasks), stream()), "linear_wgrad_grouped")
+    _count((len(tasks) + 31) // 32)

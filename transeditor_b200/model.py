@@ -52,6 +52,15 @@ def get_precision():
     return _PRECISION
 
 
+_SMALL_M = 64   # EqualLinear: up to this many rows go through the grouped weight-streaming kernel
+
+
+def lib_emulated():
+    """True only inside the CPU test-suite's `cpu_emulation` fixture (tests/emu.py replaces lib.require_cuda)."""
+    from . import lib
+    return getattr(lib.require_cuda, "__name__", "") == "<lambda>"
+
+
 def _tc(x):
     """True when the tensor-core engine handles activations like x."""
     return x.dtype == torch.bfloat16 or (x.dtype == torch.float32 and _PRECISION == "fp32")
@@ -233,9 +242,25 @@ class EqualLinear(nn.Module):
         self.lr_mul = lr_mul
 
     def forward(self, input):
-        # x (W*scale)^T + b*lr_mul as ONE addmm with alpha=scale: the reference's separate `weight * scale`
-        # elementwise kernel (:215,218) and its backward disappear (beta=0 ignores the placeholder input)
         x2 = input.reshape(-1, input.shape[-1])
+        if x2.shape[0] <= _SMALL_M and x2.dtype == torch.float32 and (x2.is_cuda or lib_emulated()):
+            # small batch of rows: weight-streaming bound -> te_linear_grouped (scale, bias * lr_mul and the fused
+            # leaky ReLU inside the kernel; data / weight / bias gradients are two more launches)
+            k = x2.shape[1]
+            if k >= 2048:  # long reduction (D's 8192 -> 512): cut over several CTAs, bias / activation afterwards
+                (out,) = op.grouped_linear([(x2, self.weight, None, self.scale, 1.0, False, k // 1024)],
+                                           tf32=_PRECISION == "bf16")
+                if self.activation:
+                    out = fused_leaky_relu(out, self.bias * self.lr_mul)
+                elif self.bias is not None:
+                    out = out + self.bias * self.lr_mul
+            else:
+                (out,) = op.grouped_linear([(x2, self.weight, self.bias, self.scale, self.lr_mul,
+                                             bool(self.activation))], tf32=_PRECISION == "bf16")
+            return out.reshape(*input.shape[:-1], out.shape[-1])
+        # many rows (adjust_style: B*512 rows of 16): a plain library GEMM.  x (W*scale)^T + b*lr_mul as ONE addmm with
+        # alpha=scale: the reference's separate `weight * scale` elementwise kernel (:215,218) and its backward
+        # disappear (beta=0 ignores the placeholder input)
         if self.activation or self.bias is None:
             out = torch.addmm(x2.new_empty(1), x2, self.weight.t(), beta=0, alpha=self.scale)
         else:  # beta folds the bias's lr_mul too: no `bias * lr_mul` kernel, forward or backward
@@ -316,10 +341,12 @@ class ModulatedConv2d(nn.Module):
         return (f"{self.__class__.__name__}({self.in_channel}, {self.out_channel}, {self.kernel_size}, "
                 f"upsample={self.upsample}, downsample={self.downsample})")
 
-    def scales(self, style, fold_scale=False):
+    def scales(self, style, fold_scale=False, s=None):
         """(s [B,Cin], d [B,Cout] or None, Wn [Cout,Cin,k,k]); with fold_scale the raw master weight is returned
-        instead of Wn = W * scale (the tensor-core route applies `scale` while repacking the weight)."""
-        s = self.modulation(style)
+        instead of Wn = W * scale (the tensor-core route applies `scale` while repacking the weight).  `s`: the
+        modulation output when the caller has computed it already (all layers in one grouped launch)."""
+        if s is None:
+            s = self.modulation(style)
         w = self.weight[0]
         d = None
         if self.demodulate:
@@ -362,13 +389,13 @@ class ModulatedConv2d(nn.Module):
         return _epilogue(out, bias, noise, noise_weight, activate)
 
 
-def _modconv_tc_operands(self, style, hw):
+def _modconv_tc_operands(self, style, hw, s=None):
     """Everything of the bf16 route that depends only on (style, weights): s, d and — at high resolution —
     the per-sample weights.  No activation is touched, so Generator.forward computes these for ALL layers on a
     side stream while the main stream runs the convolutions (`prepare`)."""
     if self.downsample:
         raise RuntimeError("tensor-core ModulatedConv2d: downsample is not used by the generator")
-    s, d, wn = self.scales(style, fold_scale=True)
+    s, d, wn = self.scales(style, fold_scale=True, s=s)
     k = self.kernel_size
     cout = self.out_channel
     if cout % 8:  # ToRGB: pad the 3 output channels to 8 (zero rows), sliced off after the conv
@@ -387,10 +414,10 @@ def _modconv_tc_operands(self, style, hw):
     return ops
 
 
-def _modconv_prepare(self, style, hw, side, main):
+def _modconv_prepare(self, style, hw, side, main, s=None):
     """Compute tc_operands on the stream `side`; forward() picks them up after waiting on the event."""
     with torch.cuda.stream(side):
-        ops = self.tc_operands(style, hw)
+        ops = self.tc_operands(style, hw, s=s)
         ev = torch.cuda.Event()
         ev.record(side)
     # temporaries allocated on the side stream but consumed (and later freed) under the main stream
@@ -723,26 +750,23 @@ class Generator(nn.Module):
         main = torch.cuda.current_stream(latent.device)
         side = _side_stream(latent.device)
         side.wait_stream(main)
-        for m, idx, r in layers:
-            m.prepare(latent[:, idx], r * r, side, main)
+        with torch.cuda.stream(side):
+            # every layer's style modulation (EqualLinear(style_dim, Cin, bias_init=1), :283) in ONE grouped launch
+            mods = op.grouped_linear([(latent[:, idx], m.modulation.weight, m.modulation.bias, m.modulation.scale,
+                                       m.modulation.lr_mul, False) for m, idx, _ in layers],
+                                     tf32=_PRECISION == "bf16")
+        for (m, idx, r), s in zip(layers, mods):
+            m.prepare(latent[:, idx], r * r, side, main, s=s)
 
     def _map_columns(self, code, network, count):
-        """:626-646 as ONE batched GEMM: column i of `code` [B,D,C] goes through its own
-        EqualLinear(+fused lrelu).  Returns [B,D,C]."""
-        code = network[0](code)
+        """:626-646 in ONE launch (op.mapping_columns -> te_linear_grouped): PixelNorm, the `count` per-column
+        EqualLinears, bias and fused leaky ReLU; no stacked weight copy, no library GEMM.  Returns [B,D,C]."""
         layers = [network[i + 1] for i in range(count)]
-        w = torch.stack([l.weight for l in layers])                            # [C, out, in]
-        bias = torch.stack([l.bias for l in layers]) * layers[0].lr_mul        # [C, out]
-        cols = code.permute(2, 0, 1)[:count]                                   # [C, B, in]
-        # scale folded into the batched GEMM (alpha) instead of a pass over the 4.2 M stacked weights
-        y = torch.baddbmm(cols.new_empty(1), cols, w.transpose(1, 2), beta=0, alpha=layers[0].scale)
-        y = fused_leaky_relu(y.permute(1, 0, 2).reshape(code.shape[0], -1), bias.reshape(-1))
-        y = y.reshape(code.shape[0], count, -1).permute(0, 2, 1)               # [B, out, C]
-        if count == code.shape[2]:
-            return y
-        out = torch.zeros_like(code)  # num_region > 1: untouched columns stay zero (:630)
-        out[:, :, :count] = y
-        return out
+        fused_norm = network[0].pixel_norm_op_dim in (1, -2) and code.shape[1] <= 512
+        if not fused_norm:
+            code = network[0](code)
+        return op.mapping_columns(code.float(), [l.weight for l in layers], [l.bias for l in layers], layers[0].scale,
+                                  layers[0].lr_mul, tf32=_PRECISION == "bf16", pixel_norm=fused_norm)
 
     def forward(self, style, op_param, return_latents=False, input_is_latent=False, noise=None,
                 randomize_noise=True, return_style=False, return_p_latent=False,

@@ -654,3 +654,181 @@ def conv2d_tc(x, w_packed, ksize, out_scale=None, bias=None, act=False):
     lib.conv2d_tc(y, x, w_packed, f32(out_scale), f32(bias), b, h, w, cin, cout, ksize, ksize,
                   1 if act else 0, ksize * ksize * cout * cin if per_sample else 0)
     return y
+
+
+# --------------------------------------------------------------------------------------------
+# Grouped EqualLinear (te_linear_grouped / te_linear_wgrad_grouped): the small-M linears of the path, many per launch
+_LRELU_GAIN = 2 ** 0.5
+
+
+def _linear_composite(x, w, b, alpha, bias_mul, act, pixel_norm):
+    """Differentiable restatement of one task with torch ops (model_spatial_query.py:75-81, 194-221): used when a
+    gradient of the gradient is asked for (create_graph=True)."""
+    if pixel_norm:
+        x = x * torch.rsqrt(torch.mean(x * x, dim=1, keepdim=True) + 1e-8)
+    y = (x @ w.t()) * alpha
+    if b is not None:
+        y = y + b * bias_mul
+    if act:
+        y = torch.nn.functional.leaky_relu(y, 0.2) * _LRELU_GAIN
+    return y
+
+
+class GroupedLinear(Function):
+    """ys[i] = act_i(alpha_i * x_i @ w_i^T + b_i * bias_mul_i) for a LIST of independent EqualLinear layers in one
+    launch; the backward pass is one grouped data-gradient launch plus one grouped weight/bias-gradient launch.
+    meta: tuple of (alpha, bias_mul, act, k_splits) per task; tensors: x_0, w_0, b_0, x_1, w_1, b_1, ... (b_i may be
+    None).  k_splits > 1 cuts a long reduction (D's 8192-wide final linear) over several CTAs; no activation then."""
+
+    @staticmethod
+    def forward(ctx, meta, tf32, *tensors):
+        n = len(meta)
+        xs, ws, bs = tensors[0::3], tensors[1::3], tensors[2::3]
+        lib.require_cuda(*[t for t in tensors if t is not None])
+        total = sum(x.shape[0] * w.shape[0] for x, w in zip(xs, ws))
+        split = any(ks > 1 for _, _, _, ks in meta)   # split-K tasks accumulate into zeros
+        flat = (torch.zeros if split else torch.empty)(total, dtype=torch.float32, device=xs[0].device)
+        ys, tasks, off = [], [], 0
+        for (alpha, bias_mul, act, ks), x, w, b in zip(meta, xs, ws, bs):
+            m, nn_ = x.shape[0], w.shape[0]
+            y = flat[off:off + m * nn_].view(m, nn_)
+            off += m * nn_
+            ys.append(y)
+            tasks.append(dict(x=x, w=w.contiguous(), y=y, bias=b, bias_mul=bias_mul, alpha=alpha, act=int(act),
+                              k_splits=ks))
+        lib.linear_grouped(tasks, tf32)
+        ctx.meta, ctx.tf32, ctx.n = meta, tf32, n
+        ctx.save_for_backward(*[t if t is not None else flat.new_empty(0) for t in tensors], *ys)
+        ctx.has_bias = [b is not None for b in bs]
+        return tuple(ys)
+
+    @staticmethod
+    def backward(ctx, *gys):
+        n, meta = ctx.n, ctx.meta
+        saved = ctx.saved_tensors
+        tensors, ys = saved[:3 * n], saved[3 * n:]
+        xs, ws = tensors[0::3], tensors[1::3]
+        bs = [b if hb else None for b, hb in zip(tensors[2::3], ctx.has_bias)]
+        grads = [None] * (3 * n)
+        if torch.is_grad_enabled():  # create_graph=True: stay differentiable (see AttnStack.backward)
+            with torch.enable_grad():
+                for i, ((alpha, bias_mul, act, _), x, w, b, gy) in enumerate(zip(meta, xs, ws, bs, gys)):
+                    if gy is None:
+                        continue
+                    alias = [t.view_as(t) if t is not None else None for t in (x, w, b)]
+                    live = [t for t in alias if t is not None and t.requires_grad]
+                    if not live:
+                        continue
+                    y = _linear_composite(alias[0], alias[1], alias[2], alpha, bias_mul, act, False)
+                    got = dict(zip(map(id, live), torch.autograd.grad(y, live, gy, create_graph=True, allow_unused=True)))
+                    for j, t in enumerate(alias):
+                        grads[3 * i + j] = None if t is None else got.get(id(t))
+            return (None, None, *grads)
+        dtasks, wtasks = [], []
+        for i, ((alpha, bias_mul, act, _), x, w, b, y, gy) in enumerate(zip(meta, xs, ws, bs, ys, gys)):
+            if gy is None:
+                continue
+            g = gy
+            if act:  # d leaky_relu(u) * gain: the sign of the output is the sign of u (gain > 0)
+                g = gy * torch.where(y > 0, _LRELU_GAIN, 0.2 * _LRELU_GAIN)
+            if ctx.needs_input_grad[2 + 3 * i]:
+                gx = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+                dtasks.append(dict(x=g, w=w.contiguous(), w_trans=True, y=gx, alpha=alpha))
+                grads[3 * i] = gx
+            need_w = ctx.needs_input_grad[3 + 3 * i]
+            need_b = b is not None and ctx.needs_input_grad[4 + 3 * i]
+            if need_w or need_b:
+                gw = torch.empty(w.shape, dtype=torch.float32, device=x.device)
+                gb = torch.empty(b.shape, dtype=torch.float32, device=x.device) if need_b else None
+                wtasks.append(dict(g=g, x=x, gw=gw, gbias=gb, alpha=alpha, bias_mul=bias_mul))
+                grads[3 * i + 1] = gw if need_w else None
+                grads[3 * i + 2] = gb
+        lib.linear_grouped(dtasks, ctx.tf32)
+        lib.linear_wgrad_grouped(wtasks)
+        return (None, None, *grads)
+
+
+def grouped_linear(layers, tf32=False):
+    """layers: list of (x [M,K], weight [N,K], bias [N] or None, alpha, bias_mul, act[, k_splits]) -> list of y [M,N]."""
+    meta = tuple((float(l[3]), float(l[4]), bool(l[5]), int(l[6]) if len(l) > 6 else 1) for l in layers)
+    flat = []
+    for l in layers:
+        flat += [l[0], l[1], l[2]]
+    return list(GroupedLinear.apply(meta, tf32, *flat))
+
+
+class MappingColumns(Function):
+    """The pre-mapping of one code (model_spatial_query.py:626-646): PixelNorm over dim 1 of code [B, D, C], then column
+    i through its own EqualLinear(D, D, lr_mul, 'fused_lrelu') — `count` layers, ONE launch, the normalisation, bias
+    and activation inside it.  Returns [B, D, C] (columns >= count stay zero, :630).  weights / biases: the layers'
+    parameters in column order."""
+
+    @staticmethod
+    def forward(ctx, code, alpha, lr_mul, tf32, count, pixel_norm, *params):
+        lib.require_cuda(code, *params)
+        ws, bs = params[:count], params[count:]
+        b, d, c = code.shape
+        cols = code.permute(2, 0, 1).contiguous()                       # [C, B, D]: unit-stride rows for the kernel
+        out = torch.empty_like(code) if count == c else torch.zeros_like(code)
+        rn = torch.empty((count, b) if pixel_norm else (0, b), dtype=torch.float32, device=code.device)
+        tasks = [dict(x=cols[i], w=ws[i].contiguous(), bias=bs[i], bias_mul=lr_mul, y=out[:, :, i], alpha=alpha, act=1,
+                      pixel_norm=pixel_norm, rnorm_out=rn[i] if pixel_norm else None) for i in range(count)]
+        lib.linear_grouped(tasks, tf32)
+        ctx.alpha, ctx.lr_mul, ctx.tf32, ctx.count, ctx.pixel_norm = alpha, lr_mul, tf32, count, pixel_norm
+        ctx.save_for_backward(code, cols, rn, out, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        code, cols, rn, out, *params = ctx.saved_tensors
+        count, alpha, lr_mul = ctx.count, ctx.alpha, ctx.lr_mul
+        ws, bs = params[:count], params[count:]
+        if torch.is_grad_enabled():  # create_graph=True
+            with torch.enable_grad():
+                acode = code.view_as(code)
+                aparams = [t.view_as(t) for t in params]
+                live = [t for t in (acode, *aparams) if t.requires_grad]
+                y = mapping_columns_reference(acode, aparams[:count], aparams[count:], alpha, lr_mul, ctx.pixel_norm)
+                got = dict(zip(map(id, live), torch.autograd.grad(y, live, gout, create_graph=True, allow_unused=True)))
+            return (got.get(id(acode)), None, None, None, None, None, *[got.get(id(t)) for t in aparams])
+        b, d, c = code.shape
+        g = gout * torch.where(out > 0, _LRELU_GAIN, 0.2 * _LRELU_GAIN)      # [B, D, C]
+        gcols = g.permute(2, 0, 1).contiguous()                                # [C, B, D]
+        gw = torch.empty((count, d, d), dtype=torch.float32, device=code.device)
+        gb = torch.empty((count, d), dtype=torch.float32, device=code.device)
+        pn = ctx.pixel_norm
+        lib.linear_wgrad_grouped([dict(g=gcols[i], x=cols[i], x_scale=rn[i] if pn else None, gw=gw[i], gbias=gb[i],
+                                       alpha=alpha, bias_mul=lr_mul) for i in range(count)])
+        gcode = None
+        if ctx.needs_input_grad[0]:
+            gxn = torch.empty((count, b, d), dtype=torch.float32, device=code.device)
+            lib.linear_grouped([dict(x=gcols[i], w=ws[i].contiguous(), w_trans=True, y=gxn[i], alpha=alpha)
+                                for i in range(count)], ctx.tf32)
+            # PixelNorm backward: xn = x * r, r = (mean x^2 + eps)^-1/2  =>  gx = r * gxn - x * r^3 * mean(gxn * x)
+            gx = gxn
+            if pn:
+                x, r = cols[:count], rn.unsqueeze(-1)
+                gx = r * gxn - x * (r * r * r) * (gxn * x).mean(-1, keepdim=True)
+            gcode = torch.zeros_like(code) if count != c else torch.empty_like(code)
+            gcode[:, :, :count] = gx.permute(1, 2, 0)
+        return (gcode, None, None, None, None, None, *gw.unbind(0), *gb.unbind(0))
+
+
+def mapping_columns_reference(code, weights, biases, alpha, lr_mul, pixel_norm=True):
+    """Differentiable torch restatement of MappingColumns (the literal loop of model_spatial_query.py:626-632)."""
+    x = code * torch.rsqrt(torch.mean(code ** 2, dim=1, keepdim=True) + 1e-8) if pixel_norm else code
+    cols = []
+    for i, (w, b) in enumerate(zip(weights, biases)):
+        cols.append(_linear_composite(x[:, :, i], w, b, alpha, lr_mul, True, False))
+    y = torch.stack(cols, dim=2)
+    if len(cols) == code.shape[2]:
+        return y
+    out = torch.cat([y, torch.zeros_like(code[:, :, len(cols):])], dim=2)
+    return out
+
+
+def mapping_columns(code, weights, biases, alpha, lr_mul, tf32=False, pixel_norm=True):
+    """pixel_norm=True: PixelNorm over dim 1 (the per-column feature vector) is computed inside the kernel; pass False
+    when the caller has normalised over another dimension already."""
+    return MappingColumns.apply(code, float(alpha), float(lr_mul), tf32, len(weights), bool(pixel_norm), *weights,
+                                *biases)
