@@ -364,6 +364,23 @@ typedef struct te_linear_wgrad_task {
 } te_linear_wgrad_task;
 int te_linear_wgrad_grouped(const te_linear_wgrad_task* tasks, int n_tasks, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * The discriminator's from-RGB layer: ConvLayer(3, C, 1) = EqualConv2d(3, C, 1) + FusedLeakyReLU(C)
+ * (model_spatial_query.py:806-808 with :731-777, :156-185) as one streaming kernel each way.
+ *   fwd:  y[b, p, o] = leaky_relu(SUM_c x[b, c, p] * w[o, c] * wscale + bias[o], slope) * gain
+ *         x f32 NCHW [B, 3, H, W] (the loader's / generator's image), y channels-last [B, H, W, C] of `dtype`
+ *         (TE_F32 / TE_BF16), w f32 [C, 3] (the [C, 3, 1, 1] master weight), bias f32 [C] or NULL.
+ *   bwd:  with gp = g * (out > 0 ? gain : gain * slope)  (the mask comes from the saved OUTPUT, utils/op/fused_act.py:27-29)
+ *         gw[o, c] += wscale * SUM_{b,p} gp * x      gbias[o] += SUM_{b,p} gp      (ACCUMULATE: zero them first)
+ *         gx[b, c, p] = wscale * SUM_o gp * w[o, c]  (written; NULL = not needed)
+ * C must be 8, 16, ..., 256 (a power of two).
+ */
+int te_from_rgb_fwd(void* y, const float* x, const float* w, const float* bias, int batch, int h, int wd, int cout,
+                    float wscale, float slope, float gain, int dtype, void* stream);
+int te_from_rgb_bwd(float* gw, float* gbias, float* gx, const void* g, const void* out, const float* x,
+                    const float* w, int batch, int h, int wd, int cout, float wscale, float slope, float gain,
+                    int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -307,6 +307,22 @@ def linear_wgrad_grouped(tasks):
             t["gbias"].copy_((g.sum(0) * t.get("bias_mul", 1.0)).float())
 
 
+def from_rgb_fwd(y, x, w, bias, wscale, slope, gain):
+    u = F.conv2d(x.double(), (w.double() * wscale).view(w.shape[0], 3, 1, 1))
+    if bias is not None:
+        u = u + bias.double().view(1, -1, 1, 1)
+    y.copy_((F.leaky_relu(u, slope) * gain).to(y.dtype))
+
+
+def from_rgb_bwd(gw, gbias, gx, g, out, x, w, wscale, slope, gain):
+    gp = g.double() * torch.where(out.double() > 0, gain, gain * slope)
+    gw.add_((torch.einsum("bohw,bchw->oc", gp, x.double()) * wscale).float())
+    if gbias is not None:
+        gbias.add_(gp.sum((0, 2, 3)).float())
+    if gx is not None:
+        gx.copy_((torch.einsum("bohw,oc->bchw", gp, w.double()) * wscale).float())
+
+
 def image_prep(dst_nchw, dst_nhwc8, src_hwc, flip, batch, h, w):
     x = src_hwc
     if flip is not None:
@@ -329,5 +345,6 @@ def install(monkeypatch):
     for name in ("fused_bias_act", "fused_bias_act_bwd", "upfirdn2d", "conv2d_simt",
                  "conv2d_wgrad_simt", "attn_core", "adam_ema", "adam_ema_devstep", "scale_bc", "dot_bc",
                  "attn_stack_fwd", "attn_stack_bwd", "pack_weights_tc", "conv_tc", "conv_wgrad_tc", "split_bf16",
-                 "image_prep", "image_quantize", "linear_grouped", "linear_wgrad_grouped"):
+                 "image_prep", "image_quantize", "linear_grouped", "linear_wgrad_grouped", "from_rgb_fwd",
+                 "from_rgb_bwd"):
         monkeypatch.setattr(lib, name, globals()[name])

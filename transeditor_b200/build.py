@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libte_b200.so")
 SOURCES = ["misc.cu", "fused_bias_act.cu", "upfirdn2d.cu", "conv_simt.cu", "conv_tc.cu", "wgrad_tc.cu", "elementwise.cu", "attn_stack.cu",
-           "image_prep.cu", "linear.cu"]
+           "image_prep.cu", "linear.cu", "from_rgb.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

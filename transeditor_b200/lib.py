@@ -101,6 +101,8 @@ _SIGNATURES = {
     "te_pack_weights_tc": ([ctypes.POINTER(PackTask), _I, _P], _I),
     "te_linear_grouped": ([ctypes.POINTER(LinearTask), _I, _I, _P], _I),
     "te_linear_wgrad_grouped": ([ctypes.POINTER(LinearWgradTask), _I, _P], _I),
+    "te_from_rgb_fwd": ([_P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _I, _P], _I),
+    "te_from_rgb_bwd": ([_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _I, _P], _I),
     "te_image_prep": ([_P, _P, _P, _P, _I, _I, _I, _I, _P], _I),
     "te_image_quantize": ([_P, _P, _I, _I, _I, _L, _L, _L, _L, _F, _F, _I, _P], _I),
     "te_attn_stack_workspace": ([ctypes.POINTER(AttnBlock), _I, _I, ctypes.POINTER(_L), ctypes.POINTER(_L)], _I),
@@ -407,3 +409,17 @@ def linear_wgrad_grouped(tasks):
         e.alpha, e.bias_mul = float(t.get("alpha", 1.0)), float(t.get("bias_mul", 1.0))
     _check(load().te_linear_wgrad_grouped(table, len(tasks), stream()), "linear_wgrad_grouped")
     _count((len(tasks) + 31) // 32)
+
+
+def from_rgb_fwd(y, x, w, bias, wscale, slope, gain):
+    b, _, h, wd = x.shape
+    _check(load().te_from_rgb_fwd(ptr(y), ptr(x), ptr(w), ptr(bias), b, h, wd, w.shape[0], wscale, slope, gain,
+                                  dtype_code(y), stream()), "from_rgb_fwd")
+    _count()
+
+
+def from_rgb_bwd(gw, gbias, gx, g, out, x, w, wscale, slope, gain):
+    b, _, h, wd = x.shape
+    _check(load().te_from_rgb_bwd(ptr(gw), ptr(gbias), ptr(gx), ptr(g), ptr(out), ptr(x), ptr(w), b, h, wd, w.shape[0],
+                                  wscale, slope, gain, dtype_code(g), stream()), "from_rgb_bwd")
+    _count()

@@ -1002,7 +1002,18 @@ class Discriminator(nn.Module):
         # RGB is zero-padded to 64 channels: a TMA box whose rows are mostly out of bounds (8 of 64 channels)
         # takes the unit's slow path (measured 4 us per tile); a dense 128-byte row costs 134 MB of extra
         # input but runs at full speed
-        out = self.convs(_to_cl(input, pad_to=64) if bf16 else input)
+        first = self.convs[0]
+        if (bf16 and input.dtype == torch.float32 and input.shape[1] == 3 and len(first) == 2
+                and isinstance(first[0], EqualConv2d) and isinstance(first[1], FusedLeakyReLU)
+                and first[0].weight.shape[2] == 1 and first[0].bias is None and first[1].bias is not None
+                and first[1].negative_slope == 0.2 and first[0].weight.shape[0] in (8, 16, 32, 64, 128, 256)):
+            # from-RGB (ConvLayer(3, C, 1), :806-808): K = 3 is a stream, not a GEMM — one dedicated kernel each way
+            # straight from the f32 NCHW image (op.FromRGB) instead of a padded tensor-core launch
+            out = op.from_rgb(input, first[0].weight, first[1].bias, first[0].scale, first[1].scale, _act_dtype())
+            for layer in list(self.convs)[1:]:
+                out = layer(out)
+        else:
+            out = self.convs(_to_cl(input, pad_to=64) if bf16 else input)
         batch, channel, height, width = out.shape
         if batch % sub_batches:
             raise ValueError("batch %d is not divisible into %d sub-batches" % (batch, sub_batches))

@@ -832,3 +832,57 @@ def mapping_columns(code, weights, biases, alpha, lr_mul, tf32=False, pixel_norm
     when the caller has normalised over another dimension already."""
     return MappingColumns.apply(code, float(alpha), float(lr_mul), tf32, len(weights), bool(pixel_norm), *weights,
                                 *biases)
+
+
+# --------------------------------------------------------------------------------------------
+# The discriminator's from-RGB layer (te_from_rgb_fwd / te_from_rgb_bwd)
+def from_rgb_reference(img, weight, bias, wscale, gain, slope=0.2):
+    """Differentiable torch restatement: EqualConv2d(3, C, 1) + FusedLeakyReLU (model_spatial_query.py:731-777)."""
+    y = torch.nn.functional.conv2d(img, weight * wscale) + bias.view(1, -1, 1, 1)
+    return torch.nn.functional.leaky_relu(y, slope) * gain
+
+
+class FromRGB(Function):
+    """out = leaky_relu(conv1x1(img, W * wscale) + bias, 0.2) * gain, img f32 NCHW [B,3,H,W] -> channels-last
+    [B,C,H,W] of `dtype`; one streaming kernel forward, one backward (weight, bias and image gradients in a single pass
+    over the activation and its gradient, LeakyReLU mask applied on the fly).  create_graph=True (R1) re-expresses the
+    backward with differentiable ops."""
+
+    @staticmethod
+    def forward(ctx, img, weight, bias, wscale, gain, dtype):
+        lib.require_cuda(img, weight, bias)
+        if img.dtype != torch.float32 or img.dim() != 4 or img.shape[1] != 3:
+            raise TypeError("from_rgb: expected a float32 [B, 3, H, W] image, got %s %s" % (img.dtype, tuple(img.shape)))
+        img = img.contiguous()
+        b, _, h, w = img.shape
+        c = weight.shape[0]
+        out = torch.empty((b, c, h, w), dtype=dtype, device=img.device, memory_format=torch.channels_last)
+        w2 = weight.detach().reshape(c, 3).contiguous()
+        lib.from_rgb_fwd(out, img, w2, bias.detach().float().contiguous(), wscale, 0.2, gain)
+        ctx.save_for_backward(img, weight, bias, out)
+        ctx.wscale, ctx.gain = wscale, gain
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        img, weight, bias, out = ctx.saved_tensors
+        wscale, gain = ctx.wscale, ctx.gain
+        if torch.is_grad_enabled():  # create_graph=True: stay differentiable
+            with torch.enable_grad():
+                alias = [t.view_as(t) for t in (img, weight, bias)]
+                live = [t for t in alias if t.requires_grad]
+                y = from_rgb_reference(alias[0], alias[1], alias[2], wscale, gain)
+                got = dict(zip(map(id, live), torch.autograd.grad(y, live, g_out.to(y.dtype), create_graph=True,
+                                                                  allow_unused=True)))
+            return (*[got.get(id(t)) for t in alias], None, None, None)
+        c = weight.shape[0]
+        g = g_out.to(out.dtype).contiguous(memory_format=torch.channels_last)
+        acc = torch.zeros(c * 4, dtype=torch.float32, device=img.device)   # [C,3] weight gradient + [C] bias gradient
+        gw, gb = acc[:c * 3].view(c, 3), acc[c * 3:]
+        gx = torch.empty_like(img) if ctx.needs_input_grad[0] else None
+        lib.from_rgb_bwd(gw, gb, gx, g, out, img, weight.detach().reshape(c, 3).contiguous(), wscale, 0.2, gain)
+        return gx, gw.view(weight.shape), gb.to(bias.dtype), None, None, None
+
+
+def from_rgb(img, weight, bias, wscale, gain=2 ** 0.5, dtype=torch.bfloat16):
+    return FromRGB.apply(img, weight, bias, float(wscale), float(gain), dtype)
