@@ -134,6 +134,13 @@ class KernelMeter:
             return 0.0, 3.0 * args[2].numel() * es(args[2])
         if name == "upfirdn2d":
             return 0.0, float((args[0].numel() + args[1].numel()) * es(args[1]))
+        if name == "from_rgb_fwd":
+            return 0.0, float(args[0].numel() * es(args[0]) + args[1].numel() * 4)
+        if name == "from_rgb_bwd":
+            return 0.0, float(2 * args[3].numel() * es(args[3]) + args[5].numel() * 4 * (2 if args[2] is not None else 1))
+        if name in ("linear_grouped", "linear_wgrad_grouped"):
+            key = "w" if name == "linear_grouped" else "gw"
+            return 0.0, float(sum(t[key].numel() * 4 for t in args[0]))
         if name == "adam_ema":
             return 0.0, 7.0 * args[0].numel() * 4
         if name in ("attn_stack_fwd", "attn_stack_bwd"):
@@ -148,7 +155,8 @@ class KernelMeter:
         from transeditor_b200 import lib
         for name in ("fused_bias_act", "fused_bias_act_bwd", "upfirdn2d", "conv2d_simt",
                      "conv2d_wgrad_simt", "adam_ema", "attn_core", "conv2d_tc", "conv_tc",
-                     "conv_wgrad_tc", "scale_bc", "dot_bc", "attn_stack_fwd", "attn_stack_bwd", "split_bf16"):
+                     "conv_wgrad_tc", "scale_bc", "dot_bc", "attn_stack_fwd", "attn_stack_bwd", "split_bf16",
+                     "from_rgb_fwd", "from_rgb_bwd", "linear_grouped", "linear_wgrad_grouped", "image_prep"):
             fn = getattr(lib, name)
             self._saved[name] = fn
 
@@ -170,6 +178,11 @@ class KernelMeter:
                 elif _name in ("fused_bias_act", "fused_bias_act_bwd"):
                     t = args[1] if _name == "fused_bias_act" else args[2]
                     tag = "%s %s %s" % (_name, tuple(t.shape), str(t.dtype)[6:])
+                elif _name in ("from_rgb_fwd", "from_rgb_bwd"):
+                    t = args[0] if _name == "from_rgb_fwd" else args[3]
+                    tag = "%s %s %s" % (_name, tuple(t.shape), str(t.dtype)[6:])
+                elif _name in ("linear_grouped", "linear_wgrad_grouped"):
+                    tag = "%s tasks%d" % (_name, len(args[0]))
                 elif _name == "upfirdn2d":
                     tag = "%s %s->%s up%d down%d %s" % (_name, tuple(args[1].shape), tuple(args[0].shape), args[7], args[9],
                                                       str(args[1].dtype)[6:])

@@ -47,8 +47,7 @@ template <> struct FrVec<float> {
 template <typename T>
 __global__ void __launch_bounds__(256)
 from_rgb_fwd_kernel(T* __restrict__ y, const float* __restrict__ x, const float* __restrict__ w,
-                    const float* __restrict__ bias, int64_t total_pix, int plane, int cout, float wscale, float slope,
-                    float gain) {
+                    const float* __restrict__ bias, int plane, int cout, float wscale, float slope, float gain) {
   const int ovec = cout >> 3, rows = blockDim.x / ovec;
   const int cg = threadIdx.x % ovec, prow = threadIdx.x / ovec;
   float wr[8][3], br[8];
@@ -59,10 +58,13 @@ from_rgb_fwd_kernel(T* __restrict__ y, const float* __restrict__ x, const float*
     for (int c = 0; c < 3; ++c) wr[j][c] = __ldg(w + o * 3 + c) * wscale;
     br[j] = bias ? __ldg(bias + o) : 0.f;
   }
-  for (int64_t gp = int64_t(blockIdx.x) * rows + prow; gp < total_pix; gp += int64_t(gridDim.x) * rows) {
-    const int64_t b = gp / plane;
-    const int p = int(gp - b * plane);
-    const float* xp = x + b * 3 * plane + p;
+  // grid.y = sample: no division in the pixel loop
+  const int64_t b = blockIdx.y;
+  const float* xb = x + b * 3 * plane;
+  T* yb = y + b * int64_t(plane) * cout + cg * 8;
+#pragma unroll 4
+  for (int p = blockIdx.x * rows + prow; p < plane; p += gridDim.x * rows) {
+    const float* xp = xb + p;
     const float x0 = __ldg(xp), x1 = __ldg(xp + plane), x2 = __ldg(xp + 2 * plane);
     float f[8];
 #pragma unroll
@@ -70,7 +72,7 @@ from_rgb_fwd_kernel(T* __restrict__ y, const float* __restrict__ x, const float*
       const float u = fmaf(x2, wr[j][2], fmaf(x1, wr[j][1], fmaf(x0, wr[j][0], br[j])));
       f[j] = (u > 0.f ? u : u * slope) * gain;
     }
-    FrVec<T>::store(y + gp * cout + cg * 8, f);
+    FrVec<T>::store(yb + int64_t(p) * cout, f);
   }
 }
 
@@ -78,7 +80,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 from_rgb_bwd_kernel(float* __restrict__ gw, float* __restrict__ gb, float* __restrict__ gx, const T* __restrict__ g,
                     const T* __restrict__ out, const float* __restrict__ x, const float* __restrict__ w,
-                    int64_t total_pix, int plane, int cout, float wscale, float slope, float gain) {
+                    int plane, int cout, float wscale, float slope, float gain) {
   extern __shared__ float fr_red[];   // [rows][cout * 4]
   const int ovec = cout >> 3, rows = blockDim.x / ovec;
   const int cg = threadIdx.x % ovec, prow = threadIdx.x / ovec;
@@ -90,19 +92,20 @@ from_rgb_bwd_kernel(float* __restrict__ gw, float* __restrict__ gb, float* __res
   float aw[8][3] = {}, ab[8] = {};
   const float m_pos = gain, m_neg = gain * slope;
   // all threads of a pixel group stay in the loop together (the shuffles below need the full group)
-  const int64_t iters = (total_pix + int64_t(gridDim.x) * rows - 1) / (int64_t(gridDim.x) * rows);
-  for (int64_t it = 0; it < iters; ++it) {
-    const int64_t gp = (it * gridDim.x + blockIdx.x) * rows + prow;
-    const bool live = gp < total_pix;
+  const int64_t b = blockIdx.y;   // grid.y = sample
+  const int step = gridDim.x * rows;
+  const int iters = (plane + step - 1) / step;
+  const T* gb_ = g + b * int64_t(plane) * cout + cg * 8;
+  const T* ob_ = out + b * int64_t(plane) * cout + cg * 8;
+#pragma unroll 2
+  for (int it = 0; it < iters; ++it) {
+    const int p = (it * gridDim.x + blockIdx.x) * rows + prow;
+    const bool live = p < plane;
     float gpv[8] = {}, x0 = 0.f, x1 = 0.f, x2 = 0.f;
-    int64_t b = 0;
-    int p = 0;
     if (live) {
-      b = gp / plane;
-      p = int(gp - b * plane);
       float gv[8], ov[8];
-      FrVec<T>::load(g + gp * cout + cg * 8, gv);
-      FrVec<T>::load(out + gp * cout + cg * 8, ov);
+      FrVec<T>::load(gb_ + int64_t(p) * cout, gv);
+      FrVec<T>::load(ob_ + int64_t(p) * cout, ov);
       const float* xp = x + b * 3 * plane + p;
       x0 = __ldg(xp); x1 = __ldg(xp + plane); x2 = __ldg(xp + 2 * plane);
 #pragma unroll
@@ -166,15 +169,19 @@ extern "C" int te_from_rgb_fwd(void* y, const float* x, const float* w, const fl
   const int64_t total = int64_t(batch) * h * wd;
   if (total == 0) return TE_OK;
   TE_CHECK_ARG(y && x && w, "from_rgb_fwd: null pointer");
-  const int rows = 256 / (cout / 8);
-  const int grid = grid_for((total + rows - 1) / rows, 1, 8);
+  TE_CHECK_ARG(batch <= 65535 && int64_t(h) * wd < (int64_t(1) << 31), "from_rgb_fwd: tensor too large");
+  const int rows = 256 / (cout / 8), plane = h * wd;
+  int gx_ = (kNumSMs * 8 + batch - 1) / batch;                 // ~8 waves of CTAs over the whole batch
+  const int need = (plane + rows - 1) / rows;
+  if (gx_ > need) gx_ = need;
+  const dim3 grid(gx_ > 0 ? gx_ : 1, batch);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == TE_BF16)
-    from_rgb_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<__nv_bfloat16*>(y), x, w, bias, total, h * wd,
-                                                              cout, wscale, slope, gain);
+    from_rgb_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<__nv_bfloat16*>(y), x, w, bias, plane, cout,
+                                                              wscale, slope, gain);
   else
-    from_rgb_fwd_kernel<float><<<grid, 256, 0, st>>>(static_cast<float*>(y), x, w, bias, total, h * wd, cout, wscale,
-                                                      slope, gain);
+    from_rgb_fwd_kernel<float><<<grid, 256, 0, st>>>(static_cast<float*>(y), x, w, bias, plane, cout, wscale, slope,
+                                                      gain);
   TE_CHECK_LAUNCH();
   return TE_OK;
 }
@@ -187,8 +194,12 @@ extern "C" int te_from_rgb_bwd(float* gw, float* gbias, float* gx, const void* g
   const int64_t total = int64_t(batch) * h * wd;
   if (total == 0) return TE_OK;
   TE_CHECK_ARG(gw && g && out && x && w, "from_rgb_bwd: null pointer");
-  const int rows = 256 / (cout / 8);
-  const int grid = grid_for((total + rows - 1) / rows, 1, 4);
+  TE_CHECK_ARG(batch <= 65535 && int64_t(h) * wd < (int64_t(1) << 31), "from_rgb_bwd: tensor too large");
+  const int rows = 256 / (cout / 8), plane = h * wd;
+  int gx_ = (kNumSMs * 4 + batch - 1) / batch;
+  const int need = (plane + rows - 1) / rows;
+  if (gx_ > need) gx_ = need;
+  const dim3 grid(gx_ > 0 ? gx_ : 1, batch);
   const size_t smem = size_t(rows) * cout * 4 * sizeof(float);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == TE_BF16) {
@@ -196,13 +207,13 @@ extern "C" int te_from_rgb_bwd(float* gw, float* gbias, float* gx, const void* g
     static bool cfg = false;
     if (!cfg) { TE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536)); cfg = true; }
     kern<<<grid, 256, smem, st>>>(gw, gbias, gx, static_cast<const __nv_bfloat16*>(g),
-                                  static_cast<const __nv_bfloat16*>(out), x, w, total, h * wd, cout, wscale, slope, gain);
+                                  static_cast<const __nv_bfloat16*>(out), x, w, plane, cout, wscale, slope, gain);
   } else {
     auto kern = from_rgb_bwd_kernel<float>;
     static bool cfg = false;
     if (!cfg) { TE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536)); cfg = true; }
     kern<<<grid, 256, smem, st>>>(gw, gbias, gx, static_cast<const float*>(g), static_cast<const float*>(out), x, w,
-                                  total, h * wd, cout, wscale, slope, gain);
+                                  plane, cout, wscale, slope, gain);
   }
   TE_CHECK_LAUNCH();
   return TE_OK;

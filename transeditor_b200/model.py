@@ -1004,6 +1004,7 @@ class Discriminator(nn.Module):
         # input but runs at full speed
         first = self.convs[0]
         if (bf16 and input.dtype == torch.float32 and input.shape[1] == 3 and len(first) == 2
+                and os.environ.get("TE_FROM_RGB", "1") != "0"
                 and isinstance(first[0], EqualConv2d) and isinstance(first[1], FusedLeakyReLU)
                 and first[0].weight.shape[2] == 1 and first[0].bias is None and first[1].bias is not None
                 and first[1].negative_slope == 0.2 and first[0].weight.shape[0] in (8, 16, 32, 64, 128, 256)):

@@ -867,11 +867,18 @@ class FromRGB(Function):
     def backward(ctx, g_out):
         img, weight, bias, out = ctx.saved_tensors
         wscale, gain = ctx.wscale, ctx.gain
-        if torch.is_grad_enabled():  # create_graph=True: stay differentiable
+        if torch.is_grad_enabled():
+            # create_graph=True (the R1 penalty): re-express the layer with the twice-differentiable tensor-core ops
+            # (zero-padded to a 64-channel operand, tc.TcConvBiasAct) and differentiate that
+            from . import tc
             with torch.enable_grad():
                 alias = [t.view_as(t) for t in (img, weight, bias)]
                 live = [t for t in alias if t.requires_grad]
-                y = from_rgb_reference(alias[0], alias[1], alias[2], wscale, gain)
+                b, _, h, w = img.shape
+                xcl = torch.zeros((b, h, w, 64), dtype=out.dtype, device=img.device)
+                xcl = torch.cat([alias[0].permute(0, 2, 3, 1).to(out.dtype), xcl[..., 3:]], dim=3).permute(0, 3, 1, 2)
+                wpad = torch.nn.functional.pad(alias[1], (0, 0, 0, 0, 0, 61))
+                y = tc.conv2d_bias_act(xcl, wpad, alias[2], wscale=wscale, gain=gain)
                 got = dict(zip(map(id, live), torch.autograd.grad(y, live, g_out.to(y.dtype), create_graph=True,
                                                                   allow_unused=True)))
             return (*[got.get(id(t)) for t in alias], None, None, None)
