@@ -4,6 +4,7 @@ TEST INFRASTRUCTURE / BASELINE ONLY: used by bench.py's `cpu_baseline` leg and b
 `bench.py --impl reference` (the reference has no runnable CPU path of its own — SURVEY.md
 fact 7 — so the "reference arm" of this tier is this port on the host cores).
 """
+import contextlib
 import math
 
 import torch
@@ -84,25 +85,37 @@ class RefClassCpuTrainer:
     reference on the host cores" that exists, since the reference itself is CUDA-only.  Loop body restated from
     train_spatial_query.py:166-306 (losses :64-105, optimisers :461-473, EMA :56-61)."""
 
-    def __init__(self, size=256, cm=2, n_trans=8, batch=1, lr=0.002, seed=0):
+    def __init__(self, size=256, cm=2, n_trans=8, batch=1, lr=0.002, seed=0, device="cpu"):
         from oracle import ref_shim
         self.shim = ref_shim
-        ref = ref_shim.load_reference_module()
+        self.device = torch.device(device)
+        if self.device.type == "cuda":
+            # the reference exactly as it runs on a GPU: its own CUDA extensions (oracle/ref_gpu.py), cuDNN convolutions
+            from oracle import ref_gpu
+            ref = ref_gpu.load_reference_model()
+            self._mode = contextlib.nullcontext
+        else:
+            ref = ref_shim.load_reference_module()
+            self._mode = ref_shim.cpu_mode
         torch.manual_seed(seed)
         t = 2 * int(math.log2(size)) - 2
-        with ref_shim.cpu_mode():
+        with self._mode():
             self.g = ref.Generator(size, 512, 512, t, channel_multiplier=cm, n_trans=n_trans, pixel_norm_op_dim=1,
                                    layer_noise_injection=False)
             self.g_ema = ref.Generator(size, 512, 512, t, channel_multiplier=cm, n_trans=n_trans, pixel_norm_op_dim=1,
                                        layer_noise_injection=False).eval()
             self.d = ref.Discriminator(size, channel_multiplier=cm)
+        self.g, self.g_ema, self.d = self.g.to(self.device), self.g_ema.to(self.device), self.d.to(self.device)
         self.g_ema.load_state_dict(self.g.state_dict())
         gr, dr = 4 / 5, 16 / 17
         self.g_opt = torch.optim.Adam(self.g.parameters(), lr=lr * gr, betas=(0 ** gr, 0.99 ** gr))
         self.d_opt = torch.optim.Adam(self.d.parameters(), lr=lr * dr, betas=(0 ** dr, 0.99 ** dr))
         self.size, self.batch = size, batch
-        self.mean_path = torch.zeros(())
+        self.mean_path = torch.zeros((), device=self.device)
         self.it = 0
+
+    def _z(self, n):
+        return torch.randn(n, 512, 16, device=self.device)
 
     @staticmethod
     def _requires_grad(model, flag):
@@ -111,10 +124,10 @@ class RefClassCpuTrainer:
 
     def step(self, real):
         b = self.batch
-        with self.shim.cpu_mode():
+        with self._mode():
             self._requires_grad(self.g, False)
             self._requires_grad(self.d, True)
-            fake, _, _ = self.g(torch.randn(b, 512, 16), torch.randn(b, 512, 16))
+            fake, _, _ = self.g(self._z(b), self._z(b))
             loss = O.d_logistic_loss(self.d(real), self.d(fake))
             self.d.zero_grad()
             loss.backward()
@@ -128,14 +141,14 @@ class RefClassCpuTrainer:
                 self.d_opt.step()
             self._requires_grad(self.g, True)
             self._requires_grad(self.d, False)
-            fake, _, _ = self.g(torch.randn(b, 512, 16), torch.randn(b, 512, 16))
+            fake, _, _ = self.g(self._z(b), self._z(b))
             loss = O.g_nonsaturating_loss(self.d(fake))
             self.g.zero_grad()
             loss.backward()
             self.g_opt.step()
             if self.it % 4 == 0:
                 n = max(1, b // 2)
-                img, lat, _ = self.g(torch.randn(n, 512, 16), torch.randn(n, 512, 16), return_latents=True)
+                img, lat, _ = self.g(self._z(n), self._z(n), return_latents=True)
                 noise = torch.randn_like(img) / math.sqrt(img.shape[2] * img.shape[3])
                 pl = O.g_path_lengths(img, lat, noise)
                 mean = self.mean_path + 0.01 * (pl.mean() - self.mean_path)
@@ -150,7 +163,7 @@ class RefClassCpuTrainer:
                 for k, v in self.g.named_parameters():
                     ema[k].mul_(decay).add_(v.detach(), alpha=1 - decay)
         self.it += 1
-        return float(loss.detach())
+        return loss.detach() if self.device.type == "cuda" else float(loss.detach())
 
 
 def make_trainer(**kw):

@@ -323,6 +323,12 @@ def from_rgb_bwd(gw, gbias, gx, g, out, x, w, wscale, slope, gain):
         gx.copy_((torch.einsum("bohw,oc->bchw", gp, w.double()) * wscale).float())
 
 
+def wgrad_unpack(out, ws, batch, o_dim, i_dim, taps, rows, ld, trans):
+    w = ws.reshape(batch, taps, rows, ld)
+    src = w[:, :, :i_dim, :o_dim].permute(0, 3, 2, 1) if trans else w[:, :, :o_dim, :i_dim].permute(0, 2, 3, 1)
+    out.copy_(src.reshape(out.shape))
+
+
 def image_prep(dst_nchw, dst_nhwc8, src_hwc, flip, batch, h, w):
     x = src_hwc
     if flip is not None:
@@ -346,5 +352,5 @@ def install(monkeypatch):
                  "conv2d_wgrad_simt", "attn_core", "adam_ema", "adam_ema_devstep", "scale_bc", "dot_bc",
                  "attn_stack_fwd", "attn_stack_bwd", "pack_weights_tc", "conv_tc", "conv_wgrad_tc", "split_bf16",
                  "image_prep", "image_quantize", "linear_grouped", "linear_wgrad_grouped", "from_rgb_fwd",
-                 "from_rgb_bwd"):
+                 "from_rgb_bwd", "wgrad_unpack"):
         monkeypatch.setattr(lib, name, globals()[name])

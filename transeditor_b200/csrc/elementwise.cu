@@ -309,3 +309,68 @@ extern "C" int te_pack_weights_tc(const te_pack_task* tasks, int n_tasks, void* 
   }
   return TE_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Weight-gradient unpack: the tcgen05 weight-gradient kernel accumulates tap-major [T][A][Bd] f32 (the layout whose
+// rows are UMMA output tiles); the master weight and its gradient are [O][I][T] (taps innermost).  ATen's generic
+// strided copy did this permute at ~1 TB/s, 117 times per training iteration; here a 32 x 32 (o, i) tile of all T
+// taps goes through shared memory so that both the reads (along the fastest dimension of the workspace) and the
+// writes (T * 32 contiguous floats per output row) are coalesced.
+//   trans == 0:  out[b][o][i][t] = ws[b][t][o * ld + i]      (ws rows = output channels)
+//   trans == 1:  out[b][o][i][t] = ws[b][t][i * ld + o]      (transposed convolutions keep the weight as [O, I]:
+//                                                              the workspace's logical (cout, cin) is (I, O))
+namespace te {
+
+__global__ void __launch_bounds__(256)
+wgrad_unpack_kernel(float* __restrict__ out, const float* __restrict__ ws, int o_dim, int i_dim, int taps, int rows,
+                    int ld, int trans) {
+  extern __shared__ float wu_tile[];   // [taps][32][33]
+  const int o0 = blockIdx.y * 32, i0 = blockIdx.x * 32;
+  const float* wsb = ws + int64_t(blockIdx.z) * taps * rows * ld;
+  float* outb = out + int64_t(blockIdx.z) * o_dim * i_dim * taps;
+  const int cx = threadIdx.x & 31, cy = threadIdx.x >> 5;   // 32 x 8
+  for (int t = 0; t < taps; ++t) {
+    const float* wt = wsb + int64_t(t) * rows * ld;
+#pragma unroll
+    for (int r = cy; r < 32; r += 8) {
+      float v = 0.f;
+      if (!trans) {
+        const int o = o0 + r, i = i0 + cx;
+        if (o < o_dim && i < i_dim) v = wt[int64_t(o) * ld + i];
+        wu_tile[(t * 32 + r) * 33 + cx] = v;           // tile[t][o_l][i_l]
+      } else {
+        const int i = i0 + r, o = o0 + cx;
+        if (o < o_dim && i < i_dim) v = wt[int64_t(i) * ld + o];
+        wu_tile[(t * 32 + cx) * 33 + r] = v;           // tile[t][o_l][i_l]
+      }
+    }
+  }
+  __syncthreads();
+  const int row_len = 32 * taps;                       // floats of one output row segment: (i_l, t) contiguous
+  for (int idx = threadIdx.x; idx < 32 * row_len; idx += 256) {
+    const int ol = idx / row_len, rem = idx - ol * row_len;
+    const int il = rem / taps, t = rem - il * taps;
+    const int o = o0 + ol, i = i0 + il;
+    if (o < o_dim && i < i_dim) outb[(int64_t(o) * i_dim + i) * taps + t] = wu_tile[(t * 32 + ol) * 33 + il];
+  }
+}
+
+}  // namespace te
+
+extern "C" int te_wgrad_unpack(float* out, const float* ws, int batch, int o_dim, int i_dim, int taps, int rows,
+                               int ld, int trans, void* stream) {
+  using namespace te;
+  TE_CHECK_ARG(batch >= 0 && o_dim >= 0 && i_dim >= 0, "wgrad_unpack: negative size");
+  if (int64_t(batch) * o_dim * i_dim == 0) return TE_OK;
+  TE_CHECK_ARG(out && ws, "wgrad_unpack: null pointer");
+  TE_CHECK_ARG(taps >= 1 && taps <= 9, "wgrad_unpack: 1..9 taps");
+  TE_CHECK_ARG(trans ? (rows >= i_dim && ld >= o_dim) : (rows >= o_dim && ld >= i_dim),
+               "wgrad_unpack: workspace [%d, %d] smaller than the weight [%d, %d]", rows, ld, o_dim, i_dim);
+  TE_CHECK_ARG(batch <= 65535, "wgrad_unpack: batch too large");
+  dim3 grid((i_dim + 31) / 32, (o_dim + 31) / 32, batch);
+  const size_t smem = size_t(taps) * 32 * 33 * sizeof(float);
+  wgrad_unpack_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(out, ws, o_dim, i_dim, taps, rows, ld,
+                                                                              trans);
+  TE_CHECK_LAUNCH();
+  return TE_OK;
+}

@@ -92,6 +92,7 @@ _SIGNATURES = {
     "te_adam_ema_devstep": ([_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _P, _F, _F, _P], _I),
     "te_conv_tc": ([_P, _P, _P, _P, _P, ctypes.POINTER(TcConvDesc), _P], _I),
     "te_conv_wgrad_tc": ([_P, _P, _P, ctypes.POINTER(TcConvDesc), _P], _I),
+    "te_wgrad_unpack": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _P], _I),
     "te_scale_bc": ([_P, _P, _P, _L, _L, _I, _I, _P], _I),
     "te_dot_bc": ([_P, _P, _P, _L, _L, _I, _I, _P], _I),
     "te_split_bf16": ([_P, _P, _P, _L, _L, _I, _I, _P], _I),
@@ -422,4 +423,10 @@ def from_rgb_bwd(gw, gbias, gx, g, out, x, w, wscale, slope, gain):
     b, _, h, wd = x.shape
     _check(load().te_from_rgb_bwd(ptr(gw), ptr(gbias), ptr(gx), ptr(g), ptr(out), ptr(x), ptr(w), b, h, wd, w.shape[0],
                                   wscale, slope, gain, dtype_code(g), stream()), "from_rgb_bwd")
+    _count()
+
+
+def wgrad_unpack(out, ws, batch, o_dim, i_dim, taps, rows, ld, trans):
+    _check(load().te_wgrad_unpack(ptr(out), ptr(ws), batch, o_dim, i_dim, taps, rows, ld, int(trans), stream()),
+           "wgrad_unpack")
     _count()

@@ -363,14 +363,11 @@ def wgrad_raw(g, x, mode, w_shape, scale=1.0):
     for launch in mode.launches(hin, win, hout, wout):
         lib.conv_wgrad_tc(gw, go, xo, _desc(x, cout, hout, wout, launch, k * k, per_sample=per_sample,
                                             wgrad_alpha=scale, split=nseg))
+    # tap-major accumulator -> [O, I, k, k] (taps innermost) in one coalesced pass (te_wgrad_unpack)
     o, i = w_shape[-4], w_shape[-3]
-    if per_sample:
-        if mode.transposed:
-            return gw[:, :, :i, :o].permute(0, 3, 2, 1).reshape(b, o, i, k, k).contiguous()
-        return gw[:, :, :o, :i].permute(0, 2, 3, 1).reshape(b, o, i, k, k).contiguous()
-    if mode.transposed:   # logical (cout, cin) = (I_store, O_store)
-        return gw[:, :i, :o].permute(2, 1, 0).reshape(o, i, k, k).contiguous()
-    return gw[:, :o, :i].permute(1, 2, 0).reshape(o, i, k, k).contiguous()
+    out = torch.empty((b, o, i, k, k) if per_sample else (o, i, k, k), dtype=torch.float32, device=x.device)
+    lib.wgrad_unpack(out, gw, b if per_sample else 1, o, i, k * k, cout, cin, mode.transposed)
+    return out
 
 
 class TcConv(Function):
