@@ -996,6 +996,9 @@ class Discriminator(nn.Module):
         e.g. cat([fake, real]) — so ONE pass gives exactly the logits of separate calls: every layer is
         per-sample except the minibatch standard deviation, which is taken per sub-batch."""
         bf16 = _tc_mode() and input.dtype in (torch.float32, torch.bfloat16)
+        # a LEAF image that requires grad is the R1 penalty's input (train_spatial_query.py:212-216): its gradient
+        # will be differentiated again, which the twice-differentiable tensor-core ops do without a recomputation
+        second_order = input.requires_grad and input.is_leaf and torch.is_grad_enabled()
         if bf16 and input.requires_grad and torch.is_grad_enabled():
             input = _DenseGrad.apply(input)
         # tensor-core modes: the whole conv stack incl. final_conv on tensor cores; statistics and linears in f32
@@ -1005,6 +1008,7 @@ class Discriminator(nn.Module):
         first = self.convs[0]
         if (bf16 and input.dtype == torch.float32 and input.shape[1] == 3 and len(first) == 2
                 and os.environ.get("TE_FROM_RGB", "1") != "0"
+                and not second_order
                 and isinstance(first[0], EqualConv2d) and isinstance(first[1], FusedLeakyReLU)
                 and first[0].weight.shape[2] == 1 and first[0].bias is None and first[1].bias is not None
                 and first[1].negative_slope == 0.2 and first[0].weight.shape[0] in (8, 16, 32, 64, 128, 256)):
