@@ -5,7 +5,9 @@
 // i.e. per tap a GEMM  D[cout, cin] = G^T . X  whose reduction dimension is the PIXELS.  Both operands are
 // read by TMA as [anchor rows x 64 channels] boxes straight from the channels-last tensors, which makes
 // them MN-major UMMA operands (the channel dimension is contiguous): no transpose pass exists anywhere.
-//   * CTA tile: 128 (cout) x 128 (cin), up to 3 taps resident in TMEM (3 x 128 of the 512 columns).
+//   * CTA tile: 128 (cout) x 128 (cin), up to 3 taps resident in TMEM (3 x 128 of the 512 columns).  A 128 x 256 tile
+//     with 2 taps resident exists behind TE_WG_N=256 (the N = 256 instruction carries twice the FLOPs per issue slot)
+//     but measured slower: see the host code.
 //   * stage = 64 anchors: ONE G tile (2 x [64 x 64ch]) shared by the taps + one shifted X tile per tap
 //     (2 x [64 x 64ch] each) = 16 + 3*16 = 64 KB, 3-stage ring: G is fetched once per anchor tile.
 //   * 4 x tcgen05.mma (M128, N128, K16 anchors) per tap per stage; taps are balanced over grid.y
@@ -15,20 +17,27 @@
 //   * Out-of-range anchors / padding taps / channel tails are zero-filled by the TMA unit.
 //   * Split-operand mode (te_tc_conv_desc.split = 2 or 3, see conv_tc.cu): g and x are bf16 plane stacks of f32
 //     values; every anchor tile is walked once per plane pair, all pairs accumulating into the same TMEM tiles.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace te {
 
-constexpr int WG_M = 128, WG_N = 128;
+constexpr int WG_M = 128;
 constexpr int WG_KA = 64;              // anchors per stage
-constexpr int WG_STAGES = 3;
-constexpr int WG_TAPS = 3;             // taps resident in TMEM
 constexpr int WG_THREADS = 192;
 constexpr int WG_HALF_BYTES = WG_KA * 128;          // one [64 anchors x 64 ch] box = 8 KB
-constexpr int WG_TILE_BYTES = 2 * WG_HALF_BYTES;    // [64 anchors x 128 ch] = 16 KB
-constexpr int WG_STAGE_BYTES = (1 + WG_TAPS) * WG_TILE_BYTES;   // G + 3 X tiles = 64 KB
-constexpr int WG_BAR_OFFSET = WG_STAGES * WG_STAGE_BYTES;
-constexpr int WG_SMEM_TOTAL = WG_BAR_OFFSET + 128 + 1024;
+constexpr int WG_TILE_BYTES = 2 * WG_HALF_BYTES;    // G tile [64 anchors x 128 ch] = 16 KB
+
+// WN = cin columns per CTA tile (128 or 256)
+template <int WN> struct WgCfg {
+  static constexpr int TAPS = 512 / WN > 3 ? 3 : 512 / WN;       // taps resident in TMEM: 3 (N=128), 2 (N=256)
+  static constexpr int X_BYTES = (WN / 64) * WG_HALF_BYTES;      // one tap's X tile
+  static constexpr int STAGE_BYTES = WG_TILE_BYTES + TAPS * X_BYTES;   // 64 KB / 80 KB
+  static constexpr int STAGES = WN == 128 ? 3 : 2;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int SMEM_TOTAL = BAR_OFFSET + 128 + 1024;
+};
 
 struct WgParams {
   int batch, cin, cout;
@@ -51,9 +60,12 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+template <int WG_N>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_x,
                 const __grid_constant__ WgParams p) {
+  using C = WgCfg<WG_N>;
+  constexpr int WG_STAGES = C::STAGES, WG_STAGE_BYTES = C::STAGE_BYTES, WG_BAR_OFFSET = C::BAR_OFFSET;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + WG_BAR_OFFSET);
@@ -114,16 +126,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
         const int tile_h = t % p.tiles_h; t /= p.tiles_h;
         const int b0 = t * p.nb, ay0 = tile_h * p.th, ax0 = tile_w * p.tw;
         uint8_t* dst = smem + s * WG_STAGE_BYTES;
-        mbar_expect_tx(&full_bar[s], (1 + ntap) * WG_TILE_BYTES);
+        mbar_expect_tx(&full_bar[s], WG_TILE_BYTES + ntap * C::X_BYTES);
         const int gx = ax0 * p.out_stride + p.out_off_x, gy = ay0 * p.out_stride + p.out_off_y;
         tma_load_5d(dst, &map_g, &full_bar[s], m0, gx, gy, b0, sg);
         tma_load_5d(dst + WG_HALF_BYTES, &map_g, &full_bar[s], m0 + 64, gx, gy, b0, sg);
         for (int tp = 0; tp < ntap; ++tp) {
           const int tap = tap0 + tp;
-          uint8_t* xd = dst + (1 + tp) * WG_TILE_BYTES;
+          uint8_t* xd = dst + WG_TILE_BYTES + tp * C::X_BYTES;
           const int xx = ax0 * p.in_stride + p.tap_dx[tap], xy = ay0 * p.in_stride + p.tap_dy[tap];
-          tma_load_5d(xd, &map_x, &full_bar[s], n0, xx, xy, b0, sx);
-          tma_load_5d(xd + WG_HALF_BYTES, &map_x, &full_bar[s], n0 + 64, xx, xy, b0, sx);
+#pragma unroll
+          for (int h = 0; h < WG_N / 64; ++h)
+            tma_load_5d(xd + h * WG_HALF_BYTES, &map_x, &full_bar[s], n0 + 64 * h, xx, xy, b0, sx);
         }
       }
     }
@@ -142,7 +155,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
           for (int k = 0; k < WG_KA / 16; ++k) {
             // 16 anchors = two 8-row groups = 2048 bytes further down the tile
             const uint64_t da = make_sw128_mn_desc(base + k * 2048, WG_HALF_BYTES);
-            const uint64_t db = make_sw128_mn_desc(base + (1 + tp) * WG_TILE_BYTES + k * 2048, WG_HALF_BYTES);
+            const uint64_t db = make_sw128_mn_desc(base + WG_TILE_BYTES + tp * C::X_BYTES + k * 2048, WG_HALF_BYTES);
             umma_bf16(tmem_base + tp * WG_N, da, db, idesc, (it | k) != 0 ? 1u : 0u);
           }
         }
@@ -226,8 +239,16 @@ extern "C" int te_conv_wgrad_tc(float* gw, const void* g, const void* x, const t
   p.tiles_b = (d.batch + p.nb - 1) / p.nb;
   p.n_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
   p.gw = gw;
-  const int out_tiles = ((d.cout + WG_M - 1) / WG_M) * ((d.cin + WG_N - 1) / WG_N);
-  const int tap_groups = (d.ntaps + WG_TAPS - 1) / WG_TAPS;
+  // cin tile: 128.  The 256-wide tile (TE_WG_N=256, Cin % 256 == 0) was measured SLOWER on every shape (512->512 @64^2
+  // B=16: 1123 -> 918 TFLOP/s; 256->256 @128^2: 1148 -> 1067; tools/wgrad_probe.py, same box): with two taps resident
+  // the nine taps need five passes over G instead of three and the 80 KB stages leave a 2-deep ring — this kernel is
+  // bound by operand feed, not by MMA issue.
+  static int force_n = -1;
+  if (force_n < 0) { const char* e = getenv("TE_WG_N"); force_n = e ? atoi(e) : 0; }
+  const int wg_n = (d.cin % 256 == 0 && force_n == 256) ? 256 : 128;
+  const int wg_taps = wg_n == 256 ? WgCfg<256>::TAPS : WgCfg<128>::TAPS;
+  const int out_tiles = ((d.cout + WG_M - 1) / WG_M) * ((d.cin + wg_n - 1) / wg_n);
+  const int tap_groups = (d.ntaps + wg_taps - 1) / wg_taps;
   p.taps_per_group = (d.ntaps + tap_groups - 1) / tap_groups;  // balanced: 9 -> 3+3+3, 4 -> 2+2
   // split the anchor reduction so that about one wave of CTAs exists, at least 8 tiles per split
   int splits;
@@ -289,11 +310,17 @@ extern "C" int te_conv_wgrad_tc(float* gw, const void* g, const void* x, const t
   }
   static bool configured = false;
   if (!configured) {
-    TE_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_TOTAL));
+    TE_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       WgCfg<128>::SMEM_TOTAL));
+    TE_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       WgCfg<256>::SMEM_TOTAL));
     configured = true;
   }
   dim3 grid(out_tiles, tap_groups, splits);
-  wgrad_tc_kernel<<<grid, WG_THREADS, WG_SMEM_TOTAL, static_cast<cudaStream_t>(stream)>>>(mg, mx, p);
+  if (wg_n == 256)
+    wgrad_tc_kernel<256><<<grid, WG_THREADS, WgCfg<256>::SMEM_TOTAL, static_cast<cudaStream_t>(stream)>>>(mg, mx, p);
+  else
+    wgrad_tc_kernel<128><<<grid, WG_THREADS, WgCfg<128>::SMEM_TOTAL, static_cast<cudaStream_t>(stream)>>>(mg, mx, p);
   TE_CHECK_LAUNCH();
   return TE_OK;
 }
