@@ -29,12 +29,19 @@ constexpr int WG_THREADS = 192;
 constexpr int WG_HALF_BYTES = WG_KA * 128;          // one [64 anchors x 64 ch] box = 8 KB
 constexpr int WG_TILE_BYTES = 2 * WG_HALF_BYTES;    // G tile [64 anchors x 128 ch] = 16 KB
 
+// Haloed X box of the HALO variant: a 4 x 16 anchor tile plus one column either side, [4][18] pixels x 64 channels per
+// half = 72 rows of 128 B (padded to a multiple of the 1024-byte swizzle atom); the three taps of a group (same dy,
+// dx = d0, d0+1, d0+2) are row-shifted VIEWS of it.
+constexpr int WG_HALO_W = 18, WG_HALO_H = 4;
+constexpr int WG_HALO_HALF = ((WG_HALO_W * WG_HALO_H * 128 + 1023) / 1024) * 1024;   // 10240
+
 // WN = cin columns per CTA tile (128 or 256)
-template <int WN> struct WgCfg {
+template <int WN, bool HALO = false> struct WgCfg {
   static constexpr int TAPS = 512 / WN > 3 ? 3 : 512 / WN;       // taps resident in TMEM: 3 (N=128), 2 (N=256)
   static constexpr int X_BYTES = (WN / 64) * WG_HALF_BYTES;      // one tap's X tile
-  static constexpr int STAGE_BYTES = WG_TILE_BYTES + TAPS * X_BYTES;   // 64 KB / 80 KB
-  static constexpr int STAGES = WN == 128 ? 3 : 2;
+  static constexpr int STAGE_BYTES = HALO ? WG_TILE_BYTES + (WN / 64) * WG_HALO_HALF   // G + ONE haloed X box: 36 KB
+                                          : WG_TILE_BYTES + TAPS * X_BYTES;            // G + TAPS X tiles: 64 / 80 KB
+  static constexpr int STAGES = HALO ? 5 : (WN == 128 ? 3 : 2);
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int SMEM_TOTAL = BAR_OFFSET + 128 + 1024;
 };
@@ -60,11 +67,11 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int WG_N>
+template <int WG_N, bool HALO>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_x,
                 const __grid_constant__ WgParams p) {
-  using C = WgCfg<WG_N>;
+  using C = WgCfg<WG_N, HALO>;
   constexpr int WG_STAGES = C::STAGES, WG_STAGE_BYTES = C::STAGE_BYTES, WG_BAR_OFFSET = C::BAR_OFFSET;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -126,8 +133,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
         const int tile_h = t % p.tiles_h; t /= p.tiles_h;
         const int b0 = t * p.nb, ay0 = tile_h * p.th, ax0 = tile_w * p.tw;
         uint8_t* dst = smem + s * WG_STAGE_BYTES;
-        mbar_expect_tx(&full_bar[s], WG_TILE_BYTES + ntap * C::X_BYTES);
         const int gx = ax0 * p.out_stride + p.out_off_x, gy = ay0 * p.out_stride + p.out_off_y;
+        if (HALO) {
+          // ONE haloed box per 64-channel half serves every tap of the group (same dy, consecutive dx)
+          mbar_expect_tx(&full_bar[s], WG_TILE_BYTES + (WG_N / 64) * (WG_HALO_W * WG_HALO_H * 128));
+          tma_load_5d(dst, &map_g, &full_bar[s], m0, gx, gy, b0, sg);
+          tma_load_5d(dst + WG_HALF_BYTES, &map_g, &full_bar[s], m0 + 64, gx, gy, b0, sg);
+          const int xx = ax0 + p.tap_dx[tap0], xy = ay0 + p.tap_dy[tap0];
+#pragma unroll
+          for (int h = 0; h < WG_N / 64; ++h)
+            tma_load_5d(dst + WG_TILE_BYTES + h * WG_HALO_HALF, &map_x, &full_bar[s], n0 + 64 * h, xx, xy, b0, sx);
+          continue;
+        }
+        mbar_expect_tx(&full_bar[s], WG_TILE_BYTES + ntap * C::X_BYTES);
         tma_load_5d(dst, &map_g, &full_bar[s], m0, gx, gy, b0, sg);
         tma_load_5d(dst + WG_HALF_BYTES, &map_g, &full_bar[s], m0 + 64, gx, gy, b0, sg);
         for (int tp = 0; tp < ntap; ++tp) {
@@ -155,7 +173,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
           for (int k = 0; k < WG_KA / 16; ++k) {
             // 16 anchors = two 8-row groups = 2048 bytes further down the tile
             const uint64_t da = make_sw128_mn_desc(base + k * 2048, WG_HALF_BYTES);
-            const uint64_t db = make_sw128_mn_desc(base + WG_TILE_BYTES + tp * C::X_BYTES + k * 2048, WG_HALF_BYTES);
+            // HALO: K16 step k = image row k of the 4 x 16 tile; the tap's view starts (k * 18 + dx - dx0) rows into the
+            // box (the swizzle is a function of the absolute address, so a row-shifted start needs no base offset)
+            const uint64_t db = HALO
+                ? make_sw128_mn_desc(base + WG_TILE_BYTES + (k * WG_HALO_W + p.tap_dx[tap0 + tp] - p.tap_dx[tap0]) * 128,
+                                     WG_HALO_HALF)
+                : make_sw128_mn_desc(base + WG_TILE_BYTES + tp * C::X_BYTES + k * 2048, WG_HALF_BYTES);
             umma_bf16(tmem_base + tp * WG_N, da, db, idesc, (it | k) != 0 ? 1u : 0u);
           }
         }
@@ -287,6 +310,18 @@ extern "C" int te_conv_wgrad_tc(float* gw, const void* g, const void* x, const t
     p.npairs = sp.n;
     for (int i = 0; i < 6; ++i) { p.pair_g[i] = sp.a[i]; p.pair_x[i] = sp.b[i]; }
   }
+  // Haloed-box variant: stride-1 input, 4 x 16 anchor tiles of ONE sample, every tap group = one row of taps with
+  // consecutive dx (the 3x3 convolutions and their transposed/polyphase forms with >= 2 taps per group)
+  static int use_halo = -1;
+  if (use_halo < 0) { const char* e = getenv("TE_WG_HALO"); use_halo = e ? atoi(e) : 1; }
+  bool halo = use_halo != 0 && wg_n == 128 && d.in_stride == 1 && p.tw == 16 && p.th == 4 && p.nb == 1 && d.ntaps >= 2;
+  for (int g0 = 0; halo && g0 < d.ntaps; g0 += p.taps_per_group) {
+    const int ng = d.ntaps - g0 < p.taps_per_group ? d.ntaps - g0 : p.taps_per_group;
+    for (int t = 1; t < ng; ++t)
+      if (d.tap_dy[g0 + t] != d.tap_dy[g0] || d.tap_dx[g0 + t] <= d.tap_dx[g0 + t - 1] ||
+          d.tap_dx[g0 + t] - d.tap_dx[g0] > WG_HALO_W - 16)
+        halo = false;
+  }
   CUtensorMap mg, mx;
   {
     const uint32_t os = uint32_t(d.out_stride);
@@ -304,23 +339,29 @@ extern "C" int te_conv_wgrad_tc(float* gw, const void* g, const void* x, const t
     uint64_t strides[4] = {uint64_t(d.cin) * 2, uint64_t(d.win) * d.cin * 2, uint64_t(d.hin) * d.win * d.cin * 2,
                            uint64_t(d.batch) * d.hin * d.win * d.cin * 2};
     uint32_t box[5] = {64, uint32_t(p.tw) * is, uint32_t(p.th) * is, uint32_t(p.nb), 1};
+    if (halo) { box[1] = WG_HALO_W; box[2] = WG_HALO_H; }
     uint32_t estr[5] = {1, is, is, 1, 1};
     int rc = encode_map_bf16(&mx, x, 5, dims, strides, box, estr);
     if (rc) return rc;
   }
   static bool configured = false;
   if (!configured) {
-    TE_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    TE_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        WgCfg<128>::SMEM_TOTAL));
-    TE_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    TE_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        WgCfg<256>::SMEM_TOTAL));
+    TE_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       WgCfg<128, true>::SMEM_TOTAL));
     configured = true;
   }
   dim3 grid(out_tiles, tap_groups, splits);
-  if (wg_n == 256)
-    wgrad_tc_kernel<256><<<grid, WG_THREADS, WgCfg<256>::SMEM_TOTAL, static_cast<cudaStream_t>(stream)>>>(mg, mx, p);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (halo)
+    wgrad_tc_kernel<128, true><<<grid, WG_THREADS, WgCfg<128, true>::SMEM_TOTAL, st>>>(mg, mx, p);
+  else if (wg_n == 256)
+    wgrad_tc_kernel<256, false><<<grid, WG_THREADS, WgCfg<256>::SMEM_TOTAL, st>>>(mg, mx, p);
   else
-    wgrad_tc_kernel<128><<<grid, WG_THREADS, WgCfg<128>::SMEM_TOTAL, static_cast<cudaStream_t>(stream)>>>(mg, mx, p);
+    wgrad_tc_kernel<128, false><<<grid, WG_THREADS, WgCfg<128>::SMEM_TOTAL, st>>>(mg, mx, p);
   TE_CHECK_LAUNCH();
   return TE_OK;
 }
