@@ -189,10 +189,12 @@ int te_conv_wgrad_tc(float* gw, const void* g, const void* x, const te_tc_conv_d
 /* te_conv_wgrad_tc's tap-major accumulator -> the master weight's layout (what autograd hands to the optimiser):
  *   trans 0:  out[b][o][i][t] = ws[b][t][o*ld + i]        trans 1:  out[b][o][i][t] = ws[b][t][i*ld + o]
  * ws [batch][taps][rows][ld] f32 (rows x ld = the padded (cout, cin) of the convolution descriptor), out
- * [batch][o_dim][i_dim][taps] f32 = the [O, I, k, k] weight gradient (batch > 1: per-sample weights).  Replaces
- * the permute + contiguous copy after every weight-gradient launch. */
-int te_wgrad_unpack(float* out, const float* ws, int batch, int o_dim, int i_dim, int taps, int rows, int ld,
-                    int trans, void* stream);
+ * [batch][o_dim][i_dim][taps] f32 = the [O, I, k, k] weight gradient (batch > 1: per-sample weights); taps = 1, 4
+ * or 9.  clear != 0: every element read is written back as 0, so the accumulator can be reused by the next
+ * te_conv_wgrad_tc launch without a memset.  Replaces the permute + contiguous copy after every weight-gradient
+ * launch (and, with clear, the zero fill before it). */
+int te_wgrad_unpack(float* out, float* ws, int batch, int o_dim, int i_dim, int taps, int rows, int ld, int trans,
+                    int clear, void* stream);
 
 /* Convenience form: stride 1, padding k/2, kh = kw in {1,3}, bf16 output. */
 int te_conv2d_tc(void* y, const void* x, const void* w, const float* out_scale, const float* bias,

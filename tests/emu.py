@@ -323,10 +323,12 @@ def from_rgb_bwd(gw, gbias, gx, g, out, x, w, wscale, slope, gain):
         gx.copy_((torch.einsum("bohw,oc->bchw", gp, w.double()) * wscale).float())
 
 
-def wgrad_unpack(out, ws, batch, o_dim, i_dim, taps, rows, ld, trans):
+def wgrad_unpack(out, ws, batch, o_dim, i_dim, taps, rows, ld, trans, clear=False):
     w = ws.reshape(batch, taps, rows, ld)
     src = w[:, :, :i_dim, :o_dim].permute(0, 3, 2, 1) if trans else w[:, :, :o_dim, :i_dim].permute(0, 2, 3, 1)
     out.copy_(src.reshape(out.shape))
+    if clear:
+        (w[:, :, :i_dim, :o_dim] if trans else w[:, :, :o_dim, :i_dim]).zero_()
 
 
 def image_prep(dst_nchw, dst_nhwc8, src_hwc, flip, batch, h, w):

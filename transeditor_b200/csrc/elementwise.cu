@@ -321,56 +321,75 @@ extern "C" int te_pack_weights_tc(const te_pack_task* tasks, int n_tasks, void* 
 //                                                              the workspace's logical (cout, cin) is (I, O))
 namespace te {
 
+template <int TAPS>
 __global__ void __launch_bounds__(256)
-wgrad_unpack_kernel(float* __restrict__ out, const float* __restrict__ ws, int o_dim, int i_dim, int taps, int rows,
-                    int ld, int trans) {
-  extern __shared__ float wu_tile[];   // [taps][32][33]
+wgrad_unpack_kernel(float* __restrict__ out, float* __restrict__ ws, int o_dim, int i_dim, int rows, int ld, int trans,
+                    int clear) {
+  extern __shared__ float wu_tile[];   // [TAPS][32][33]
   const int o0 = blockIdx.y * 32, i0 = blockIdx.x * 32;
-  const float* wsb = ws + int64_t(blockIdx.z) * taps * rows * ld;
-  float* outb = out + int64_t(blockIdx.z) * o_dim * i_dim * taps;
+  float* wsb = ws + int64_t(blockIdx.z) * TAPS * rows * ld;
+  float* outb = out + int64_t(blockIdx.z) * o_dim * i_dim * TAPS;
   const int cx = threadIdx.x & 31, cy = threadIdx.x >> 5;   // 32 x 8
-  for (int t = 0; t < taps; ++t) {
-    const float* wt = wsb + int64_t(t) * rows * ld;
+  // all of this thread's loads first (TAPS x 4 independent 4-byte loads in flight), then the shared-memory transpose
+  float v[TAPS][4];
 #pragma unroll
-    for (int r = cy; r < 32; r += 8) {
-      float v = 0.f;
-      if (!trans) {
-        const int o = o0 + r, i = i0 + cx;
-        if (o < o_dim && i < i_dim) v = wt[int64_t(o) * ld + i];
-        wu_tile[(t * 32 + r) * 33 + cx] = v;           // tile[t][o_l][i_l]
-      } else {
-        const int i = i0 + r, o = o0 + cx;
-        if (o < o_dim && i < i_dim) v = wt[int64_t(i) * ld + o];
-        wu_tile[(t * 32 + cx) * 33 + r] = v;           // tile[t][o_l][i_l]
-      }
+  for (int t = 0; t < TAPS; ++t) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int r = cy + 8 * q;
+      const int o = trans ? o0 + cx : o0 + r, i = trans ? i0 + r : i0 + cx;
+      const int64_t off = int64_t(t) * rows * ld + (trans ? int64_t(i) * ld + o : int64_t(o) * ld + i);
+      const bool ok = o < o_dim && i < i_dim;
+      v[t][q] = ok ? wsb[off] : 0.f;
+      if (clear && ok) wsb[off] = 0.f;     // hand the accumulator back zeroed: the next launch needs no memset
     }
   }
+#pragma unroll
+  for (int t = 0; t < TAPS; ++t)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int r = cy + 8 * q;
+      if (!trans) wu_tile[(t * 32 + r) * 33 + cx] = v[t][q];    // tile[t][o_l][i_l]
+      else wu_tile[(t * 32 + cx) * 33 + r] = v[t][q];
+    }
   __syncthreads();
-  const int row_len = 32 * taps;                       // floats of one output row segment: (i_l, t) contiguous
+  constexpr int row_len = 32 * TAPS;                   // floats of one output row segment: (i_l, t) contiguous
   for (int idx = threadIdx.x; idx < 32 * row_len; idx += 256) {
     const int ol = idx / row_len, rem = idx - ol * row_len;
-    const int il = rem / taps, t = rem - il * taps;
+    const int il = rem / TAPS, t = rem - il * TAPS;
     const int o = o0 + ol, i = i0 + il;
-    if (o < o_dim && i < i_dim) outb[(int64_t(o) * i_dim + i) * taps + t] = wu_tile[(t * 32 + ol) * 33 + il];
+    if (o < o_dim && i < i_dim) outb[(int64_t(o) * i_dim + i) * TAPS + t] = wu_tile[(t * 32 + ol) * 33 + il];
   }
+}
+
+template <int TAPS>
+static int wgrad_unpack_launch(float* out, float* ws, int batch, int o_dim, int i_dim, int rows, int ld, int trans,
+                               int clear, cudaStream_t st) {
+  dim3 grid((i_dim + 31) / 32, (o_dim + 31) / 32, batch);
+  const size_t smem = size_t(TAPS) * 32 * 33 * sizeof(float);
+  wgrad_unpack_kernel<TAPS><<<grid, 256, smem, st>>>(out, ws, o_dim, i_dim, rows, ld, trans, clear);
+  TE_CHECK_LAUNCH();
+  return TE_OK;
 }
 
 }  // namespace te
 
-extern "C" int te_wgrad_unpack(float* out, const float* ws, int batch, int o_dim, int i_dim, int taps, int rows,
-                               int ld, int trans, void* stream) {
+extern "C" int te_wgrad_unpack(float* out, float* ws, int batch, int o_dim, int i_dim, int taps, int rows, int ld,
+                               int trans, int clear, void* stream) {
   using namespace te;
   TE_CHECK_ARG(batch >= 0 && o_dim >= 0 && i_dim >= 0, "wgrad_unpack: negative size");
   if (int64_t(batch) * o_dim * i_dim == 0) return TE_OK;
   TE_CHECK_ARG(out && ws, "wgrad_unpack: null pointer");
-  TE_CHECK_ARG(taps >= 1 && taps <= 9, "wgrad_unpack: 1..9 taps");
   TE_CHECK_ARG(trans ? (rows >= i_dim && ld >= o_dim) : (rows >= o_dim && ld >= i_dim),
                "wgrad_unpack: workspace [%d, %d] smaller than the weight [%d, %d]", rows, ld, o_dim, i_dim);
   TE_CHECK_ARG(batch <= 65535, "wgrad_unpack: batch too large");
-  dim3 grid((i_dim + 31) / 32, (o_dim + 31) / 32, batch);
-  const size_t smem = size_t(taps) * 32 * 33 * sizeof(float);
-  wgrad_unpack_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(out, ws, o_dim, i_dim, taps, rows, ld,
-                                                                              trans);
-  TE_CHECK_LAUNCH();
-  return TE_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (taps) {
+    case 1: return wgrad_unpack_launch<1>(out, ws, batch, o_dim, i_dim, rows, ld, trans, clear, st);
+    case 4: return wgrad_unpack_launch<4>(out, ws, batch, o_dim, i_dim, rows, ld, trans, clear, st);
+    case 9: return wgrad_unpack_launch<9>(out, ws, batch, o_dim, i_dim, rows, ld, trans, clear, st);
+    default: break;
+  }
+  set_error("wgrad_unpack: kernels of 1, 4 (2x2) or 9 (3x3) taps only, got %d", taps);
+  return TE_ERR_INVALID;
 }

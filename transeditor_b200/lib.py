@@ -92,7 +92,7 @@ _SIGNATURES = {
     "te_adam_ema_devstep": ([_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _P, _F, _F, _P], _I),
     "te_conv_tc": ([_P, _P, _P, _P, _P, ctypes.POINTER(TcConvDesc), _P], _I),
     "te_conv_wgrad_tc": ([_P, _P, _P, ctypes.POINTER(TcConvDesc), _P], _I),
-    "te_wgrad_unpack": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _P], _I),
+    "te_wgrad_unpack": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P], _I),
     "te_scale_bc": ([_P, _P, _P, _L, _L, _I, _I, _P], _I),
     "te_dot_bc": ([_P, _P, _P, _L, _L, _I, _I, _P], _I),
     "te_split_bf16": ([_P, _P, _P, _L, _L, _I, _I, _P], _I),
@@ -426,7 +426,7 @@ def from_rgb_bwd(gw, gbias, gx, g, out, x, w, wscale, slope, gain):
     _count()
 
 
-def wgrad_unpack(out, ws, batch, o_dim, i_dim, taps, rows, ld, trans):
-    _check(load().te_wgrad_unpack(ptr(out), ptr(ws), batch, o_dim, i_dim, taps, rows, ld, int(trans), stream()),
-           "wgrad_unpack")
+def wgrad_unpack(out, ws, batch, o_dim, i_dim, taps, rows, ld, trans, clear=False):
+    _check(load().te_wgrad_unpack(ptr(out), ptr(ws), batch, o_dim, i_dim, taps, rows, ld, int(trans), int(clear),
+                                  stream()), "wgrad_unpack")
     _count()

@@ -25,6 +25,8 @@ Two operand precisions, selected by the dtype of the activations:
 Reference call sites replaced: F.conv2d / F.conv_transpose2d in model_spatial_query.py:177-183,318,327,333
 and their autograd gradients.
 """
+import os
+
 import torch
 from torch.autograd import Function
 
@@ -348,6 +350,23 @@ def conv_raw(x, wp, mode, out_scale=None, bias=None, act=False, act_gain=0.0, re
     return y
 
 
+_WGRAD_WS = {}   # (shape, device, stream) -> all-zero f32 accumulator handed back zeroed by te_wgrad_unpack(clear=1)
+
+
+def _wgrad_workspace(shape, device):
+    """The tap-major f32 accumulator of one weight-gradient launch.  CUDA: a persistent buffer per (shape, stream)
+    that is all-zero between uses — te_wgrad_unpack reads it and writes the zeros back in the same pass, so neither a
+    memset nor an allocation precedes the ~120 weight-gradient launches of an iteration.  (Kernels on one stream run in
+    order, so consecutive launches may share it; TE_WGRAD_WS_CACHE=0 allocates a fresh zeroed buffer per call.)"""
+    if device.type != "cuda" or os.environ.get("TE_WGRAD_WS_CACHE", "1") == "0":
+        return torch.zeros(shape, dtype=torch.float32, device=device), False
+    key = (shape, device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _WGRAD_WS.get(key)
+    if ws is None:
+        ws = _WGRAD_WS[key] = torch.zeros(shape, dtype=torch.float32, device=device)
+    return ws, True
+
+
 def wgrad_raw(g, x, mode, w_shape, scale=1.0):
     """Gradient w.r.t. the master weight [O, I, K, K] (f32) of y = conv(x, W * scale; mode) given g = dL/dy."""
     lib.require_cuda(g, x)
@@ -359,14 +378,21 @@ def wgrad_raw(g, x, mode, w_shape, scale=1.0):
     k = mode.k
     per_sample = len(w_shape) == 5
     shape = (b, k * k, cout, cin) if per_sample else (k * k, cout, cin)
-    gw = torch.zeros(shape, dtype=torch.float32, device=x.device)
-    for launch in mode.launches(hin, win, hout, wout):
-        lib.conv_wgrad_tc(gw, go, xo, _desc(x, cout, hout, wout, launch, k * k, per_sample=per_sample,
-                                            wgrad_alpha=scale, split=nseg))
-    # tap-major accumulator -> [O, I, k, k] (taps innermost) in one coalesced pass (te_wgrad_unpack)
+    gw, cached = _wgrad_workspace(shape, x.device)
     o, i = w_shape[-4], w_shape[-3]
     out = torch.empty((b, o, i, k, k) if per_sample else (o, i, k, k), dtype=torch.float32, device=x.device)
-    lib.wgrad_unpack(out, gw, b if per_sample else 1, o, i, k * k, cout, cin, mode.transposed)
+    try:
+        for launch in mode.launches(hin, win, hout, wout):
+            lib.conv_wgrad_tc(gw, go, xo, _desc(x, cout, hout, wout, launch, k * k, per_sample=per_sample,
+                                                wgrad_alpha=scale, split=nseg))
+        # tap-major accumulator -> [O, I, k, k] (taps innermost) in one coalesced pass that also re-zeroes it
+        lib.wgrad_unpack(out, gw, b if per_sample else 1, o, i, k * k, cout, cin, mode.transposed, cached)
+    except Exception:
+        if cached:   # a half-finished accumulation must not be served again
+            _WGRAD_WS.clear()
+        raise
+    if cached and (o < (cin if mode.transposed else cout) or i < (cout if mode.transposed else cin)):
+        gw.zero_()   # padded rows / columns are not visited by the unpack (ToRGB's 3 -> 8 channels): clear them too
     return out
 
 
