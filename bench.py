@@ -344,6 +344,69 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def other_configs(dev):
+    """BASELINE configs that are not the headline, measured in the same run (device-resident inputs, CUDA events, CUDA
+    graphs like the product's inference API): [0] the reference's CPU-runnable case on the GPU (generator forward 256^2
+    batch 1), [3] generator inference 1024^2 batch 8, [4] pSp inversion forward 256^2 batch 32.  Best effort: a failure
+    is recorded, never raised (the headline line must still print)."""
+    import gc
+    out = {}
+
+    def timed_ms(fn, iters):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    def release():
+        gc.collect()
+        torch.cuda.empty_cache()
+
+    try:
+        import model_spatial_query as M
+        from transeditor_b200 import model as te_model
+        from transeditor_b200.inference import GraphedGenerator
+        te_model.set_precision("bf16")
+        torch.backends.cuda.matmul.allow_tf32 = True
+        for key, size, batch, iters in (("generator_forward_256_b1", 256, 1, 50), ("generator_inference_1024_b8", 1024, 8, 10)):
+            torch.manual_seed(0)
+            t = 2 * (size.bit_length() - 1) - 2
+            g = M.Generator(size, 512, 512, t, channel_multiplier=2, n_trans=8, pixel_norm_op_dim=1).to(dev).eval()
+            z, p = torch.randn(batch, 512, 16, device=dev), torch.randn(batch, 512, 16, device=dev)
+            gg = GraphedGenerator(g, batch)
+            ms = timed_ms(lambda: gg(z, p), iters)
+            out[key] = {"ms_per_forward": round(ms, 3), "img_per_s": round(batch / ms * 1e3, 1), "dtype": "bf16",
+                        "mode": "cuda-graph, inputs on the device"}
+            del gg, g
+            release()
+    except Exception as e:  # noqa: BLE001
+        out["generator_error"] = repr(e)[:300]
+    try:
+        import model_spatial_query as M
+        from transeditor_b200 import model as te_model
+        from transeditor_b200.inversion import GradualStyleEncoder, InversionPipeline
+        te_model.set_precision("bf16")
+        torch.manual_seed(0)
+        enc = GradualStyleEncoder(50, "ir_se").to(dev).eval()
+        g = M.Generator(256, 512, 512, 14, channel_multiplier=2, n_trans=8, pixel_norm_op_dim=1).to(dev).eval()
+        x = torch.rand(32, 3, 256, 256, device=dev) * 2 - 1
+        pipe = InversionPipeline(enc, g, resize=False, graph=True)
+        ms = timed_ms(lambda: pipe(x), 10)
+        out["inversion_forward_256_b32"] = {"ms_per_forward": round(ms, 3), "img_per_s": round(32 / ms * 1e3, 1),
+                                            "dtype": "bf16", "mode": "pSp encoder + generator, one cuda graph"}
+        del pipe, enc, g
+        release()
+    except Exception as e:  # noqa: BLE001
+        out["inversion_error"] = repr(e)[:300]
+    return out
+
+
 # ------------------------------------------------------------------------------ our arm
 def run_ours(args, rank, local_rank, world):
     import torch.distributed as dist
@@ -501,6 +564,8 @@ def run_ours(args, rank, local_rank, world):
                                "lazy_regularisers": "same cadence as the main line (i = 0 .. steps-1)"}
         del tr32
         te_model.set_precision(args.precision)
+    if rank == 0 and world == 1 and not args.no_extras:
+        line["other_configs"] = other_configs(dev)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, cores, done, dt, kind = cpu_train_rate(2, 0, batch=1, seconds_cap=20, lazy=False)
         line["cpu_baseline"] = {"value": round(rate, 4), "unit": UNIT, "cores": cores, "kind": kind,
@@ -516,6 +581,7 @@ def main():
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the other_configs sub-record (BASELINE configs 0/3/4)")
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "fp32_simt"],
