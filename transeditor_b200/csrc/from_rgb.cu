@@ -76,8 +76,8 @@ from_rgb_fwd_kernel(T* __restrict__ y, const float* __restrict__ x, const float*
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256)
+template <typename T, bool GX>
+__global__ void __launch_bounds__(256, GX ? 2 : 3)
 from_rgb_bwd_kernel(float* __restrict__ gw, float* __restrict__ gb, float* __restrict__ gx, const T* __restrict__ g,
                     const T* __restrict__ out, const float* __restrict__ x, const float* __restrict__ w,
                     int plane, int cout, float wscale, float slope, float gain) {
@@ -88,7 +88,7 @@ from_rgb_bwd_kernel(float* __restrict__ gw, float* __restrict__ gb, float* __res
 #pragma unroll
   for (int j = 0; j < 8; ++j)
 #pragma unroll
-    for (int c = 0; c < 3; ++c) wr[j][c] = gx ? __ldg(w + (cg * 8 + j) * 3 + c) * wscale : 0.f;
+    for (int c = 0; c < 3; ++c) wr[j][c] = GX ? __ldg(w + (cg * 8 + j) * 3 + c) * wscale : 0.f;
   float aw[8][3] = {}, ab[8] = {};
   const float m_pos = gain, m_neg = gain * slope;
   // all threads of a pixel group stay in the loop together (the shuffles below need the full group)
@@ -97,7 +97,7 @@ from_rgb_bwd_kernel(float* __restrict__ gw, float* __restrict__ gb, float* __res
   const int iters = (plane + step - 1) / step;
   const T* gb_ = g + b * int64_t(plane) * cout + cg * 8;
   const T* ob_ = out + b * int64_t(plane) * cout + cg * 8;
-#pragma unroll 2
+#pragma unroll(GX ? 2 : 4)
   for (int it = 0; it < iters; ++it) {
     const int p = (it * gridDim.x + blockIdx.x) * rows + prow;
     const bool live = p < plane;
@@ -117,7 +117,7 @@ from_rgb_bwd_kernel(float* __restrict__ gw, float* __restrict__ gb, float* __res
         aw[j][2] = fmaf(gpv[j], x2, aw[j][2]);
       }
     }
-    if (gx) {  // image gradient: sum over all output channels = over the ovec threads of this pixel (consecutive lanes)
+    if (GX) {  // image gradient: sum over all output channels = over the ovec threads of this pixel (consecutive lanes)
       float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -202,18 +202,22 @@ extern "C" int te_from_rgb_bwd(float* gw, float* gbias, float* gx, const void* g
   const dim3 grid(gx_ > 0 ? gx_ : 1, batch);
   const size_t smem = size_t(rows) * cout * 4 * sizeof(float);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static bool cfg = false;
+  if (!cfg) {
+    TE_CHECK_CUDA(cudaFuncSetAttribute(from_rgb_bwd_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    TE_CHECK_CUDA(cudaFuncSetAttribute(from_rgb_bwd_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    TE_CHECK_CUDA(cudaFuncSetAttribute(from_rgb_bwd_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    TE_CHECK_CUDA(cudaFuncSetAttribute(from_rgb_bwd_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    cfg = true;
+  }
   if (dtype == TE_BF16) {
-    auto kern = from_rgb_bwd_kernel<__nv_bfloat16>;
-    static bool cfg = false;
-    if (!cfg) { TE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536)); cfg = true; }
-    kern<<<grid, 256, smem, st>>>(gw, gbias, gx, static_cast<const __nv_bfloat16*>(g),
-                                  static_cast<const __nv_bfloat16*>(out), x, w, plane, cout, wscale, slope, gain);
+    const __nv_bfloat16 *gq = static_cast<const __nv_bfloat16*>(g), *oq = static_cast<const __nv_bfloat16*>(out);
+    if (gx) from_rgb_bwd_kernel<__nv_bfloat16, true><<<grid, 256, smem, st>>>(gw, gbias, gx, gq, oq, x, w, plane, cout, wscale, slope, gain);
+    else from_rgb_bwd_kernel<__nv_bfloat16, false><<<grid, 256, smem, st>>>(gw, gbias, gx, gq, oq, x, w, plane, cout, wscale, slope, gain);
   } else {
-    auto kern = from_rgb_bwd_kernel<float>;
-    static bool cfg = false;
-    if (!cfg) { TE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536)); cfg = true; }
-    kern<<<grid, 256, smem, st>>>(gw, gbias, gx, static_cast<const float*>(g), static_cast<const float*>(out), x, w,
-                                  plane, cout, wscale, slope, gain);
+    const float *gq = static_cast<const float*>(g), *oq = static_cast<const float*>(out);
+    if (gx) from_rgb_bwd_kernel<float, true><<<grid, 256, smem, st>>>(gw, gbias, gx, gq, oq, x, w, plane, cout, wscale, slope, gain);
+    else from_rgb_bwd_kernel<float, false><<<grid, 256, smem, st>>>(gw, gbias, gx, gq, oq, x, w, plane, cout, wscale, slope, gain);
   }
   TE_CHECK_LAUNCH();
   return TE_OK;
