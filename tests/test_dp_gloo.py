@@ -4,6 +4,8 @@ parameters == single-process Adam on the rank-averaged gradient; skipped tail gr
 import os
 import socket
 
+import pytest
+
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -137,3 +139,30 @@ def test_bucketed_overlapped_allreduce_sums_the_ranks_gradients():
     assert torch.allclose(out[0], want, atol=1e-6)
     o = ref.offsets["unused"]
     assert out[0][o:o + 5].abs().sum().item() == 0
+
+
+def _loss_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from transeditor_b200.train_step import Trainer
+    tr = Trainer.__new__(Trainer)      # only the reduction helpers are exercised: no models, no GPU
+    tr.world, tr.rank = world, rank
+    tr.losses = {"d": torch.tensor(1.0 + rank), "g": torch.tensor(10.0 * (rank + 1)), "r1": torch.tensor(0.5)}
+    tr.mean_path_length = torch.tensor(2.0 + 4 * rank)
+    keys, vec = tr.reduced_losses()
+    out[rank] = (keys, vec.tolist(), float(tr.mean_path_length_avg()))
+    dist.destroy_process_group()
+
+
+def test_loss_dict_and_path_length_reduction_match_the_reference_semantics():
+    """reduce_loss_dict (utils/distributed.py:102-124): sorted keys, reduce to rank 0, divided by the world size THERE
+    (the other ranks keep what dist.reduce leaves them); reduce_sum(mean_path_length) / world on every rank."""
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_loss_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    keys, vec0, mpl0 = out[0]
+    assert keys == ["d", "g", "r1"]
+    assert vec0 == pytest.approx([1.5, 15.0, 0.5])
+    assert mpl0 == pytest.approx(4.0) and out[1][2] == pytest.approx(4.0)
