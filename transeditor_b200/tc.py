@@ -367,6 +367,12 @@ def _wgrad_workspace(shape, device):
     return ws, True
 
 
+def clear_wgrad_workspaces():
+    """Drop the cached weight-gradient accumulators (a new Trainer / a new set of CUDA graphs starts from fresh ones
+    rather than from buffers that live in another graph's memory pool)."""
+    _WGRAD_WS.clear()
+
+
 def wgrad_raw(g, x, mode, w_shape, scale=1.0):
     """Gradient w.r.t. the master weight [O, I, K, K] (f32) of y = conv(x, W * scale; mode) given g = dL/dy."""
     lib.require_cuda(g, x)

@@ -329,6 +329,7 @@ class Trainer:
         # bf16 route: tap-major bf16 copies of the shared conv weights, re-packed once per optimiser step
         # (consulted only inside this trainer's own phases: tc.use_pack_cache)
         self._packs = tc.PackCache()
+        tc.clear_wgrad_workspaces()
         self._packs.register(p for _, p in self.g_flat.params + self.d_flat.params)
         self._ema_in_step = False  # set per phase by step(): the LAST generator update of an iteration carries the EMA
         # gradient exchange overlapped with backward (N > 1): bucketed all-reduces issued from autograd hooks
@@ -354,10 +355,13 @@ class Trainer:
 
     # ------------------------------------------------------------------ CUDA graphs
     def enable_graphs(self, flag=True):
-        """Replay each phase (D step, R1, G step, path regulariser) from captured CUDA graphs: forward +
-        backward in one graph, the optimiser update in a second one, the NCCL gradient all-reduce issued
-        between them.  Call after at least one eager iteration (lazy initialisation must be done)."""
+        """Replay each phase (D step, R1, G step, path regulariser) from captured CUDA graphs: forward + backward
+        (incl. the bucketed NCCL gradient exchange when N > 1) in one graph, the optimiser update in a second one.
+        Call after at least one eager iteration (lazy initialisation must be done)."""
         self.use_graphs = flag
+        if not flag:
+            self._graphs = {}   # captured graphs (and the buffers in their pools) go; a later enable re-captures
+        tc.clear_wgrad_workspaces()
 
     def _phase(self, name, fwdbwd, flat, optim, n_groups):
         with tc.use_pack_cache(self._packs):
