@@ -114,3 +114,66 @@ def test_models_match_the_reference_classes_on_the_gpu(ref_ops, size, batch):
             outs.append((img, lat, d(img)))
     for a, r in zip(*outs):
         assert (a - r).abs().max().item() < 1e-3
+
+
+def test_full_baseline_size_against_the_reference_classes(ref_ops):
+    """BASELINE configs[1] size (256^2, batch 16): forward, G-step gradients and D-step gradients of THIS repository's
+    modules against the reference's own classes (its CUDA ops + cuDNN in true fp32) on the same GPU with the same
+    weights and inputs.  fp32 parity mode (split-operand tensor-core convolutions): image / logits < 1e-3, gradients
+    within 5e-3 of the tensor's max; bf16 mode: image mean-abs error < 2 % of the image std."""
+    import model_spatial_query as M
+    import torch.nn.functional as F
+    from transeditor_b200 import model as te_model
+    ref = ref_gpu.load_reference_model()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    size, batch = 256, 16
+    sdg = O.synthetic_state(O.generator_shapes(size, 2))
+    sdd = O.synthetic_state(O.discriminator_shapes(size, 2))
+    z, p = _rand(batch, 512, 16, seed=21), _rand(batch, 512, 16, seed=22)
+    real = _rand(batch, 3, size, size, seed=23).clamp(-1, 1)
+    probe = ["convs.11.conv.weight", "convs.0.conv.weight", "conv1.conv.modulation.weight", "to_rgbs.5.conv.weight",
+             "interact.3.mlp.0.weight", "spatial_mapping_network.5.weight", "convs.11.activate.bias"]
+    dprobe = ["convs.0.0.weight", "convs.1.conv1.0.weight", "convs.6.skip.1.weight", "final_linear.0.weight", "convs.0.1.bias"]
+
+    def run(mod):
+        g = mod.Generator(size, 512, 512, 14, channel_multiplier=2, n_trans=8, pixel_norm_op_dim=1).to(DEV)
+        d = mod.Discriminator(size, channel_multiplier=2).to(DEV)
+        g.load_state_dict(sdg, strict=True)
+        d.load_state_dict(sdd, strict=True)
+        for q in d.parameters():
+            q.requires_grad_(False)
+        img, _, _ = g(z, p)
+        g_loss = F.softplus(-d(img)).mean()            # train_spatial_query.py:86-89
+        g_loss.backward()
+        gp = dict(g.named_parameters())
+        g_grads = {k: gp[k].grad.detach().clone() for k in probe}
+        for q in d.parameters():
+            q.requires_grad_(True)
+        fake = img.detach()
+        d_loss = F.softplus(-d(real)).mean() + F.softplus(d(fake)).mean()   # :69-73
+        d_loss.backward()
+        dp = dict(d.named_parameters())
+        d_grads = {k: dp[k].grad.detach().clone() for k in dprobe}
+        return img.detach(), float(g_loss), float(d_loss), g_grads, d_grads
+
+    te_model.set_precision("fp32")
+    try:
+        theirs = run(ref)
+        ours = run(M)
+        assert (ours[0] - theirs[0]).abs().max().item() < 1e-3
+        assert abs(ours[1] - theirs[1]) < 1e-3 and abs(ours[2] - theirs[2]) < 1e-3
+        for got, want in ((ours[3], theirs[3]), (ours[4], theirs[4])):
+            for k in want:
+                err = (got[k] - want[k]).abs().max().item() / max(want[k].abs().max().item(), 1e-20)
+                assert err < 5e-3, (k, err)
+        te_model.set_precision("bf16")
+        torch.backends.cuda.matmul.allow_tf32 = True
+        with torch.no_grad():
+            g = M.Generator(size, 512, 512, 14, channel_multiplier=2, n_trans=8, pixel_norm_op_dim=1).to(DEV).eval()
+            g.load_state_dict(sdg, strict=True)
+            img16 = g(z, p)[0].float()
+        assert (img16 - theirs[0]).abs().mean().item() < 0.02 * theirs[0].std().item()
+    finally:
+        te_model.set_precision("fp32")
+        torch.backends.cuda.matmul.allow_tf32 = False
