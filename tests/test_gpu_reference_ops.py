@@ -177,3 +177,52 @@ def test_full_baseline_size_against_the_reference_classes(ref_ops):
     finally:
         te_model.set_precision("fp32")
         torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def test_full_size_regularisers_against_the_reference_classes(ref_ops):
+    """The two double-backward phases at BASELINE size against the reference's classes on the same GPU (fp32 parity mode):
+    R1 penalty (train_spatial_query.py:76-83) at batch 16 and the path-length penalty (:92-105) at batch 8 — values and
+    probed parameter gradients."""
+    import model_spatial_query as M
+    from transeditor_b200 import model as te_model
+    ref = ref_gpu.load_reference_model()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    size = 256
+    sdg = O.synthetic_state(O.generator_shapes(size, 2))
+    sdd = O.synthetic_state(O.discriminator_shapes(size, 2))
+    real = _rand(16, 3, size, size, seed=31).clamp(-1, 1)
+    z, p = _rand(8, 512, 16, seed=32), _rand(8, 512, 16, seed=33)
+    noise = _rand(8, 3, size, size, seed=34) / size
+    dprobe = ["convs.0.0.weight", "convs.1.conv2.1.weight", "convs.3.conv1.0.weight", "final_conv.0.weight"]
+    gprobe = ["convs.10.conv.weight", "convs.2.conv.weight", "convs.5.conv.modulation.weight", "to_rgb1.conv.weight"]
+
+    def run(mod):
+        d = mod.Discriminator(size, channel_multiplier=2).to(DEV)
+        d.load_state_dict(sdd, strict=True)
+        r = real.clone().requires_grad_(True)
+        pred = d(r)
+        r1 = O.d_r1_penalty(pred, r)
+        (10 / 2 * r1 * 16 + 0 * pred[0]).backward()
+        dp = dict(d.named_parameters())
+        d_grads = {k: dp[k].grad.detach().clone() for k in dprobe}
+        del d, pred, r
+        g = mod.Generator(size, 512, 512, 14, channel_multiplier=2, n_trans=8, pixel_norm_op_dim=1).to(DEV)
+        g.load_state_dict(sdg, strict=True)
+        img, lat, _ = g(z, p, return_latents=True)
+        pl = O.g_path_lengths(img, lat, noise)
+        pen = (pl - pl.mean().detach() * 0.5).pow(2).mean()
+        (2 * 4 * pen + 0 * img[0, 0, 0, 0]).backward()
+        gp = dict(g.named_parameters())
+        g_grads = {k: gp[k].grad.detach().clone() for k in gprobe}
+        return float(r1), d_grads, pl.detach().clone(), g_grads
+
+    te_model.set_precision("fp32")
+    theirs = run(ref)
+    ours = run(M)
+    assert abs(ours[0] - theirs[0]) < 2e-3 * max(abs(theirs[0]), 1e-6)
+    assert (ours[2] - theirs[2]).abs().max().item() < 2e-3 * theirs[2].abs().max().item()
+    for got, want in ((ours[1], theirs[1]), (ours[3], theirs[3])):
+        for k in want:
+            err = (got[k] - want[k]).abs().max().item() / max(want[k].abs().max().item(), 1e-20)
+            assert err < 1e-2, (k, err)
