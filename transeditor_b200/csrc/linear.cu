@@ -4,7 +4,8 @@
 //
 // Shape of the problem: M = batch (1..64 rows), K, N up to 512 (8192 for D's first final linear): every weight is
 // used by M rows only, so the layers are bound by STREAMING THE WEIGHTS from HBM/L2 (arithmetic intensity M/2
-// FLOP/byte), not by math.  One warp owns one 8-column output tile and walks the whole reduction: its B operand is
+// FLOP/byte), not by math.  Four warps share one 8-column output tile, a quarter of the reduction each (enough 16-byte
+// loads in flight: 27 -> 13 us per launch, the 16.8 MB mapping launch at ~1.3 TB/s): the B operand is
 // read straight from global memory as 16-byte vectors (a lane's four k values of one weight row: every sector fully
 // used), the 16-row A tile sits in shared memory, products on mma.sync.m16n8k8 TF32 — 3 x TF32 (hi*hi + hi*lo + lo*hi,
 // ~1e-6 relative) in the fp32 parity mode, single-pass TF32 otherwise — with the k index permuted inside each 16-wide
@@ -16,7 +17,10 @@ namespace te {
 constexpr int LIN_MAX_TASKS = 32;
 constexpr int LIN_KC = 512;              // reduction chunk staged in shared memory
 constexpr int LIN_LDA = LIN_KC + 16;     // padded row: conflict-free float4 fragment reads
-constexpr int LIN_WARPS = 8;             // 8 output tiles of 8 columns = 64 columns per CTA
+constexpr int LIN_KS = 4;                // warps sharing one 8-column tile: each walks a quarter of the reduction
+constexpr int LIN_TILES = 4;             // 8-column tiles per CTA (32 output columns)
+constexpr int LIN_WARPS = LIN_KS * LIN_TILES;   // 16 warps: enough 16-byte weight loads in flight to stream from HBM
+constexpr int LIN_COLS = 8 * LIN_TILES;
 
 struct LinTaskDev {
   te_linear_task t;
@@ -59,11 +63,13 @@ __device__ __forceinline__ void lin_mma_step(float (&acc)[4], const float (&a)[4
 // y[m, n] = act( alpha * rnorm[m] * SUM_k x[m, k] * B(k, n) + bias[n] * bias_mul )
 //   w_trans == 0:  B(k, n) = w[n * w_ld + k]   (forward: the reduction runs along a weight row)
 //   w_trans == 1:  B(k, n) = w[k * w_ld + n]   (data gradient: the reduction runs down a weight column)
+// CTA = 16 warps = 4 column tiles x 4 reduction quarters; the quarters' partial fragments meet in shared memory.
 template <bool X3>
 __global__ void __launch_bounds__(LIN_WARPS * 32) linear_grouped_kernel(const __grid_constant__ LinParams P) {
   extern __shared__ float lin_smem[];
   float* As = lin_smem;                       // [16][LIN_LDA]
   float* rnorm = As + 16 * LIN_LDA;           // [16]
+  float* part = rnorm + 16;                   // [LIN_WARPS][32 lanes][4]
   int ti = 0;
   while (ti + 1 < P.n_tasks && int(blockIdx.x) >= P.task[ti + 1].first_block) ++ti;
   const LinTaskDev& T = P.task[ti];
@@ -73,8 +79,9 @@ __global__ void __launch_bounds__(LIN_WARPS * 32) linear_grouped_kernel(const __
   const int mg = item % T.m_groups;
   const int ks = item / T.m_groups;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tq = lane & 3;
+  const int tile = warp / LIN_KS, kq = warp % LIN_KS;
   const int m0 = mg * 16;
-  const int n0 = chunk * (8 * LIN_WARPS) + warp * 8;
+  const int n0 = chunk * LIN_COLS + tile * 8;
   // this CTA's share of the reduction (whole 16-slices)
   const int k16 = (t.k + 15) >> 4;
   const int per = (k16 + T.k_splits - 1) / T.k_splits;
@@ -82,20 +89,19 @@ __global__ void __launch_bounds__(LIN_WARPS * 32) linear_grouped_kernel(const __
   const bool vec_b = !t.w_trans && (t.w_ld & 3) == 0 && (t.k & 3) == 0 && (reinterpret_cast<uintptr_t>(t.w) & 15) == 0;
   const bool tile_live = n0 < t.n;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  float ssq = 0.f;  // pixel norm: this thread's share of SUM_k x^2 for row (threadIdx.x >> 4)
+  float ssq = 0.f;  // pixel norm: this thread's share of SUM_k x^2 for row `warp`
 
   for (int kc = kb; kc < ke; kc += LIN_KC) {
     const int klen = min(LIN_KC, ke - kc);
     const int kpad = (klen + 15) & ~15;
     __syncthreads();
-    // stage x[m0 .. m0+16, kc .. kc+klen) (zero rows / columns beyond the task's extent); 16 threads per row
+    // stage x[m0 .. m0+16, kc .. kc+klen) (zero rows / columns beyond the task's extent): one warp per row
     {
-      const int r = threadIdx.x >> 4, c = threadIdx.x & 15;
-      const bool row_ok = m0 + r < t.m;
-      const float* src = t.x + int64_t(m0 + r) * t.x_rs;
-      for (int k = c; k < kpad; k += 16) {
+      const bool row_ok = m0 + warp < t.m;
+      const float* src = t.x + int64_t(m0 + warp) * t.x_rs;
+      for (int k = lane; k < kpad; k += 32) {
         const float v = (row_ok && k < klen) ? __ldg(src + int64_t(kc + k) * t.x_cs) : 0.f;
-        As[r * LIN_LDA + k] = v;
+        As[warp * LIN_LDA + k] = v;
         ssq += v * v;
       }
     }
@@ -105,8 +111,11 @@ __global__ void __launch_bounds__(LIN_WARPS * 32) linear_grouped_kernel(const __
       const float* a1p = As + (g + 8) * LIN_LDA + 4 * tq;
       const int n = n0 + g;
       const bool col_ok = n < t.n;
-#pragma unroll 4
-      for (int s = 0; s < kpad; s += 16) {
+      // this warp's quarter of the chunk's 16-wide slices
+      const int nsl = kpad >> 4, qsl = (nsl + LIN_KS - 1) / LIN_KS;
+      const int s_lo = kq * qsl * 16, s_hi = min(kpad, (kq + 1) * qsl * 16);
+#pragma unroll 8
+      for (int s = s_lo; s < s_hi; s += 16) {
         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (col_ok) {
           const int k = kc + s + 4 * tq;
@@ -138,19 +147,25 @@ __global__ void __launch_bounds__(LIN_WARPS * 32) linear_grouped_kernel(const __
       }
     }
   }
-  if (t.pixel_norm) {
-    // rows are owned by 16 consecutive threads: reduce the squares inside each half warp
+  if (t.pixel_norm) {   // row `warp` was staged by this warp: reduce its squares across the lanes
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) ssq += __shfl_xor_sync(0xffffffffu, ssq, o);
-    if ((threadIdx.x & 15) == 0) {
+    for (int o = 16; o > 0; o >>= 1) ssq += __shfl_xor_sync(0xffffffffu, ssq, o);
+    if (lane == 0) {
       const float rn = rsqrtf(ssq / float(t.k) + 1e-8f);
-      rnorm[threadIdx.x >> 4] = rn;
-      const int m = m0 + (threadIdx.x >> 4);
+      rnorm[warp] = rn;
+      const int m = m0 + warp;
       if (t.rnorm_out && chunk == 0 && m < t.m) t.rnorm_out[m] = rn;
     }
-    __syncthreads();
   }
-  if (!tile_live) return;
+  // the reduction quarters of a tile meet in shared memory
+  *reinterpret_cast<float4*>(part + (warp * 32 + lane) * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  __syncthreads();
+  if (!tile_live || kq != 0) return;
+#pragma unroll
+  for (int q = 1; q < LIN_KS; ++q) {
+    const float4 o = *reinterpret_cast<const float4*>(part + ((warp + q) * 32 + lane) * 4);
+    acc[0] += o.x; acc[1] += o.y; acc[2] += o.z; acc[3] += o.w;
+  }
   // accumulator fragment: acc[0], acc[1] = row g, columns 2tq, 2tq+1; acc[2], acc[3] = row g+8
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
@@ -249,7 +264,7 @@ extern "C" int te_linear_grouped(const te_linear_task* tasks, int n_tasks, int p
   TE_CHECK_ARG(n_tasks >= 0 && (tasks != nullptr || n_tasks == 0), "linear_grouped: null task table");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   static bool configured = false;
-  const int smem = (16 * LIN_LDA + 16) * 4;
+  const int smem = (16 * LIN_LDA + 16 + LIN_WARPS * 32 * 4) * 4;
   if (!configured) {
     TE_CHECK_CUDA(cudaFuncSetAttribute(linear_grouped_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     TE_CHECK_CUDA(cudaFuncSetAttribute(linear_grouped_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -273,7 +288,7 @@ extern "C" int te_linear_grouped(const te_linear_task* tasks, int n_tasks, int p
       LinTaskDev& d = P.task[P.n_tasks++];
       d.t = t;
       d.first_block = blocks;
-      d.n_chunks = (t.n + 8 * LIN_WARPS - 1) / (8 * LIN_WARPS);
+      d.n_chunks = (t.n + LIN_COLS - 1) / LIN_COLS;
       d.m_groups = (t.m + 15) / 16;
       d.k_splits = t.k_splits;
       blocks += d.n_chunks * d.m_groups * d.k_splits;
