@@ -350,6 +350,7 @@ def image_quantize(dst_hwc, src, low, high):
 
 def install(monkeypatch):
     monkeypatch.setattr(lib, "require_cuda", lambda *a: None)
+    monkeypatch.setattr(lib, "emulated", True)
     for name in ("fused_bias_act", "fused_bias_act_bwd", "upfirdn2d", "conv2d_simt",
                  "conv2d_wgrad_simt", "attn_core", "adam_ema", "adam_ema_devstep", "scale_bc", "dot_bc",
                  "attn_stack_fwd", "attn_stack_bwd", "pack_weights_tc", "conv_tc", "conv_wgrad_tc", "split_bf16",

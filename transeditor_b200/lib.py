@@ -114,6 +114,7 @@ _SIGNATURES = {
 }
 
 _lib = None
+emulated = False   # set by the CPU test-suite's emulation fixture only (tests/emu.py); the product never sets it
 launch_count = 0  # number of te_* kernel launches issued through this binding (bench.py reads it)
 
 

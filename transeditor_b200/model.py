@@ -56,9 +56,9 @@ _SMALL_M = 64   # EqualLinear: up to this many rows go through the grouped weigh
 
 
 def lib_emulated():
-    """True only inside the CPU test-suite's `cpu_emulation` fixture (tests/emu.py replaces lib.require_cuda)."""
+    """True only inside the CPU test-suite's `cpu_emulation` fixture (tests/emu.py sets lib.emulated)."""
     from . import lib
-    return getattr(lib.require_cuda, "__name__", "") == "<lambda>"
+    return lib.emulated
 
 
 def _tc(x):
