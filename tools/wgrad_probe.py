@@ -33,7 +33,8 @@ def main():
     print("TE_WG_N=%s" % os.environ.get("TE_WG_N", "auto"))
     g = torch.Generator().manual_seed(0)
     cases = [(16, 512, 512, 64, False), (16, 256, 256, 128, False), (16, 128, 128, 256, False), (16, 512, 512, 32, False),
-             (8, 256, 256, 128, True), (16, 256, 512, 64, False), (16, 512, 512, 16, False), (2, 256, 128, 24, False)]
+             (8, 256, 256, 128, True), (16, 256, 256, 128, True), (16, 128, 128, 256, True), (8, 128, 128, 256, True),
+             (16, 256, 512, 64, False), (16, 512, 512, 16, False), (2, 256, 128, 24, False)]
     for b, cin, cout, h, ps in cases:
         x = torch.randn(b, cin, h, h, generator=g).cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
         gy = torch.randn(b, cout, h, h, generator=g).cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)

@@ -282,10 +282,25 @@ extern "C" int te_conv_wgrad_tc(float* gw, const void* g, const void* x, const t
     p.tiles_per_sample = p.tiles_w * p.tiles_h;
     // one CTA per SM (196 KB of shared memory): keep the grid within ONE wave — 150 CTAs on 148 SMs would
     // run two waves and double the kernel time — so round the split count DOWN
-    int sps = kNumSMs / (out_tiles * tap_groups * d.batch);
-    int max_sps = (p.tiles_per_sample + 7) / 8;
-    if (sps > max_sps) sps = max_sps;
-    if (sps < 1) sps = 1;
+    // one CTA per SM (shared memory): pick the per-sample split count with the best WAVE efficiency
+    // items / (ceil(items / 148) * 148) — batch 16 x 4 tiles x 3 tap groups = 192 CTAs unsplit is 1.3 waves, the second
+    // a third full (0.65); 3 splits make 576 = 3.9 waves (0.97).  Fewer splits on near-ties: each is an atomic pass.
+    const int max_sps = (p.tiles_per_sample + 7) / 8;
+    const int base = out_tiles * tap_groups * d.batch;
+    int sps = 1;
+    double best = 0.0;
+    static int wave_split = -1;   // TE_WG_WAVE_SPLIT=0: the former rule (one wave, rounded down)
+    if (wave_split < 0) { const char* e = getenv("TE_WG_WAVE_SPLIT"); wave_split = e ? atoi(e) : 1; }
+    if (!wave_split) {
+      sps = kNumSMs / base;
+      if (sps > max_sps) sps = max_sps;
+      if (sps < 1) sps = 1;
+    }
+    for (int c = 1; wave_split && c <= 12 && c <= max_sps; ++c) {
+      const int items = base * c;
+      const double eff = double(items) / double(((items + kNumSMs - 1) / kNumSMs) * kNumSMs);
+      if (eff > best + 0.03) { best = eff; sps = c; }
+    }
     p.tiles_per_split = (p.tiles_per_sample + sps - 1) / sps;
     sps = (p.tiles_per_sample + p.tiles_per_split - 1) / p.tiles_per_split;
     p.splits_per_sample = sps;
