@@ -391,6 +391,19 @@ int te_from_rgb_bwd(float* gw, float* gbias, float* gx, const void* g, const voi
                     const float* w, int batch, int h, int wd, int cout, float wscale, float slope, float gain,
                     int dtype, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Blur followed by bias + leaky ReLU in one pass: the tail of an UPSAMPLING StyledConv,
+ *   out = self.blur(conv_transpose2d(...)) (model_spatial_query.py:318-322) ... self.activate(out) (:398-400),
+ * i.e. upfirdn2d(x, fir, up=1, down=1, pad) then fused_leaky_relu(., bias, slope, gain):
+ *   out[n, y, x, c] = leaky_relu(SUM_k fir-taps * x + bias[c], slope) * gain
+ * Channels-last tensors only ([major, H, W, minor], minor % (128 / sizeof(T)) == 0), FIR up to 4 x 4; bias FLOAT32
+ * [minor].  Returns TE_ERR_UNSUPPORTED when the geometry is not the TMA-staged kernel's (the caller then runs
+ * te_upfirdn2d and te_fused_bias_act).
+ */
+int te_upfirdn2d_bias_act(void* out, const void* x, const float* fir, const float* bias, int64_t major, int in_h,
+                          int in_w, int minor, int kh, int kw, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
+                          float slope, float gain, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -331,6 +331,10 @@ def wgrad_unpack(out, ws, batch, o_dim, i_dim, taps, rows, ld, trans, clear=Fals
         (w[:, :, :i_dim, :o_dim] if trans else w[:, :, :o_dim, :i_dim]).zero_()
 
 
+def upfirdn2d_bias_act(out, x, fir, bias, major, in_h, in_w, minor, px0, px1, py0, py1, slope, gain):
+    return False   # the emulation always takes the two-call route (upfirdn2d, then fused_bias_act)
+
+
 def image_prep(dst_nchw, dst_nhwc8, src_hwc, flip, batch, h, w):
     x = src_hwc
     if flip is not None:
@@ -355,5 +359,5 @@ def install(monkeypatch):
                  "conv2d_wgrad_simt", "attn_core", "adam_ema", "adam_ema_devstep", "scale_bc", "dot_bc",
                  "attn_stack_fwd", "attn_stack_bwd", "pack_weights_tc", "conv_tc", "conv_wgrad_tc", "split_bf16",
                  "image_prep", "image_quantize", "linear_grouped", "linear_wgrad_grouped", "from_rgb_fwd",
-                 "from_rgb_bwd", "wgrad_unpack"):
+                 "from_rgb_bwd", "wgrad_unpack", "upfirdn2d_bias_act"):
         monkeypatch.setattr(lib, name, globals()[name])

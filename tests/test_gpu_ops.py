@@ -430,3 +430,45 @@ def test_adam_ema_matches_torch_adam():
         ema_ref.mul_(0.998).add_(q.detach(), alpha=0.002)
     assert (p - q.detach()).abs().max().item() < 5e-6
     assert (ema - ema_ref).abs().max().item() < 5e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("shape,pad", [((4, 128, 129, 129), (1, 1)), ((2, 64, 66, 40), (2, 2)), ((16, 128, 257, 257), (1, 1)),
+                                       ((2, 24, 33, 33), (1, 1))])
+def test_blur_bias_act_matches_the_two_step_form(dtype, shape, pad):
+    """op.blur_bias_act (te_upfirdn2d_bias_act, or the two-launch route for geometries the fused kernel does not cover)
+    == fused_leaky_relu(upfirdn2d(x)) of the existing operators; gradients and double backward included."""
+    from transeditor_b200 import op
+    g = torch.Generator().manual_seed(3)
+    n, c, h, w = shape
+    k = torch.tensor([1., 3., 3., 1.])
+    fir = (k[None] * k[:, None] / 16).cuda()
+
+    def make():
+        x = torch.randn(n, c, h, w, generator=torch.Generator().manual_seed(1)).cuda().to(dtype)
+        x = x.contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        b = (torch.randn(c, generator=torch.Generator().manual_seed(2)) * 0.5).cuda().requires_grad_(True)
+        return x, b
+    x1, b1 = make()
+    y1 = op.blur_bias_act(x1, fir, pad, b1)
+    x2, b2 = make()
+    y2 = op.fused_leaky_relu(op.upfirdn2d(x2, fir, pad=pad), b2)
+    tol = 2e-2 if dtype == torch.bfloat16 else 1e-5
+    assert y1.shape == y2.shape and y1.dtype == dtype
+    assert (y1.float() - y2.float()).abs().max().item() <= tol * max(1.0, y2.float().abs().max().item())
+    gy = torch.randn(y2.shape, generator=g).cuda().to(dtype)
+    (gx1, gb1) = torch.autograd.grad(y1, (x1, b1), gy, create_graph=True)
+    (gx2, gb2) = torch.autograd.grad(y2, (x2, b2), gy, create_graph=True)
+    if dtype == torch.float32:
+        assert (gx1 - gx2).abs().max().item() <= tol * max(1.0, gx2.abs().max().item())
+        assert (gb1 - gb2).abs().max().item() <= 1e-3 * max(1.0, gb2.abs().max().item())
+    else:
+        # the two forms round the pre-activation differently, so the leaky-ReLU mask of a few near-zero elements flips
+        cos = torch.nn.functional.cosine_similarity(gx1.float().flatten(), gx2.float().flatten(), dim=0).item()
+        assert cos > 0.999
+        assert (gb1.float() - gb2.float()).abs().max().item() <= 5e-2 * max(1.0, gb2.float().abs().max().item())
+    if dtype == torch.float32 and n * c * h * w < 4_000_000:
+        (gg1,) = torch.autograd.grad(gx1.square().sum(), x1, allow_unused=True)
+        (gg2,) = torch.autograd.grad(gx2.square().sum(), x2, allow_unused=True)
+        assert (gg1 is None) == (gg2 is None)

@@ -757,6 +757,10 @@ struct FirTmaTiling {
   int box_w, box_h;    // tw + 3, th + 3
   int tiles_x, tiles_y, chunks;
   int64_t jobs;
+  // optional epilogue (te_upfirdn2d_bias_act): out = leaky_relu(fir(x) + bias[c], slope) * gain
+  const float* bias;
+  float slope, gain;
+  int act;
 };
 constexpr int FIR_TMA_STAGES = 2;
 constexpr int FIR_TMA_MAX_THREADS = 256;  // x 2 CTAs per SM -> 128 registers per thread, no spills
@@ -895,6 +899,22 @@ fir_nhwc_tma_kernel(T* __restrict__ out, const __grid_constant__ CUtensorMap in_
                 }
             }
         }
+        if (t.act) {
+          // fused bias + leaky ReLU of the layer that follows the blur (StyledConv's upsampling branch)
+          const float* bp = t.bias + chunk * Pack16<T>::CHUNK + q8 * Pack16<T>::ELEMS;
+          float2 bq[Pack16<T>::NQ];
+#pragma unroll
+          for (int q = 0; q < Pack16<T>::NQ; ++q) bq[q] = make_float2(__ldg(bp + 2 * q), __ldg(bp + 2 * q + 1));
+#pragma unroll
+          for (int a = 0; a < F2_TY; ++a)
+#pragma unroll
+            for (int w = 0; w < F2_XW; ++w)
+#pragma unroll
+              for (int q = 0; q < Pack16<T>::NQ; ++q) {
+                const float u0 = acc[a][w][q].x + bq[q].x, u1 = acc[a][w][q].y + bq[q].y;
+                acc[a][w][q] = make_float2(fmaxf(u0, t.slope * u0) * t.gain, fmaxf(u1, t.slope * u1) * t.gain);
+              }
+        }
 #pragma unroll
         for (int a = 0; a < F2_TY; ++a) {
           if (oy0 + a >= p.out_h) break;
@@ -914,10 +934,12 @@ fir_nhwc_tma_kernel(T* __restrict__ out, const __grid_constant__ CUtensorMap in_
 
 template <typename T>
 static int launch_fir_nhwc_tma(T* out, const T* in, const float* fir, const UpfirdnParams& p, cudaStream_t st,
-                               int* status) {
+                               int* status, const float* bias = nullptr, float slope = 1.f, float gain = 1.f,
+                               int act = 0) {
   *status = TE_OK;
   if constexpr (IsTmaFir<T>::value) {
     FirTmaTiling t;
+    t.bias = bias; t.slope = slope; t.gain = gain; t.act = act;
     const int nx = (p.out_w + 31) / 32;
     t.tw = (((p.out_w + nx - 1) / nx) + 1) & ~1;
     t.xpairs = t.tw / 2;
@@ -1261,4 +1283,51 @@ extern "C" int te_upfirdn2d(void* out, const void* in, const float* fir, int64_t
   }
   set_error("upfirdn2d: unknown dtype %d", dtype);
   return TE_ERR_INVALID;
+}
+
+template <typename T>
+static int upfirdn2d_bias_act_typed(void* out_, const void* in_, const float* fir, const float* bias, float slope,
+                                    float gain, const te::UpfirdnParams& p, cudaStream_t st) {
+  using namespace te;
+  T* out = static_cast<T*>(out_);
+  const T* in = static_cast<const T*>(in_);
+  constexpr int NVEC = 16 / sizeof(T);
+  const int64_t total = p.major * p.out_h * int64_t(p.out_w) * p.minor;
+  const bool ok = p.minor % NVEC == 0 && p.kh <= 4 && p.kw <= 4 && p.minor % (128 / int(sizeof(T))) == 0 &&
+                  total >= (int64_t(1) << 20) && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+  int status = TE_OK;
+  if (ok && launch_fir_nhwc_tma<T>(out, in, fir, p, st, &status, bias, slope, gain, 1)) {
+    if (status != TE_OK) return status;
+    TE_CHECK_LAUNCH();
+    return TE_OK;
+  }
+  set_error("upfirdn2d_bias_act: geometry not covered by the TMA-staged channels-last kernel");
+  return TE_ERR_UNSUPPORTED;
+}
+
+extern "C" int te_upfirdn2d_bias_act(void* out, const void* in, const float* fir, const float* bias, int64_t major,
+                                     int in_h, int in_w, int minor, int kh, int kw, int pad_x0, int pad_x1, int pad_y0,
+                                     int pad_y1, float slope, float gain, int dtype, void* stream) {
+  using namespace te;
+  if (major == 0) return TE_OK;
+  TE_CHECK_ARG(out && in && fir && bias, "upfirdn2d_bias_act: null pointer");
+  TE_CHECK_ARG(major >= 0 && in_h > 0 && in_w > 0 && minor > 1, "upfirdn2d_bias_act: channels-last input expected");
+  TE_CHECK_ARG(kh >= 1 && kw >= 1 && kh <= 4 && kw <= 4, "upfirdn2d_bias_act: FIR of up to 4 x 4 taps");
+  TE_CHECK_ARG(gain > 0.f && slope >= 0.f && slope <= 1.f, "upfirdn2d_bias_act: gain > 0 and 0 <= slope <= 1");
+  UpfirdnParams p;
+  p.major = major; p.in_h = in_h; p.in_w = in_w; p.minor = minor; p.kh = kh; p.kw = kw;
+  p.up_x = p.up_y = p.down_x = p.down_y = 1;
+  p.pad_x0 = pad_x0; p.pad_y0 = pad_y0;
+  p.out_h = in_h + pad_y0 + pad_y1 - kh + 1;
+  p.out_w = in_w + pad_x0 + pad_x1 - kw + 1;
+  TE_CHECK_ARG(p.out_h > 0 && p.out_w > 0, "upfirdn2d_bias_act: empty output");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (dtype) {
+    case TE_BF16: return upfirdn2d_bias_act_typed<__nv_bfloat16>(out, in, fir, bias, slope, gain, p, st);
+    case TE_F16: return upfirdn2d_bias_act_typed<__half>(out, in, fir, bias, slope, gain, p, st);
+    case TE_F32: return upfirdn2d_bias_act_typed<float>(out, in, fir, bias, slope, gain, p, st);
+  }
+  set_error("upfirdn2d_bias_act: dtype must be bf16, f16 or f32");
+  return TE_ERR_UNSUPPORTED;
 }

@@ -86,6 +86,7 @@ _SIGNATURES = {
     "te_fused_bias_act": ([_P, _P, _P, _P, _I, _I, _F, _F, _L, _L, _L, _I, _P], _I),
     "te_fused_bias_act_bwd": ([_P, _P, _P, _P, _F, _F, _L, _L, _L, _I, _P], _I),
     "te_upfirdn2d": ([_P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P], _I),
+    "te_upfirdn2d_bias_act": ([_P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _I, _P], _I),
     "te_conv2d_simt": ([_P, _P, _P, _P, _P, _P, _P, _P, ctypes.POINTER(ConvGeom), _I, _P], _I),
     "te_conv2d_wgrad_simt": ([_P, _P, _P, _P, _P, ctypes.POINTER(ConvGeom), _I, _P], _I),
     "te_adam_ema": ([_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _F, _P], _I),
@@ -431,3 +432,18 @@ def wgrad_unpack(out, ws, batch, o_dim, i_dim, taps, rows, ld, trans, clear=Fals
     _check(load().te_wgrad_unpack(ptr(out), ptr(ws), batch, o_dim, i_dim, taps, rows, ld, int(trans), int(clear),
                                   stream()), "wgrad_unpack")
     _count()
+
+
+TE_ERR_UNSUPPORTED = -2
+
+
+def upfirdn2d_bias_act(out, x, fir, bias, major, in_h, in_w, minor, px0, px1, py0, py1, slope, gain):
+    """Returns False (nothing launched) when the geometry is not covered by the fused kernel."""
+    kh, kw = fir.shape
+    rc = load().te_upfirdn2d_bias_act(ptr(out), ptr(x), ptr(fir), ptr(bias), major, in_h, in_w, minor, kh, kw, px0, px1,
+                                      py0, py1, slope, gain, dtype_code(x), stream())
+    if rc == TE_ERR_UNSUPPORTED:
+        return False
+    _check(rc, "upfirdn2d_bias_act")
+    _count()
+    return True

@@ -453,7 +453,11 @@ def _modconv_forward_tc(self, x, ops, bias, noise, noise_weight, activate, fused
     cout = self.out_channel
     if wb is not None:
         if self.upsample:
-            v = self.blur(tc.conv_transpose2d(x, wb, wscale=wscale))
+            v = tc.conv_transpose2d(x, wb, wscale=wscale)
+            if activate and noise is None and bias is not None and wn.shape[0] == cout:
+                # blur -> bias -> leaky ReLU in ONE pass over the activation (op.BlurBiasAct)
+                return op.blur_bias_act(v, self.blur.kernel, self.blur.pad, bias.reshape(-1))
+            v = self.blur(v)
         elif fused_ok and noise is None:
             pb = None if bias is None else F.pad(bias.reshape(-1), (0, wn.shape[0] - cout))
             v = tc.conv_raw(x, tc.pack_weight(wb, False, wscale, tc.nseg_for(x)), tc.Mode("s1", k), bias=pb,

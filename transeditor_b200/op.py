@@ -224,6 +224,52 @@ class UpFirDn2d(Function):
         return grad_input, None, None, None, None
 
 
+class BlurBiasAct(Function):
+    """fused_leaky_relu(upfirdn2d(x, kernel, pad=pad), bias, slope, gain) for channels-last activations in ONE pass
+    (te_upfirdn2d_bias_act: the blur's output never round-trips through HBM before the activation); two launches when
+    the geometry is not the fused kernel's.  Backward is the composition of the differentiable pieces — the masked
+    gradient from FusedLeakyReLUFunctionBackward (sign of the saved OUTPUT), then the blur's adjoint — so second order
+    works exactly as for the unfused ops."""
+
+    @staticmethod
+    def forward(ctx, x, kernel, pad, bias, negative_slope, scale):
+        lib.require_cuda(x, kernel, bias)
+        px0, px1, py0, py1 = pad
+        kh, kw = kernel.shape
+        xc, cl = _canonical(x)
+        n, c, h, w = xc.shape
+        out = None
+        if cl and 0 <= negative_slope <= 1 and scale > 0:
+            oh, ow = h + py0 + py1 - kh + 1, w + px0 + px1 - kw + 1
+            out = torch.empty((n, c, oh, ow), dtype=xc.dtype, device=xc.device, memory_format=torch.channels_last)
+            if not lib.upfirdn2d_bias_act(out, xc, _fir_f32(kernel), bias.detach().float().contiguous(), n, h, w, c, px0,
+                                          px1, py0, py1, float(negative_slope), float(scale)):
+                out = None
+        if out is None:
+            out = _bias_act(_upfirdn2d_native(xc, kernel, (1, 1), (1, 1), pad), bias, None, 3, 0, negative_slope, scale)
+        ctx.save_for_backward(kernel, torch.flip(kernel, [0, 1]), out)
+        ctx.in_size, ctx.out_size, ctx.pad = tuple(x.shape), (out.shape[2], out.shape[3]), pad
+        ctx.g_pad = (kw - px0 - 1, w - out.shape[3] + px0, kh - py0 - 1, h - out.shape[2] + py0)
+        ctx.negative_slope, ctx.scale, ctx.bias_dtype = negative_slope, scale, bias.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        kernel, grad_kernel, out = ctx.saved_tensors
+        g_v, g_b = FusedLeakyReLUFunctionBackward.apply(grad_output, out, True, ctx.negative_slope, ctx.scale,
+                                                        ctx.bias_dtype)
+        g_x = None
+        if ctx.needs_input_grad[0]:
+            g_x = UpFirDn2dBackward.apply(g_v, kernel, grad_kernel, (1, 1), (1, 1), ctx.pad, ctx.g_pad, ctx.in_size,
+                                          ctx.out_size)
+        return g_x, None, None, (g_b if ctx.needs_input_grad[3] else None), None, None
+
+
+def blur_bias_act(input, kernel, pad, bias, negative_slope=0.2, scale=2 ** 0.5):
+    """upfirdn2d(input, kernel, pad=pad) + bias -> leaky ReLU * scale, fused (same pad on both axes)."""
+    return BlurBiasAct.apply(input, kernel, (pad[0], pad[1], pad[0], pad[1]), bias, negative_slope, scale)
+
+
 def upfirdn2d(input, kernel, up=1, down=1, pad=(0, 0)):
     """utils/op/upfirdn2d.py:143-148 — same pad on both axes."""
     return UpFirDn2d.apply(input, kernel, (up, up), (down, down), (pad[0], pad[1], pad[0], pad[1]))
