@@ -480,6 +480,17 @@ def _modconv_forward_tc(self, x, ops, bias, noise, noise_weight, activate, fused
             v = tc.conv_raw(op.scale_bc(x, s), wp, tc.Mode("s1", k), out_scale=d, bias=pb, act=activate)
         return v if wn.shape[0] == cout else v[:, :cout]
     u = op.scale_bc(x, s)
+    if d is not None and wn.shape[0] == cout and os.environ.get("TE_CONV_SCALED", "1") != "0":
+        # demodulation in the convolution epilogue (tc.TcConvScaled; d commutes with the blur: both are per-channel
+        # linear), and for the upsampling layers blur + bias + leaky ReLU in one pass behind it
+        if self.upsample:
+            v = tc.conv_transpose2d_scaled(u, wn, d, wscale=wscale)
+            if activate and noise is None and bias is not None:
+                return op.blur_bias_act(v, self.blur.kernel, self.blur.pad, bias.reshape(-1))
+            v = self.blur(v)
+        else:
+            v = tc.conv2d_scaled(u, wn, d, wscale=wscale)
+        return _epilogue(v, bias, noise, noise_weight, activate)
     if self.upsample:
         v = self.blur(tc.conv_transpose2d(u, wn, wscale=wscale))
     else:

@@ -523,6 +523,39 @@ class TcConvBiasActCarry(Function):
         return gx, gw, (g_b if ctx.needs_input_grad[2] else None), None, None, None
 
 
+class TcConvScaled(Function):
+    """y = d[b, cout] * conv(x, W * wscale; mode): the demodulation coefficient of ModulatedConv2d
+    (model_spatial_query.py:301-304) applied in the convolution kernel's epilogue instead of a pass of its own over
+    the activation.  Backward is a composition of differentiable pieces — g_c = g_y * d (ScaleBC), g_d = sum_pixels
+    (g_y * y) / d (DotBC on the saved OUTPUT: y = d * c, and d = rsqrt(.) > 0), then the usual data / weight gradient
+    kernels — so second order works like for the unfused ops."""
+
+    @staticmethod
+    def forward(ctx, x, w, d, mode, wscale=1.0):
+        y = conv_raw(x, pack_weight(w, mode.transposed, wscale, nseg_for(x)), mode, out_scale=d)
+        ctx.save_for_backward(x, w, d, y)
+        ctx.mode, ctx.wscale = mode, wscale
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        from .op import DotBC, ScaleBC
+        x, w, d, y = ctx.saved_tensors
+        mode, wscale = ctx.mode, ctx.wscale
+        gx = gw = gd = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            g_c = ScaleBC.apply(gy, d)
+            if ctx.needs_input_grad[0]:
+                gx = TcConv.apply(g_c, w, mode.adjoint((x.shape[2], x.shape[3])), wscale)
+                if gx.shape[1] != x.shape[1]:
+                    gx = gx[:, :x.shape[1]]
+            if ctx.needs_input_grad[1]:
+                gw = TcWeightGrad.apply(x, g_c, mode, tuple(w.shape), wscale)
+        if ctx.needs_input_grad[2]:
+            gd = (DotBC.apply(gy, y) / d.to(torch.float32)).to(d.dtype)
+        return gx, gw, gd, None, None
+
+
 class TcConvResidual(Function):
     """y = conv(x, W * wscale; mode) + residual with the sum taken in the convolution epilogue (the ResBlock
     skip connection, model_spatial_query.py:795-797): no separate pass over the two activations."""
@@ -574,6 +607,17 @@ def conv2d(x, w, stride=1, wscale=1.0):
     """F.conv2d(x, w * wscale, stride, padding = k//2 if stride == 1 else 0) in bf16 on tensor cores.
     w [O, I, K, K], or [B, O, I, K, K] for per-sample weights (the reference's groups=batch form)."""
     return TcConv.apply(x, w, _fwd_mode(w, stride), wscale)
+
+
+def conv2d_scaled(x, w, d, stride=1, wscale=1.0):
+    """d[b, cout] * conv2d(x, w * wscale): per-(sample, output channel) scale in the convolution epilogue."""
+    return TcConvScaled.apply(x, w, d, _fwd_mode(w, stride), wscale)
+
+
+def conv_transpose2d_scaled(x, w_oi, d, stride=2, wscale=1.0):
+    """d[b, cout] * conv_transpose2d(x, (w_oi * wscale)^T, stride 2): the same for the polyphase transposed conv."""
+    assert stride == 2
+    return TcConvScaled.apply(x, w_oi, d, Mode("up", w_oi.shape[-1]), wscale)
 
 
 def conv_transpose2d(x, w_oi, stride=2, wscale=1.0):
