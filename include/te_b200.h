@@ -404,6 +404,15 @@ int te_upfirdn2d_bias_act(void* out, const void* x, const float* fir, const floa
                           int in_w, int minor, int kh, int kw, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
                           float slope, float gain, int dtype, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Weight-only factor of ModulatedConv2d's demodulation (model_spatial_query.py:301-303 with the style factored out:
+ * demod[b,o] = rsqrt(SUM_i style[b,i]^2 * energy[o,i] + eps)) and its gradient, f32:
+ *   te_weight_energy:      energy[r] = coef * SUM_t w[r*taps + t]^2     r over the O*I rows of the [O,I,k,k] weight
+ *   te_weight_energy_bwd:  gw[r*taps + t] = w[r*taps + t] * g[r] * coef2
+ */
+int te_weight_energy(float* energy, const float* w, int64_t rows, int taps, float coef, void* stream);
+int te_weight_energy_bwd(float* gw, const float* w, const float* g, int64_t rows, int taps, float coef2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

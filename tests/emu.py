@@ -335,6 +335,14 @@ def upfirdn2d_bias_act(out, x, fir, bias, major, in_h, in_w, minor, px0, px1, py
     return False   # the emulation always takes the two-call route (upfirdn2d, then fused_bias_act)
 
 
+def weight_energy(energy, w, rows, taps, coef):
+    energy.copy_((w.reshape(rows, taps).double().square().sum(1) * coef).reshape(energy.shape).float())
+
+
+def weight_energy_bwd(gw, w, g, rows, taps, coef2):
+    gw.copy_((w.reshape(rows, taps).double() * g.reshape(rows, 1).double() * coef2).reshape(gw.shape).float())
+
+
 def image_prep(dst_nchw, dst_nhwc8, src_hwc, flip, batch, h, w):
     x = src_hwc
     if flip is not None:
@@ -359,5 +367,6 @@ def install(monkeypatch):
                  "conv2d_wgrad_simt", "attn_core", "adam_ema", "adam_ema_devstep", "scale_bc", "dot_bc",
                  "attn_stack_fwd", "attn_stack_bwd", "pack_weights_tc", "conv_tc", "conv_wgrad_tc", "split_bf16",
                  "image_prep", "image_quantize", "linear_grouped", "linear_wgrad_grouped", "from_rgb_fwd",
-                 "from_rgb_bwd", "wgrad_unpack", "upfirdn2d_bias_act"):
+                 "from_rgb_bwd", "wgrad_unpack", "upfirdn2d_bias_act", "weight_energy",
+                 "weight_energy_bwd"):
         monkeypatch.setattr(lib, name, globals()[name])

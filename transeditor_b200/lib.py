@@ -94,6 +94,8 @@ _SIGNATURES = {
     "te_conv_tc": ([_P, _P, _P, _P, _P, ctypes.POINTER(TcConvDesc), _P], _I),
     "te_conv_wgrad_tc": ([_P, _P, _P, ctypes.POINTER(TcConvDesc), _P], _I),
     "te_wgrad_unpack": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P], _I),
+    "te_weight_energy": ([_P, _P, _L, _I, _F, _P], _I),
+    "te_weight_energy_bwd": ([_P, _P, _P, _L, _I, _F, _P], _I),
     "te_scale_bc": ([_P, _P, _P, _L, _L, _I, _I, _P], _I),
     "te_dot_bc": ([_P, _P, _P, _L, _L, _I, _I, _P], _I),
     "te_split_bf16": ([_P, _P, _P, _L, _L, _I, _I, _P], _I),
@@ -447,3 +449,13 @@ def upfirdn2d_bias_act(out, x, fir, bias, major, in_h, in_w, minor, px0, px1, py
     _check(rc, "upfirdn2d_bias_act")
     _count()
     return True
+
+
+def weight_energy(energy, w, rows, taps, coef):
+    _check(load().te_weight_energy(ptr(energy), ptr(w), rows, taps, coef, stream()), "weight_energy")
+    _count()
+
+
+def weight_energy_bwd(gw, w, g, rows, taps, coef2):
+    _check(load().te_weight_energy_bwd(ptr(gw), ptr(w), ptr(g), rows, taps, coef2, stream()), "weight_energy_bwd")
+    _count()

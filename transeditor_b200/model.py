@@ -294,13 +294,27 @@ class WeightEnergy(torch.autograd.Function):
     def forward(ctx, w, scale):
         ctx.save_for_backward(w)
         ctx.scale = scale
+        if (w.is_cuda or lib_emulated()) and w.dtype == torch.float32 and w.is_contiguous() \
+                and os.environ.get("TE_WEIGHT_ENERGY", "1") != "0":
+            from . import lib
+            o, i, kh, kw = w.shape
+            energy = torch.empty((o, i), dtype=torch.float32, device=w.device)
+            lib.weight_energy(energy, w.detach(), o * i, kh * kw, scale * scale)   # one row of taps per thread
+            return energy
         # ||W[o,i,:]||^2 * scale^2 with ONE pass over the weight (the literal mul / square / sum chain is three)
         return torch.linalg.vector_norm(w, dim=(2, 3)).square_().mul_(scale * scale)
 
     @staticmethod
     def backward(ctx, g):
         (w,) = ctx.saved_tensors
-        return w * (g * (2.0 * ctx.scale * ctx.scale))[:, :, None, None], None
+        if not torch.is_grad_enabled() and (w.is_cuda or lib_emulated()) and w.dtype == torch.float32 \
+                and w.is_contiguous() and g.dtype == torch.float32 and os.environ.get("TE_WEIGHT_ENERGY", "1") != "0":
+            from . import lib
+            o, i, kh, kw = w.shape
+            gw = torch.empty_like(w)
+            lib.weight_energy_bwd(gw, w.detach(), g.contiguous(), o * i, kh * kw, 2.0 * ctx.scale * ctx.scale)
+            return gw, None
+        return w * (g * (2.0 * ctx.scale * ctx.scale))[:, :, None, None], None   # differentiable form (create_graph)
 
 
 class ModulatedConv2d(nn.Module):
