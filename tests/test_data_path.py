@@ -110,3 +110,45 @@ def test_gpu_full_size_round_trip_and_edges():
     got = pipe.load(u8.cpu().pin_memory(), fl.cpu().pin_memory())
     torch.cuda.synchronize()
     assert torch.equal(got, x)
+
+
+def test_uint8_dataset_reads_the_reference_lmdb_layout(monkeypatch):
+    """Uint8Dataset mirrors utils/dataset.py:9-45: keys `{resolution}-{index:05d}`, `length`, decode with PIL, and a
+    corrupt record falls through to another index — checked against an in-memory stand-in for the lmdb module."""
+    import io
+    import sys
+    import types
+    from PIL import Image
+    imgs = [GOLD["prep_a_u8"][i] for i in range(3)]
+    store = {b"length": b"3"}
+    for i, im in enumerate(imgs):
+        buf = io.BytesIO()
+        Image.fromarray(im).save(buf, format="png")
+        store[("16-%05d" % i).encode()] = buf.getvalue()
+    store[b"16-00001"] = b"not an image"
+
+    class Txn:
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+        def get(self, key):
+            return store.get(key)
+
+    class Env:
+        def begin(self, write=False):
+            return Txn()
+
+    fake = types.ModuleType("lmdb")
+    fake.open = lambda path, **kw: Env()
+    monkeypatch.setitem(sys.modules, "lmdb", fake)
+    from transeditor_b200 import data
+    ds = data.Uint8Dataset("ignored", resolution=16)
+    assert len(ds) == 3
+    assert np.array_equal(ds[0].numpy(), imgs[0]) and np.array_equal(ds[2].numpy(), imgs[2])
+    import random
+    random.seed(0)
+    got = ds[1].numpy()          # corrupt record: retried at a random index, like the reference
+    assert any(np.array_equal(got, im) for im in (imgs[0], imgs[2]))
